@@ -1,0 +1,98 @@
+"""ctypes binding of libtik.so (include/tik.h).  No fallback: a missing library is an error."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtik.so")
+
+TIK_F32, TIK_BF16 = 0, 1
+MAX_BLOCKS, MAX_SLABS, MAX_JOINTS = 16, 6, 32
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+RES_NONE, RES_IDENTITY, RES_STEM, RES_CONV = 0, 1, 2, 3
+OUT_NODE_MAJOR, OUT_TIME_MAJOR, OUT_ROWS_F32 = 0, 1, 2
+
+vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class TikSlab(C.Structure):
+    _fields_ = [("a_dev", vp), ("c", i32), ("t_in", i32), ("t_mul", i32), ("t_off", i32)]
+
+
+class TikRowGemm(C.Structure):
+    _fields_ = [("n_slabs", i32), ("slabs", TikSlab * MAX_SLABS), ("w_dev", vp), ("bias_dev", vp),
+                ("bias_per_node", i32), ("nv", i64), ("v", i32), ("t_out", i32), ("c_out", i32),
+                ("c_out_valid", i32), ("act", i32), ("slope", f32), ("res_kind", i32), ("res_dev", vp),
+                ("res_w_dev", vp), ("res_cin", i32), ("res_t_mul", i32), ("res_t_in", i32), ("out_dev", vp),
+                ("out_layout", i32)]
+
+
+class TikBlock(C.Structure):
+    _fields_ = [("c_in", i32), ("c_out", i32), ("stride", i32), ("kt", i32), ("res_kind", i32),
+                ("agg_dev", vp), ("w_gcn_dev", vp), ("b_gcn_dev", vp), ("w_tcn_dev", vp), ("b_tcn_dev", vp),
+                ("w_res_stem_dev", vp)]
+
+
+class TikNet(C.Structure):
+    _fields_ = [("V", i32), ("K", i32), ("c_in", i32), ("n_blocks", i32), ("in_scale_dev", vp),
+                ("in_shift_dev", vp), ("blocks", TikBlock * MAX_BLOCKS), ("head_hidden", i32), ("head_out", i32),
+                ("w1_dev", vp), ("b1_dev", vp), ("w2_dev", vp), ("b2_dev", vp), ("leaky_slope", f32)]
+
+
+_PROTOS = {
+    "tik_version": (C.c_int, []),
+    "tik_last_error": (C.c_char_p, []),
+    "tik_check_device": (C.c_int, []),
+    "tik_rot6d_to_rotmat": (C.c_int, [vp, vp, i64, vp]),
+    "tik_aa_to_rotmat": (C.c_int, [vp, vp, i64, vp]),
+    "tik_batch_rodrigues": (C.c_int, [vp, vp, i64, vp]),
+    "tik_rotmat_to_aa": (C.c_int, [vp, vp, i64, C.c_int, vp]),
+    "tik_fk_body": (C.c_int, [vp, C.c_int, C.POINTER(f32), C.POINTER(i32), C.c_int, vp, vp, vp, vp, i64, vp]),
+    "tik_stem_gcn": (C.c_int, [C.c_int, vp, vp, vp, vp, vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_int, C.c_int, vp]),
+    "tik_aggregate": (C.c_int, [C.c_int, vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "tik_rowgemm": (C.c_int, [C.c_int, C.POINTER(TikRowGemm), vp]),
+    "tik_stgcn_out_frames": (C.c_int, [C.POINTER(TikNet), C.c_int]),
+    "tik_stgcn_workspace_bytes": (C.c_int, [C.POINTER(TikNet), C.c_int, i64, C.c_int, C.POINTER(i64)]),
+    "tik_stgcn_plan_create": (C.c_int, [C.POINTER(TikNet), C.c_int, i64, C.c_int, vp, i64, C.POINTER(vp)]),
+    "tik_stgcn_plan_run": (C.c_int, [vp, vp, i64, vp, vp, vp]),
+    "tik_stgcn_plan_launches": (i64, [vp, i64]),
+    "tik_stgcn_plan_destroy": (None, [vp]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Names declared in include/tik.h (used by the CPU-side ABI test)."""
+    return sorted(_PROTOS)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m temporal_inverse_kinematics_b200.build` "
+                "(there is no CPU or PyTorch fallback for the CUDA path)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().tik_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libtik error {rc}: {msg}")
+
+
+def ptr(t):
+    """Device (or host) address of a tensor, or None."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

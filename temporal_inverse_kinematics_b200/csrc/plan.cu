@@ -1,0 +1,311 @@
+// Whole-network launch plan: PoseRegressor.forward (pose_trainer.py:94-133) =
+// StgGcn18 backbone (st_gcn_aaai18.py:113-133) + Linear/LeakyReLU/Linear head, as a fixed sequence of
+// kernels over caller-owned workspace.  Clips are processed n_chunk at a time so that the per-layer
+// activations of a chunk stay resident in the 126 MB L2 between producer and consumer kernels.
+#include <string.h>
+
+#include <vector>
+
+#include "tik_common.cuh"
+#include "umma_prepared.h"
+
+namespace tik {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int out_frames(int t, int stride) { return (t - 1) / stride + 1; }
+
+struct Step {
+  enum Kind { STEM, AGG, GEMM } kind;
+  TikRowGemm g;              // GEMM
+  UmmaPrepared* prep = nullptr;
+  // STEM / AGG arguments
+  const void* src = nullptr; void* dst = nullptr;
+  int t = 0, c = 0, cout = 0;
+  const TikBlock* blk = nullptr;
+  bool src_is_input = false;  // GEMM: residual comes from the user's input pointer (stem residual)
+  bool dst_is_output = false; // GEMM: writes the user's poses pointer
+};
+
+}  // namespace tik
+
+struct TikPlan {
+  TikNet net;
+  int dtype;
+  int64_t n_chunk;
+  int T, T_out;
+  size_t es;                 // element size of activations
+  std::vector<tik::Step> steps;
+  void* feat = nullptr;      // backbone output of the current chunk, (n, T', V*C_last)
+  int64_t feat_elems_per_clip = 0;
+  int c_last = 0;
+  ~TikPlan() {
+    for (auto& s : steps)
+      if (s.prep) tik::umma_free(s.prep);
+  }
+};
+
+namespace tik {
+
+struct WsLayout {
+  int64_t x_elems, agg_elems, h_elems, z_elems;   // per clip
+  int64_t off_x0, off_x1, off_agg, off_h, off_z, total_bytes;
+};
+
+static int check_net(const TikNet* net, int dtype) {
+  TIK_CHECK_ARG(net != nullptr, "null net");
+  TIK_CHECK_ARG(dtype == TIK_F32 || dtype == TIK_BF16, "bad dtype %d", dtype);
+  TIK_CHECK_ARG(net->n_blocks >= 1 && net->n_blocks <= TIK_MAX_BLOCKS, "n_blocks=%d", net->n_blocks);
+  TIK_CHECK_ARG(net->V >= 1 && net->V <= 32 && net->K >= 1 && net->K <= 5, "V=%d K=%d unsupported", net->V, net->K);
+  TIK_CHECK_ARG(net->c_in >= 1 && net->c_in * net->K <= 40, "stem needs K*c_in <= 40 (got c_in=%d K=%d)", net->c_in, net->K);
+  TIK_CHECK_ARG(net->blocks[0].c_in == net->c_in, "block 0 c_in mismatch");
+  const int cmul = dtype == TIK_BF16 ? 64 : 4;
+  for (int i = 0; i < net->n_blocks; ++i) {
+    const TikBlock& b = net->blocks[i];
+    TIK_CHECK_ARG(b.kt >= 1 && (b.kt % 2) == 1 && b.kt + 1 <= TIK_MAX_SLABS, "block %d: temporal kernel %d unsupported", i, b.kt);
+    TIK_CHECK_ARG(b.stride >= 1 && b.stride <= 8, "block %d: stride %d", i, b.stride);
+    TIK_CHECK_ARG(b.c_out % cmul == 0, "block %d: c_out=%d must be a multiple of %d for this dtype", i, b.c_out, cmul);
+    if (i > 0) {
+      TIK_CHECK_ARG(b.c_in == net->blocks[i - 1].c_out, "block %d: c_in does not chain", i);
+      TIK_CHECK_ARG(net->K <= TIK_MAX_SLABS, "K");
+      TIK_CHECK_ARG(b.res_kind == TIK_RES_NONE || b.res_kind == TIK_RES_IDENTITY || b.res_kind == TIK_RES_CONV, "block %d: res_kind", i);
+    } else {
+      TIK_CHECK_ARG(b.res_kind == TIK_RES_NONE || b.res_kind == TIK_RES_STEM, "block 0: residual must be none or stem-conv");
+      TIK_CHECK_ARG(b.res_kind != TIK_RES_STEM || (b.c_in <= 8 && b.w_res_stem_dev), "block 0: stem residual needs c_in <= 8");
+    }
+    TIK_CHECK_ARG(b.agg_dev && b.w_gcn_dev && b.b_gcn_dev && b.w_tcn_dev && b.b_tcn_dev, "block %d: null weight pointer", i);
+  }
+  if (net->head_hidden > 0) {
+    TIK_CHECK_ARG(net->w1_dev && net->b1_dev && net->w2_dev && net->b2_dev && net->head_out > 0, "head pointers");
+    TIK_CHECK_ARG(net->head_hidden % cmul == 0, "head hidden=%d must be a multiple of %d", net->head_hidden, cmul);
+  }
+  return TIK_OK;
+}
+
+static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+static void ws_layout(const TikNet* net, int dtype, int64_t n, int T, WsLayout* L, int* t_out_final) {
+  const int64_t V = net->V;
+  int t = T;
+  int64_t x = 0, a = 0, h = 0;
+  for (int i = 0; i < net->n_blocks; ++i) {
+    const TikBlock& b = net->blocks[i];
+    if (i > 0) {
+      x = std::max<int64_t>(x, V * t * b.c_in);
+      a = std::max<int64_t>(a, (int64_t)net->K * V * t * b.c_in);
+    }
+    h = std::max<int64_t>(h, V * t * b.c_out);
+    t = out_frames(t, b.stride);
+    x = std::max<int64_t>(x, V * t * b.c_out);
+  }
+  *t_out_final = t;
+  L->x_elems = x; L->agg_elems = a; L->h_elems = h;
+  L->z_elems = net->head_hidden > 0 ? (int64_t)t * net->head_hidden : 0;
+  const int64_t es = dtype == TIK_BF16 ? 2 : 4;
+  int64_t off = 0;
+  L->off_x0 = off; off = align_up(off + x * n * es, 1024);
+  L->off_x1 = off; off = align_up(off + x * n * es, 1024);
+  L->off_agg = off; off = align_up(off + a * n * es, 1024);
+  L->off_h = off; off = align_up(off + h * n * es, 1024);
+  L->off_z = off; off = align_up(off + L->z_elems * n * es, 1024);
+  L->total_bytes = off;
+}
+
+}  // namespace tik
+
+extern "C" {
+
+int tik_version(void) { return 100; }
+const char* tik_last_error(void) { return tik::g_err; }
+
+int tik_check_device(void) {
+  using namespace tik;
+  int dev = 0;
+  TIK_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  TIK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("libtik.so is built for sm_100a only; device %d has compute capability major %d", dev, major);
+    return TIK_ERR_UNSUPPORTED;
+  }
+  return TIK_OK;
+}
+
+int tik_stgcn_out_frames(const TikNet* net, int T) {
+  if (!net || T < 1) return -1;
+  int t = T;
+  for (int i = 0; i < net->n_blocks; ++i) t = tik::out_frames(t, net->blocks[i].stride);
+  return t;
+}
+
+int tik_stgcn_workspace_bytes(const TikNet* net, int dtype, int64_t n_chunk, int T, int64_t* bytes) {
+  using namespace tik;
+  int rc = check_net(net, dtype);
+  if (rc != TIK_OK) return rc;
+  TIK_CHECK_ARG(n_chunk >= 1 && T >= 1 && bytes, "bad arguments");
+  WsLayout L;
+  int tf;
+  ws_layout(net, dtype, n_chunk, T, &L, &tf);
+  *bytes = L.total_bytes;
+  return TIK_OK;
+}
+
+int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int T, void* workspace, int64_t ws_bytes,
+                          TikPlan** plan_out) {
+  using namespace tik;
+  int rc = check_net(net, dtype);
+  if (rc != TIK_OK) return rc;
+  TIK_CHECK_ARG(n_chunk >= 1 && T >= 1 && plan_out, "bad arguments");
+  WsLayout L;
+  int tf;
+  ws_layout(net, dtype, n_chunk, T, &L, &tf);
+  if (!workspace || ws_bytes < L.total_bytes) {
+    set_error("workspace of %lld bytes is smaller than the %lld bytes this plan needs", (long long)ws_bytes, (long long)L.total_bytes);
+    return TIK_ERR_WORKSPACE;
+  }
+  TIK_CHECK_ARG(((uintptr_t)workspace & 1023) == 0, "workspace must be 1024-byte aligned");
+  TikPlan* P = new TikPlan();
+  P->net = *net; P->dtype = dtype; P->n_chunk = n_chunk; P->T = T; P->T_out = tf;
+  P->es = dtype == TIK_BF16 ? 2 : 4;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  void* xbuf[2] = {ws + L.off_x0, ws + L.off_x1};
+  void* agg = ws + L.off_agg;
+  void* hbuf = ws + L.off_h;
+  void* zbuf = ws + L.off_z;
+  const int V = net->V, K = net->K;
+  const int64_t nv = n_chunk * V;
+  int t = T;
+  int cur = 0;   // xbuf[cur] holds the input of the next block (from block 1 on)
+  for (int i = 0; i < net->n_blocks; ++i) {
+    const TikBlock& b = P->net.blocks[i];
+    const int pad = (b.kt - 1) / 2;
+    const int t_o = out_frames(t, b.stride);
+    const bool last = i == net->n_blocks - 1;
+    if (i == 0) {
+      Step s; s.kind = Step::STEM; s.dst = hbuf; s.t = t; s.blk = &b;
+      P->steps.push_back(s);
+    } else {
+      Step s; s.kind = Step::AGG; s.src = xbuf[cur]; s.dst = agg; s.t = t; s.c = b.c_in; s.blk = &b;
+      P->steps.push_back(s);
+      Step g; g.kind = Step::GEMM; memset(&g.g, 0, sizeof(g.g));
+      g.g.n_slabs = K;
+      for (int k = 0; k < K; ++k)
+        g.g.slabs[k] = {reinterpret_cast<uint8_t*>(agg) + (int64_t)k * nv * t * b.c_in * P->es, b.c_in, t, 1, 0};
+      g.g.w_dev = b.w_gcn_dev; g.g.bias_dev = b.b_gcn_dev; g.g.bias_per_node = 1;
+      g.g.nv = nv; g.g.v = V; g.g.t_out = t; g.g.c_out = b.c_out; g.g.c_out_valid = b.c_out;
+      g.g.act = TIK_ACT_RELU; g.g.res_kind = TIK_RES_NONE;
+      g.g.out_dev = hbuf; g.g.out_layout = TIK_OUT_NODE_MAJOR;
+      P->steps.push_back(g);
+    }
+    Step c; c.kind = Step::GEMM; memset(&c.g, 0, sizeof(c.g));
+    int ns = 0;
+    for (int dt = 0; dt < b.kt; ++dt) c.g.slabs[ns++] = {hbuf, b.c_out, t, b.stride, dt - pad};
+    if (b.res_kind == TIK_RES_CONV) c.g.slabs[ns++] = {xbuf[cur], b.c_in, t, b.stride, 0};
+    c.g.n_slabs = ns;
+    c.g.w_dev = b.w_tcn_dev; c.g.bias_dev = b.b_tcn_dev; c.g.bias_per_node = (b.res_kind == TIK_RES_STEM) ? 1 : 0;
+    c.g.nv = nv; c.g.v = V; c.g.t_out = t_o; c.g.c_out = b.c_out; c.g.c_out_valid = b.c_out;
+    c.g.act = TIK_ACT_RELU;
+    if (b.res_kind == TIK_RES_IDENTITY) { c.g.res_kind = TIK_RES_IDENTITY; c.g.res_dev = xbuf[cur]; }
+    else if (b.res_kind == TIK_RES_STEM) {
+      c.g.res_kind = TIK_RES_STEM; c.g.res_dev = nullptr; c.src_is_input = true;
+      c.g.res_w_dev = b.w_res_stem_dev; c.g.res_cin = b.c_in; c.g.res_t_mul = b.stride; c.g.res_t_in = t;
+    } else c.g.res_kind = TIK_RES_NONE;
+    const int nxt = (i == 0) ? 0 : cur ^ 1;
+    c.g.out_dev = xbuf[nxt];
+    c.g.out_layout = last ? TIK_OUT_TIME_MAJOR : TIK_OUT_NODE_MAJOR;
+    P->steps.push_back(c);
+    cur = nxt;
+    t = t_o;
+    if (last) { P->feat = xbuf[nxt]; P->c_last = b.c_out; }
+  }
+  P->feat_elems_per_clip = (int64_t)tf * V * P->c_last;
+  if (net->head_hidden > 0) {
+    const int feat_c = V * P->c_last;
+    Step h1; h1.kind = Step::GEMM; memset(&h1.g, 0, sizeof(h1.g));
+    h1.g.n_slabs = 1;
+    h1.g.slabs[0] = {P->feat, feat_c, (int32_t)(n_chunk * tf), 1, 0};
+    h1.g.w_dev = net->w1_dev; h1.g.bias_dev = net->b1_dev; h1.g.bias_per_node = 0;
+    h1.g.nv = 1; h1.g.v = 1; h1.g.t_out = (int32_t)(n_chunk * tf); h1.g.c_out = net->head_hidden; h1.g.c_out_valid = net->head_hidden;
+    h1.g.act = TIK_ACT_LEAKY; h1.g.slope = net->leaky_slope; h1.g.res_kind = TIK_RES_NONE;
+    h1.g.out_dev = zbuf; h1.g.out_layout = TIK_OUT_NODE_MAJOR;
+    P->steps.push_back(h1);
+    Step h2; h2.kind = Step::GEMM; memset(&h2.g, 0, sizeof(h2.g));
+    h2.g.n_slabs = 1;
+    h2.g.slabs[0] = {zbuf, net->head_hidden, (int32_t)(n_chunk * tf), 1, 0};
+    h2.g.w_dev = net->w2_dev; h2.g.bias_dev = net->b2_dev; h2.g.bias_per_node = 0;
+    h2.g.nv = 1; h2.g.v = 1; h2.g.t_out = (int32_t)(n_chunk * tf);
+    h2.g.c_out = dtype == TIK_BF16 ? (int)align_up(net->head_out, 64) : net->head_out;
+    h2.g.c_out_valid = net->head_out;
+    h2.g.act = TIK_ACT_NONE; h2.g.res_kind = TIK_RES_NONE;
+    h2.g.out_dev = nullptr; h2.dst_is_output = true; h2.g.out_layout = TIK_OUT_ROWS_F32;
+    P->steps.push_back(h2);
+  }
+  if (dtype == TIK_BF16) {
+    for (auto& s : P->steps) {
+      if (s.kind != Step::GEMM) continue;
+      int rc2 = umma_prepare(&s.g, s.g.nv, &s.prep);
+      if (rc2 != TIK_OK) { delete P; return rc2; }
+    }
+  }
+  *plan_out = P;
+  return TIK_OK;
+}
+
+int tik_stgcn_plan_run(TikPlan* P, const float* x, int64_t N, float* poses, void* feat_out, void* stream) {
+  using namespace tik;
+  TIK_CHECK_ARG(P && x && N >= 0, "bad arguments");
+  TIK_CHECK_ARG(P->net.head_hidden == 0 || poses, "poses pointer required");
+  cudaStream_t s = (cudaStream_t)stream;
+  const TikNet& net = P->net;
+  const int V = net.V, T = P->T;
+  for (int64_t n0 = 0; n0 < N; n0 += P->n_chunk) {
+    const int64_t n = std::min<int64_t>(P->n_chunk, N - n0);
+    const float* xc = x + n0 * (int64_t)T * V * net.c_in;
+    for (auto& st : P->steps) {
+      int rc = TIK_OK;
+      if (st.kind == Step::STEM) {
+        const TikBlock& b = *st.blk;
+        rc = tik_stem_gcn(P->dtype, xc, net.in_scale_dev, net.in_shift_dev, b.agg_dev, reinterpret_cast<const float*>(b.w_gcn_dev),
+                          b.b_gcn_dev, st.dst, n, st.t, V, b.c_in, net.K, b.c_out, 1, s);
+      } else if (st.kind == Step::AGG) {
+        // planes are spaced for the full chunk (tensor maps are baked for n_chunk), so aggregate the full
+        // chunk capacity only when it is full; a partial last chunk still uses the chunk-capacity plane stride.
+        rc = tik_aggregate(P->dtype, st.src, st.blk->agg_dev, st.dst, P->n_chunk, st.t, V, st.c, net.K, s);
+      } else {
+        TikRowGemm g = st.g;
+        if (g.v == 1) {           // head: rows = n * T'
+          g.t_out = (int32_t)(n * P->T_out);
+          g.slabs[0].t_in = g.t_out;
+        } else {
+          g.nv = n * V;
+        }
+        if (st.src_is_input) g.res_dev = xc;
+        if (st.dst_is_output) g.out_dev = poses + n0 * (int64_t)P->T_out * net.head_out;
+        rc = P->dtype == TIK_BF16 ? umma_launch(st.prep, &g, s) : rowgemm_f32(&g, s);
+      }
+      if (rc != TIK_OK) return rc;
+    }
+    if (feat_out) {
+      TIK_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(feat_out) + n0 * P->feat_elems_per_clip * P->es, P->feat,
+                               (size_t)(n * P->feat_elems_per_clip) * P->es, cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  return TIK_OK;
+}
+
+int64_t tik_stgcn_plan_launches(const TikPlan* P, int64_t N) {
+  if (!P || N <= 0) return 0;
+  int64_t chunks = (N + P->n_chunk - 1) / P->n_chunk;
+  return chunks * (int64_t)P->steps.size();
+}
+
+void tik_stgcn_plan_destroy(TikPlan* P) { delete P; }
+
+}  // extern "C"

@@ -1,0 +1,242 @@
+"""Host side of the CUDA path: eval-mode folding of the reference parameters into packed
+weights and cached launch plans over libtik.so.
+
+The packed algebra, for one ST-GCN block with A^ = A * edge_importance (st_gcn_aaai18.py:128-129),
+BN folded as s = gamma / sqrt(var + eps), o = beta - mean * s:
+
+  gcn   H[n,w,t,c] = relu( sum_{k,ci} s1[c] Wg[k*Cout+c,ci] * (sum_v A^[k,v,w] X[n,v,t,ci])
+                           + s1[c] * sum_k bg[k*Cout+c] * colsum_k[w] + o1[c] )        (gconv_origin.py:59-63)
+  tcn   Y[n,w,t',c] = relu( sum_{dt,c'} s2[c] Wt[c,c',dt] H[n,w,s*t'+dt-pad,c'] + s2[c] bt[c] + o2[c] + R )
+  res   R = X (identity) | sum_ci s3[c] Wr[c,ci] X[n,w,s*t',ci] + s3[c] br[c] + o3[c]   (st_gcn_aaai18.py:191-214)
+
+There is no CPU or eager-PyTorch fallback: anything but eval-mode CUDA tensors raises.
+"""
+import ctypes as C
+import weakref
+
+import torch
+
+from . import _lib as L
+
+BN_EPS_DEFAULT = 1e-5
+_DTYPES = {"fp32": (L.TIK_F32, torch.float32), "bf16": (L.TIK_BF16, torch.bfloat16)}
+
+
+def resolve_dtype(name):
+    if name not in _DTYPES:
+        raise ValueError(f"compute dtype must be 'fp32' or 'bf16', got {name!r}")
+    return _DTYPES[name]
+
+
+def _bn_fold(bn):
+    """(scale, shift) of an eval-mode BatchNorm, float64."""
+    var = bn.running_var.detach().double()
+    mean = bn.running_mean.detach().double()
+    g = bn.weight.detach().double() if bn.weight is not None else torch.ones_like(var)
+    b = bn.bias.detach().double() if bn.bias is not None else torch.zeros_like(var)
+    s = g / torch.sqrt(var + bn.eps)
+    return s, b - mean * s
+
+
+def fold_gcn(conv_weight, conv_bias, A_hat, K, bn=None):
+    """-> w (Cout, K*Cin) f64, bias table (V, Cout) f64 for the aggregate-first graph convolution."""
+    KC, cin = conv_weight.shape[0], conv_weight.shape[1]
+    cout = KC // K
+    W = conv_weight.detach().double().reshape(K, cout, cin)               # out-channel index k*Cout+c
+    bg = conv_bias.detach().double().reshape(K, cout) if conv_bias is not None else torch.zeros(K, cout, dtype=torch.float64, device=W.device)
+    colsum = A_hat.detach().double().sum(dim=1)                           # (K, V): sum over v of A^[k,v,w]
+    w = W.permute(1, 0, 2).reshape(cout, K * cin)
+    b = torch.einsum("kc,kw->wc", bg, colsum)
+    if bn is not None:
+        s, o = _bn_fold(bn)
+        w = w * s[:, None]
+        b = b * s[None, :] + o[None, :]
+    return w, b
+
+
+def fold_tcn(conv, bn, res_conv=None, res_bn=None):
+    """-> w (Cout, kt*Cout [+Cin]) f64, bias (Cout) f64 for temporal conv + BN (+ residual 1x1 conv + BN)."""
+    Wt = conv.weight.detach().double()[..., 0]                            # (Cout, Cout, kt)
+    cout, _, kt = Wt.shape
+    s2, o2 = _bn_fold(bn)
+    bt = conv.bias.detach().double() if conv.bias is not None else torch.zeros(cout, dtype=torch.float64, device=Wt.device)
+    w = (Wt.permute(0, 2, 1) * s2[:, None, None]).reshape(cout, kt * cout)   # column dt*Cout + c'
+    b = s2 * bt + o2
+    wr = None
+    if res_conv is not None:
+        s3, o3 = _bn_fold(res_bn)
+        Wr = res_conv.weight.detach().double()[:, :, 0, 0]               # (Cout, Cin)
+        br = res_conv.bias.detach().double() if res_conv.bias is not None else torch.zeros(cout, dtype=torch.float64, device=Wt.device)
+        wr = Wr * s3[:, None]
+        b = b + s3 * br + o3
+    return w, b, wr
+
+
+class PackedNet:
+    """Device-resident packed weights + the TikNet descriptor that points at them."""
+
+    def __init__(self, backbone, head, dtype_name):
+        self.dtype_name = dtype_name
+        self.code, self.tdtype = resolve_dtype(dtype_name)
+        dev = backbone.A.device
+        self.device = dev
+        self.keep = []                                                    # tensors referenced by raw pointer
+        self.named = {}                                                   # same tensors by name (introspection/tests)
+        net = L.TikNet()
+        A = backbone.A.detach()
+        K, V = A.shape[0], A.shape[1]
+        blocks = list(backbone.st_gcn_networks)
+        if len(blocks) > L.MAX_BLOCKS:
+            raise ValueError(f"at most {L.MAX_BLOCKS} ST-GCN blocks are supported")
+        cin0 = blocks[0].in_channels
+        net.V, net.K, net.c_in, net.n_blocks = V, K, cin0, len(blocks)
+        if isinstance(backbone.data_bn, torch.nn.BatchNorm1d):
+            s0, o0 = _bn_fold(backbone.data_bn)                           # channel index v*C + c
+        else:
+            s0 = torch.ones(V * cin0, dtype=torch.float64, device=dev)
+            o0 = torch.zeros(V * cin0, dtype=torch.float64, device=dev)
+        net.in_scale_dev = self._f32(s0, "in_scale")
+        net.in_shift_dev = self._f32(o0, "in_shift")
+        for i, blk in enumerate(blocks):
+            imp = backbone.edge_importance[i]
+            A_hat = A * imp.detach() if torch.is_tensor(imp) else A * imp
+            b = net.blocks[i]
+            b.c_in, b.c_out, b.stride, b.kt = blk.in_channels, blk.out_channels, blk.stride, blk.temporal_kernel
+            wg, bg = fold_gcn(blk.gcn.conv.weight, blk.gcn.conv.bias, A_hat, K, blk.tcn[0])
+            b.agg_dev = self._f32(A_hat.double(), f"b{i}.agg")
+            # the stem kernel computes in fp32
+            b.w_gcn_dev = self._f32(wg, f"b{i}.w_gcn") if i == 0 else self._act(wg, f"b{i}.w_gcn")
+            b.b_gcn_dev = self._f32(bg, f"b{i}.b_gcn")
+            res_conv = res_bn = None
+            if blk.residual_kind == "conv":
+                res_conv, res_bn = blk.residual[0], blk.residual[1]
+            wt, bt, wr = fold_tcn(blk.tcn[2], blk.tcn[3], res_conv, res_bn)
+            if blk.residual_kind == "none":
+                b.res_kind = L.RES_NONE
+            elif blk.residual_kind == "identity":
+                if i == 0:
+                    raise NotImplementedError("an identity residual on the first block is not supported by the CUDA path")
+                b.res_kind = L.RES_IDENTITY
+            elif i == 0:
+                if cin0 > 8:
+                    raise NotImplementedError("first-block residual convolution needs in_channels <= 8")
+                b.res_kind = L.RES_STEM
+                s0v, o0v = s0.view(V, cin0), o0.view(V, cin0)
+                b.w_res_stem_dev = self._f32(wr[None, :, :] * s0v[:, None, :], f"b{i}.w_res_stem")  # (V, Cout, Cin)
+                bt = bt[None, :] + torch.einsum("ci,vi->vc", wr, o0v)                    # (V, Cout)
+            else:
+                b.res_kind = L.RES_CONV
+                wt = torch.cat([wt, wr], dim=1)
+            b.w_tcn_dev = self._act(wt, f"b{i}.w_tcn")
+            b.b_tcn_dev = self._f32(bt, f"b{i}.b_tcn")
+        self.c_last = blocks[-1].out_channels
+        if head is not None:
+            lin1, slope, lin2 = head
+            net.head_hidden, net.head_out = lin1.out_features, lin2.out_features
+            net.leaky_slope = float(slope)
+            net.w1_dev = self._act(lin1.weight.detach().double(), "w1")
+            net.b1_dev = self._f32(lin1.bias.detach().double(), "b1")
+            w2, b2 = lin2.weight.detach().double(), lin2.bias.detach().double()
+            if self.code == L.TIK_BF16:                                    # pad rows to the 64-column MMA granule
+                rows = (w2.shape[0] + 63) // 64 * 64
+                w2 = torch.cat([w2, w2.new_zeros(rows - w2.shape[0], w2.shape[1])])
+                b2 = torch.cat([b2, b2.new_zeros(rows - b2.shape[0])])
+            net.w2_dev = self._act(w2, "w2")
+            net.b2_dev = self._f32(b2, "b2")
+            self.head_out = lin2.out_features
+        else:
+            net.head_hidden = net.head_out = 0
+            self.head_out = 0
+        self.net = net
+        self.V, self.K, self.c_in = V, K, cin0
+
+    def _f32(self, t, name):
+        t = t.to(torch.float32).contiguous()
+        self.keep.append(t)
+        self.named[name] = t
+        return t.data_ptr()
+
+    def _act(self, t, name):
+        t = t.to(self.tdtype).contiguous()
+        self.keep.append(t)
+        self.named[name] = t
+        return t.data_ptr()
+
+
+class Plan:
+    def __init__(self, packed, n_chunk, T):
+        lib = L.lib()
+        self.packed = packed
+        self.n_chunk, self.T = n_chunk, T
+        nbytes = L.i64(0)
+        L.check(lib.tik_stgcn_workspace_bytes(C.byref(packed.net), packed.code, n_chunk, T, C.byref(nbytes)))
+        self.workspace = torch.empty(nbytes.value + 1024, dtype=torch.uint8, device=packed.device)
+        base = (self.workspace.data_ptr() + 1023) // 1024 * 1024
+        handle = L.vp()
+        L.check(lib.tik_stgcn_plan_create(C.byref(packed.net), packed.code, n_chunk, T, C.c_void_p(base), nbytes.value,
+                                          C.byref(handle)))
+        self.handle = handle
+        self.T_out = lib.tik_stgcn_out_frames(C.byref(packed.net), T)
+        self.workspace_bytes = nbytes.value
+        self._fin = weakref.finalize(self, lib.tik_stgcn_plan_destroy, handle)
+
+    def launches(self, N):
+        return int(L.lib().tik_stgcn_plan_launches(self.handle, N))
+
+    def run(self, x, want_feat=False):
+        p = self.packed
+        N = x.shape[0]
+        poses = torch.empty((N, self.T_out, p.head_out), dtype=torch.float32, device=x.device) if p.head_out else None
+        feat = torch.empty((N, self.T_out, p.V * p.c_last), dtype=p.tdtype, device=x.device) if want_feat else None
+        L.check(L.lib().tik_stgcn_plan_run(self.handle, L.ptr(x), N, L.ptr(poses), L.ptr(feat), L.stream_ptr(x.device)))
+        return poses, feat
+
+
+def default_chunk(T):
+    """Clips per chunk: about 8K frames (~140K activation rows), so a chunk's widest layer (bf16) is ~36 MB
+    and producer->consumer traffic stays in the 126 MB L2."""
+    return max(1, 8192 // max(T, 1))
+
+
+class Engine:
+    """Per-model cache of packed weights and plans, invalidated when any parameter/buffer changes."""
+
+    def __init__(self, backbone, head_fn=None):
+        self._backbone = weakref.ref(backbone)
+        self._head_fn = head_fn
+        self._packed = {}
+        self._plans = {}
+        self._stamp = None
+
+    def _stamp_now(self, backbone, extra):
+        ts = list(backbone.parameters()) + list(backbone.buffers()) + extra
+        return tuple((t.data_ptr(), t._version, t.device.index) for t in ts)
+
+    def plan(self, dtype_name, N, T, chunk=None):
+        backbone = self._backbone()
+        head = self._head_fn() if self._head_fn else None
+        extra = [] if head is None else [head[0].weight, head[0].bias, head[2].weight, head[2].bias]
+        stamp = self._stamp_now(backbone, extra)
+        if stamp != self._stamp:
+            self._packed.clear()
+            self._plans.clear()
+            self._stamp = stamp
+        if dtype_name not in self._packed:
+            self._packed[dtype_name] = PackedNet(backbone, head, dtype_name)
+        n_chunk = int(chunk) if chunk else default_chunk(T)
+        n_chunk = max(1, min(n_chunk, N))
+        key = (dtype_name, n_chunk, T)
+        if key not in self._plans:
+            self._plans[key] = Plan(self._packed[dtype_name], n_chunk, T)
+        return self._plans[key]
+
+
+def require_cuda_eval(module, x, what):
+    if module.training:
+        raise NotImplementedError(
+            f"{what}: the CUDA path implements eval-mode inference only (BatchNorm is folded); call .eval()")
+    if not torch.is_tensor(x):
+        raise TypeError(f"{what}: expected a torch.Tensor, got {type(x)}")
+    if not x.is_cuda:
+        raise RuntimeError(f"{what}: input must be a CUDA tensor -- there is no CPU fallback")
+    L.check(L.lib().tik_check_device())

@@ -1,0 +1,95 @@
+"""PoseRegressor / IKPoseTrainer with the reference's API on top of the CUDA engine.
+
+Mirrors reference pose_trainer.py:66-133 (PoseRegressor) and :136-144 (IKPoseTrainer.forward and the
+``regressor.`` state_dict prefix used by Lightning checkpoints, inference.py:136).  Training
+(pose_trainer.py:146-260) is out of scope: the CUDA path is eval-only.
+"""
+import argparse
+
+import torch
+import torch.nn as nn
+
+from . import engine
+from .st_gcn import StgConfig, StgGcn18, StgLayerConfig, _ComputeDtypeMixin, _default_dtype
+
+# (in_channels, out_channels, temporal_stride) of the eight blocks; the first in_channels is hparams.kps_channel
+_BLOCKS = [(None, 64, 1), (64, 64, 1), (64, 128, 2), (128, 128, 1), (128, 128, 1), (128, 128, 2), (128, 256, 2),
+           (256, 256, 2)]
+
+
+def default_hparams(**over):
+    """The argparse defaults of reference pose_trainer.py:204-218."""
+    hp = dict(lr=1e-4, win_size=9, bs=256, kps_channel=3, graph_layout="coco", max_hop=2, dilation=1,
+              keypoint_format="coco", n_out_joints=22, n_out_channels=3)
+    hp.update(over)
+    return argparse.Namespace(**hp)
+
+
+class PoseRegressor(nn.Module, _ComputeDtypeMixin):
+    def __init__(self, hparams):
+        super().__init__()
+        self.graph_cfg = dict(layout=hparams.graph_layout, strategy="uniform", max_hop=hparams.max_hop,
+                              dilation=hparams.dilation)
+        layers = [StgLayerConfig(in_channels=hparams.kps_channel if ci is None else ci, out_channels=co,
+                                 temporal_stride=s, is_residual=True) for ci, co, s in _BLOCKS]
+        self.backbone = StgGcn18(config=StgConfig(layers=layers, temporal_kernel_size=3), graph_cfg=self.graph_cfg)
+        self.pose_dim = 22 * 3
+        self.pose_regressor = nn.Sequential(nn.Linear(17 * 256, 512), nn.LeakyReLU(), nn.Dropout(0.7),
+                                            nn.Linear(512, self.pose_dim))
+        self.compute_dtype = _default_dtype()
+        self.chunk_clips = None
+        self._engine = None
+
+    def _head(self):
+        return self.pose_regressor[0], self.pose_regressor[1].negative_slope, self.pose_regressor[3]
+
+    def plan_for(self, N, T):
+        if self._engine is None:
+            self._engine = engine.Engine(self.backbone, self._head)
+        return self._engine.plan(self.compute_dtype, N, T, self.chunk_clips)
+
+    def forward(self, x, init_pose=None, n_iter=3):
+        """x (N, T, V, C) -> {'poses': (N, T', 66)} axis-angle, joint-major (reference pose_trainer.py:94-133).
+        ``init_pose`` / ``n_iter`` belong to the reference's commented-out iterative 6-D head and are ignored
+        there as well."""
+        engine.require_cuda_eval(self, x, "PoseRegressor")
+        x = self.backbone._check_input(x)
+        N, T = x.shape[0], x.shape[1]
+        if N == 0:
+            return {"poses": x.new_zeros((0, self.backbone.out_frames(T), self.pose_dim))}
+        poses, _ = self.plan_for(N, T).run(x)
+        return {"poses": poses}
+
+
+class IKPoseTrainer(nn.Module, _ComputeDtypeMixin):
+    """Inference-side stand-in for the reference LightningModule (pose_trainer.py:136-144): same attribute
+    names (``hparams``, ``regressor``, ``device``), same forward, loads Lightning checkpoints."""
+
+    def __init__(self, hparams=None):
+        super().__init__()
+        self.hparams = hparams if hparams is not None else default_hparams()
+        self.regressor = PoseRegressor(self.hparams)
+        self.compute_dtype = _default_dtype()
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def forward(self, keypoints_3d):
+        return self.regressor(keypoints_3d)
+
+    @classmethod
+    def load_from_checkpoint(cls, path, map_location=None):
+        """Reads a pytorch_lightning checkpoint written by the reference trainer (inference.py:136): a dict with
+        ``state_dict`` (keys prefixed ``regressor.``) and the pickled hparams."""
+        ckpt = torch.load(path, map_location=map_location or "cpu", weights_only=False)
+        hp = ckpt.get("hparams", ckpt.get("hyper_parameters", None))
+        if isinstance(hp, dict):
+            hp = default_hparams(**hp)
+        model = cls(hp)
+        sd = {k: v for k, v in ckpt["state_dict"].items() if k.startswith("regressor.")}
+        model.load_state_dict(sd, strict=True)
+        return model
+
+    def training_step(self, *a, **k):
+        raise NotImplementedError("training is out of scope for the CUDA inference path (reference pose_trainer.py:146)")

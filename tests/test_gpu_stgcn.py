@@ -1,0 +1,143 @@
+"""ST-GCN IK forward on the GPU (through libtik.so) vs the oracle / reference-generated goldens."""
+import numpy as np
+import pytest
+import torch
+
+import packed_emulator
+from oracle import stgcn_port as sp, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-4          # north_star tolerance for the fp32 path
+TOL_BF16_ABS = 0.08     # stated bf16 tolerance on 'poses' (output RMS ~1.3 rad): max-abs
+TOL_BF16_RMS = 0.02     # and RMS error
+
+
+def _model(seed=0, dtype="fp32", cuda=True):
+    from temporal_inverse_kinematics_b200.pose_regressor import PoseRegressor, default_hparams
+    m = PoseRegressor(default_hparams()).eval()
+    sd = synth.make_regressor_state(sp.build_adjacency("coco", "uniform", 2, 1), seed=seed)
+    m.load_state_dict(sd, strict=True)
+    return (m.cuda() if cuda else m).set_compute_dtype(dtype), sd
+
+
+@pytest.mark.parametrize("tag", ["t9", "t64", "t13", "t1", "t128"])
+def test_fp32_matches_reference_golden(golden, tag):
+    g = golden("stgcn.npz")
+    m, sd = _model()
+    assert synth.state_checksum(sd) == float(g["state_checksum"])
+    n, t, seed = [int(v) for v in g[f"{tag}_shape"]]
+    y = m(synth.make_clips(n, t, seed=seed).cuda())["poses"].cpu().numpy()
+    assert y.shape == g[f"{tag}_poses"].shape
+    assert np.abs(y - g[f"{tag}_poses"]).max() < TOL_F32
+    feat = m.backbone(synth.make_clips(n, t, seed=seed).cuda()).cpu().numpy()
+    assert np.abs(feat.reshape(-1)[:2048] - g[f"{tag}_feat_head"]).max() < TOL_F32
+
+
+@pytest.mark.parametrize("n,t,chunk", [(5, 9, 2), (3, 64, None), (7, 20, 3), (64, 9, None)])
+def test_fp32_matches_oracle_with_chunking(n, t, chunk):
+    m, sd = _model()
+    m.chunk_clips = chunk
+    x = synth.make_clips(n, t, seed=n * 100 + t)
+    y = m(x.cuda())["poses"].cpu()
+    want = sp.regressor_forward(sd, x)["poses"]
+    assert float((y - want).abs().max()) < TOL_F32
+
+
+@pytest.mark.parametrize("n,t,chunk", [(4, 64, None), (5, 9, 2), (3, 13, None), (2, 128, 1), (40, 16, 16)])
+def test_bf16_within_stated_tolerance(n, t, chunk):
+    m, sd = _model(dtype="bf16")
+    m.chunk_clips = chunk
+    x = synth.make_clips(n, t, seed=n * 100 + t)
+    y = m(x.cuda())["poses"].cpu()
+    want = sp.regressor_forward(sd, x)["poses"]
+    err = (y - want).abs()
+    assert float(err.max()) < TOL_BF16_ABS, float(err.max())
+    assert float(err.pow(2).mean().sqrt()) < TOL_BF16_RMS
+    # the tensor-core path must agree with a bf16-rounding emulation of the same packed algebra much more tightly
+    from temporal_inverse_kinematics_b200 import engine
+    mc, _ = _model(dtype="bf16", cuda=False)
+    emu = packed_emulator.forward(engine.PackedNet(mc.backbone, mc._head(), "bf16"), x)
+    assert float((y - emu).abs().max()) < 0.03
+
+
+def test_dance_config1(golden):
+    """BASELINE.json configs[0]: dance_contemporary.npz windows, win_size 9."""
+    g = golden("dance.npz")
+    m, sd = _model()
+    assert synth.state_checksum(sd) == float(g["state_checksum"])
+    names = [str(s) for s in g["joint_3d_names"]]
+    wins = sp.inference_windows(sp.moveai_to_coco(g["joints_3d"], names), 9).astype(np.float32)
+    y = m(torch.from_numpy(wins).cuda())["poses"].cpu().numpy()
+    assert y.shape == (231, 1, 66)
+    assert np.abs(y - g["poses"]).max() < TOL_F32
+    y1 = torch.cat([m(torch.from_numpy(wins[i:i + 1]).cuda())["poses"] for i in range(0, 231, 23)]).cpu().numpy()
+    assert np.abs(y1 - g["poses"][::23]).max() < TOL_F32              # batch 1, as configs[0] runs it
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", TOL_F32), ("bf16", 0.15)])
+def test_backbone_variants(golden, dtype, tol):
+    """K=3 partitions (distance / spatial), temporal kernel 5, a block without residual."""
+    from temporal_inverse_kinematics_b200.st_gcn import StgConfig, StgGcn18, StgLayerConfig
+    g = golden("stgcn_variants.npz")
+    layers = [(3, 64, 1, True), (64, 64, 2, True), (64, 128, 1, True)]
+    cases = [("distance", 2, 3, layers, 5, 77, 10, "distance2_feat"), ("spatial", 1, 3, layers, 5, 77, 10, "spatial1_feat"),
+             ("spatial", 2, 3, layers, 5, 77, 10, "spatial2_feat"),
+             ("uniform", 2, 5, [(3, 64, 1, False), (64, 64, 1, True), (64, 128, 2, True)], 6, 78, 11, "kt5_feat")]
+    for strategy, max_hop, kt, lay, seed, xseed, t, key in cases:
+        graph_cfg = dict(layout="coco", strategy=strategy, max_hop=max_hop, dilation=1)
+        bb = StgGcn18(StgConfig([StgLayerConfig(*l) for l in lay], kt), graph_cfg).eval()
+        bb.load_state_dict(synth.make_backbone_state(sp.build_adjacency("coco", strategy, max_hop, 1), lay, kt=kt, seed=seed, prefix=""))
+        bb = bb.cuda().set_compute_dtype(dtype)
+        f = bb(synth.make_clips(2, t, seed=xseed).cuda()).cpu().numpy()
+        assert f.shape == g[key].shape
+        assert np.abs(f - g[key]).max() < tol, (key, np.abs(f - g[key]).max())
+
+
+@pytest.mark.parametrize("K", [1, 3])
+def test_graph_conv_module_matches_reference(golden, K):
+    from temporal_inverse_kinematics_b200.st_gcn import ConvTemporalGraphical
+    g = golden("stgcn_variants.npz")
+    m = ConvTemporalGraphical(8, 16, K).eval()
+    m.load_state_dict({"conv.weight": torch.from_numpy(g[f"gconv{K}_w"]), "conv.bias": torch.from_numpy(g[f"gconv{K}_b"])})
+    m = m.cuda()
+    y, A = m(torch.from_numpy(g[f"gconv{K}_x"]).cuda(), torch.from_numpy(g[f"gconv{K}_A"]).cuda())
+    assert y.shape == g[f"gconv{K}_y"].shape and y.is_contiguous()
+    assert np.abs(y.cpu().numpy() - g[f"gconv{K}_y"]).max() < TOL_F32
+
+
+@pytest.mark.parametrize("cin,cout,stride,residual,dtype,tol", [
+    (3, 64, 1, True, "fp32", TOL_F32), (64, 64, 1, True, "fp32", TOL_F32), (64, 128, 2, True, "fp32", TOL_F32),
+    (64, 64, 1, False, "fp32", TOL_F32), (64, 128, 2, True, "bf16", 0.06), (128, 128, 1, True, "bf16", 0.06)])
+def test_block_module_matches_oracle(cin, cout, stride, residual, dtype, tol):
+    from temporal_inverse_kinematics_b200.st_gcn import StGcnBlock
+    A = sp.build_adjacency("coco", "uniform", 2, 1)
+    sd_all = synth.make_backbone_state(A, [(cin, cout, stride, residual)], kt=3, seed=9, prefix="")
+    sd = {k[len("st_gcn_networks.0."):]: v for k, v in sd_all.items() if k.startswith("st_gcn_networks.0.")}
+    blk = StGcnBlock(cin, cout, (3, 1), stride, residual=residual).eval()
+    blk.load_state_dict(sd, strict=True)
+    blk = blk.cuda().set_compute_dtype(dtype)
+    x = torch.from_numpy(np.random.RandomState(4).standard_normal((3, cin, 11, 17)).astype(np.float32))
+    Ah = torch.from_numpy(A.astype(np.float32)) * sd_all["edge_importance.0"]
+    y, _ = blk(x.cuda(), Ah.cuda())
+    with torch.no_grad():
+        want = sp.st_gcn_block(x, Ah, sd_all, "st_gcn_networks.0.", cin, cout, stride, residual)
+    assert y.shape == want.shape
+    assert float((y.cpu() - want).abs().max()) < tol
+
+
+def test_weight_update_invalidates_cache():
+    m, sd = _model()
+    x = synth.make_clips(2, 9, seed=1).cuda()
+    y0 = m(x)["poses"].clone()
+    with torch.no_grad():
+        m.pose_regressor[3].bias.add_(1.0)
+    y1 = m(x)["poses"]
+    assert float((y1 - y0 - 1.0).abs().max()) < 1e-5
+
+
+def test_errors_surface_as_exceptions():
+    m, _ = _model()
+    with pytest.raises(ValueError):
+        m(torch.zeros(2, 9, 16, 3).cuda())                            # wrong node count
+    assert m(torch.zeros(0, 9, 17, 3).cuda())["poses"].shape == (0, 1, 66)
