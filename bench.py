@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""Headline benchmark: IK-solved frames/s (ST-GCN forward + SMPL-X body FK) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype bf16|fp32]
+
+Workload (BASELINE.json configs[2]): B=4096 clips of T=64 root-relative COCO-17 frames per GPU, bf16
+tensor-core ST-GCN forward (PoseRegressor) + 22-joint body FK on the B*T/16 solved poses.  A "step" is one
+pass of that path over one synthetic batch.  One process per GPU; with N>1 every rank works on its own shard
+(weak scaling) and the solved poses are all-gathered over NCCL once per step.  Rank 0 prints ONE JSON line.
+
+`--impl reference` times the reference's CPU implementation of the same path (the oracle port of its PyTorch
+modules, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU, T_FRAMES, V, C_IN, J = 4096, 64, 17, 3, 22
+METRIC = "IK-solved frames/sec (ST-GCN fwd + SMPL-X FK)"
+UNIT = "frames/s"
+CPU_SAMPLE_CLIPS = 256
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def _oracle_model():
+    from oracle import stgcn_port as sp, synth
+    A = sp.build_adjacency("coco", "uniform", 2, 1)
+    return sp, synth, synth.make_regressor_state(A, seed=0)
+
+
+def cpu_reference_step(sd, sp, fk_port, x, rest, parents):
+    """The reference's CPU path for one batch: PoseRegressor forward (oracle port of the PyTorch modules) + FK."""
+    poses = sp.regressor_forward(sd, x)["poses"]
+    aa = poses.reshape(-1, J, 3).numpy()
+    joints, _, _ = fk_port.fk_from_axis_angle(aa, rest, parents)
+    return poses, joints
+
+
+def time_cpu(clips, iters, warm=1):
+    import torch
+    from oracle import fk_port
+    sp, synth, sd = _oracle_model()
+    x = synth.make_clips(clips, T_FRAMES, seed=1234)
+    rest, parents = synth.make_rest_skeleton(), synth.SMPLX_BODY_PARENTS
+    for _ in range(warm):
+        cpu_reference_step(sd, sp, fk_port, x, rest, parents)
+    ts = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        cpu_reference_step(sd, sp, fk_port, x, rest, parents)
+        ts.append(time.perf_counter() - t0)
+    return clips * T_FRAMES / (sum(ts) / len(ts)), sum(ts) / len(ts), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    fps, sec, threads = time_cpu(CPU_SAMPLE_CLIPS, max(1, args.steps), warm=max(1, min(args.warmup, 2)))
+    sample = f"{CPU_SAMPLE_CLIPS} clips x T={T_FRAMES} per step (bounded sample of the B={B_PER_GPU} batch), fp32, torch CPU"
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[2]: B={B_PER_GPU} clips/GPU, T={T_FRAMES}, ST-GCN fwd + 22-joint FK", "sample": sample},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from temporal_inverse_kinematics_b200 import _lib, smpl_util, synthetic as synth
+    from temporal_inverse_kinematics_b200.graph import Graph
+    from temporal_inverse_kinematics_b200.pose_regressor import PoseRegressor, default_hparams
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.lib().tik_check_device())
+
+    B, T = args.batch, T_FRAMES
+    model = PoseRegressor(default_hparams()).eval()
+    model.load_state_dict(synth.make_regressor_state(Graph("coco", "uniform", 2, 1).A, seed=0))
+    model = model.to(dev).set_compute_dtype(args.dtype)
+    if args.chunk:
+        model.chunk_clips = args.chunk
+    rest, parents = synth.make_rest_skeleton(), synth.SMPLX_BODY_PARENTS
+
+    x_host = synth.make_clips(B, T, seed=1234 + rank).pin_memory()
+    x_dev = x_host.to(dev)
+    T_out = model.backbone.out_frames(T)
+    gathered = torch.empty((world * B, T_out, 66), device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(x):
+        poses = model(x)["poses"]                                # (B, T', 66) axis-angle
+        joints = smpl_util.fk_body(poses.view(-1, J, 3), rest, parents)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, poses)
+        return poses, joints
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev)
+    barrier()
+
+    # ---- device-resident timing: CUDA events per step on the launching stream, L2 flushed between steps
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        step(x_dev)
+        b.record()
+    barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+
+    # ---- end to end through the public API: pinned host input -> H2D -> forward + FK -> D2H of the results
+    out_p = torch.empty((B, T_out, 66), dtype=torch.float32).pin_memory()
+    out_j = torch.empty((B * T_out, J, 3), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        x = x_host.to(dev, non_blocking=True)
+        poses, joints = step(x)
+        out_p.copy_(poses, non_blocking=True)
+        out_j.copy_(joints, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks, peak_src = _peaks()
+        plan = model.plan_for(B, T)
+        kinds, gemm_flops = plan.profile(x_dev)                  # CUDA events around every kernel (one extra run)
+        g_ms, g_n = kinds["gemm"]
+        achieved = gemm_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+        peak = peaks["bf16_tflops_sustained"] if args.dtype == "bf16" else 74.0
+        launches_per_step = plan.launches(B) + 1                 # + FK
+        roofline = {"bound": "tensor", "kernel": "rowgemm_umma_kernel" if args.dtype == "bf16" else "rowgemm_f32_kernel",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "peak_source": (peak_src + " bf16_tflops_sustained (kernel timed inside a long step)") if args.dtype == "bf16" else "nominal fp32 SIMT 148 SM x 128 FMA x 2 x 1.965 GHz",
+                    "launches": g_n, "avg_launch_us": g_ms * 1e3 / max(g_n, 1), "flops_per_step": gemm_flops,
+                    "kernel_ms_per_step": {k: v[0] for k, v in kinds.items()}, "traffic": None}
+        line = {"metric": METRIC, "value": world * B * T / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": f"configs[2]: B={B} clips/GPU, T={T}, {args.dtype} ST-GCN fwd (PoseRegressor, random-init "
+                                       f"weights) + 22-joint body FK on {B * T_out} solved poses/GPU",
+                           "global_batch": world * B, "frames_per_step": world * B * T, "chunk_clips": plan.n_chunk,
+                           "l2": "flushed between timed steps (256 MiB memset)", "parallelism": f"dp{world}",
+                           "gather": "NCCL all_gather of poses each step" if world > 1 else "none"},
+                "e2e": {"value": world * B * T / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": (out_p.numel() + out_j.numel()) * 4},
+                "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline}
+        if world == 1 and not args.no_cpu:
+            torch.set_num_threads(os.cpu_count() or 1)
+            fps, sec, threads = time_cpu(CPU_SAMPLE_CLIPS, 3)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{CPU_SAMPLE_CLIPS} of the {B} clips (T={T}), 3 iterations, oracle port of the "
+                                              f"reference PyTorch modules + numpy FK; {sec:.2f} s/iteration"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

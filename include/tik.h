@@ -180,6 +180,11 @@ int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int T, 
  * n_chunk at a time so that per-layer activations stay L2-resident. */
 int tik_stgcn_plan_run(TikPlan* plan, const float* x_dev, int64_t N, float* poses_dev, void* feat_dev,
                        void* stream);
+/* Measurement aid (synchronises the stream): one run with CUDA events around every kernel.
+ * ms_by_kind[3] / launches_by_kind[3] = {stem, aggregate, implicit-GEMM}; flops_gemm = algorithmic
+ * 2*rows*K*c_out summed over the implicit-GEMM launches. */
+int tik_stgcn_plan_profile(TikPlan* plan, const float* x_dev, int64_t N, float* poses_dev, void* stream,
+                           double* ms_by_kind, int64_t* launches_by_kind, double* flops_gemm);
 /* kernels one tik_stgcn_plan_run over N clips launches (for bench.py's gpu_launches). */
 int64_t tik_stgcn_plan_launches(const TikPlan* plan, int64_t N);
 void tik_stgcn_plan_destroy(TikPlan* plan);

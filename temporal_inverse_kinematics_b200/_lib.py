@@ -55,6 +55,7 @@ _PROTOS = {
     "tik_stgcn_workspace_bytes": (C.c_int, [C.POINTER(TikNet), C.c_int, i64, C.c_int, C.POINTER(i64)]),
     "tik_stgcn_plan_create": (C.c_int, [C.POINTER(TikNet), C.c_int, i64, C.c_int, vp, i64, C.POINTER(vp)]),
     "tik_stgcn_plan_run": (C.c_int, [vp, vp, i64, vp, vp, vp]),
+    "tik_stgcn_plan_profile": (C.c_int, [vp, vp, i64, vp, vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]),
     "tik_stgcn_plan_launches": (i64, [vp, i64]),
     "tik_stgcn_plan_destroy": (None, [vp]),
 }

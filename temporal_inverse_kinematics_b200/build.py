@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([_nvcc(), "-shared", "-o", LIB, *objs, "-cudart", "static"])
+    subprocess.check_call([_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB, *objs, "-cudart", "static"])
     return LIB
 
 

@@ -258,11 +258,9 @@ int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int T, 
   return TIK_OK;
 }
 
-int tik_stgcn_plan_run(TikPlan* P, const float* x, int64_t N, float* poses, void* feat_out, void* stream) {
+static int run_impl(TikPlan* P, const float* x, int64_t N, float* poses, void* feat_out, cudaStream_t s,
+                    std::vector<cudaEvent_t>* events) {
   using namespace tik;
-  TIK_CHECK_ARG(P && x && N >= 0, "bad arguments");
-  TIK_CHECK_ARG(P->net.head_hidden == 0 || poses, "poses pointer required");
-  cudaStream_t s = (cudaStream_t)stream;
   const TikNet& net = P->net;
   const int V = net.V, T = P->T;
   for (int64_t n0 = 0; n0 < N; n0 += P->n_chunk) {
@@ -270,6 +268,12 @@ int tik_stgcn_plan_run(TikPlan* P, const float* x, int64_t N, float* poses, void
     const float* xc = x + n0 * (int64_t)T * V * net.c_in;
     for (auto& st : P->steps) {
       int rc = TIK_OK;
+      if (events) {
+        cudaEvent_t e;
+        TIK_CUDA(cudaEventCreate(&e));
+        TIK_CUDA(cudaEventRecord(e, s));
+        events->push_back(e);
+      }
       if (st.kind == Step::STEM) {
         const TikBlock& b = *st.blk;
         rc = tik_stem_gcn(P->dtype, xc, net.in_scale_dev, net.in_shift_dev, b.agg_dev, reinterpret_cast<const float*>(b.w_gcn_dev),
@@ -297,6 +301,53 @@ int tik_stgcn_plan_run(TikPlan* P, const float* x, int64_t N, float* poses, void
                                (size_t)(n * P->feat_elems_per_clip) * P->es, cudaMemcpyDeviceToDevice, s));
     }
   }
+  if (events) {
+    cudaEvent_t e;
+    TIK_CUDA(cudaEventCreate(&e));
+    TIK_CUDA(cudaEventRecord(e, s));
+    events->push_back(e);
+  }
+  return TIK_OK;
+}
+
+int tik_stgcn_plan_run(TikPlan* P, const float* x, int64_t N, float* poses, void* feat_out, void* stream) {
+  using namespace tik;
+  TIK_CHECK_ARG(P && x && N >= 0, "bad arguments");
+  TIK_CHECK_ARG(P->net.head_hidden == 0 || poses, "poses pointer required");
+  return run_impl(P, x, N, poses, feat_out, (cudaStream_t)stream, nullptr);
+}
+
+int tik_stgcn_plan_profile(TikPlan* P, const float* x, int64_t N, float* poses, void* stream, double* ms_by_kind,
+                           int64_t* launches_by_kind, double* flops_gemm) {
+  using namespace tik;
+  TIK_CHECK_ARG(P && x && N >= 0 && ms_by_kind && launches_by_kind && flops_gemm, "bad arguments");
+  TIK_CHECK_ARG(P->net.head_hidden == 0 || poses, "poses pointer required");
+  std::vector<cudaEvent_t> ev;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = run_impl(P, x, N, poses, nullptr, s, &ev);
+  if (rc != TIK_OK) return rc;
+  TIK_CUDA(cudaStreamSynchronize(s));
+  for (int k = 0; k < 3; ++k) { ms_by_kind[k] = 0; launches_by_kind[k] = 0; }
+  *flops_gemm = 0;
+  size_t i = 0;
+  for (int64_t n0 = 0; n0 < N; n0 += P->n_chunk) {
+    const int64_t n = std::min<int64_t>(P->n_chunk, N - n0);
+    for (auto& st : P->steps) {
+      float ms = 0;
+      TIK_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      const int kind = st.kind == Step::STEM ? 0 : (st.kind == Step::AGG ? 1 : 2);
+      ms_by_kind[kind] += ms;
+      launches_by_kind[kind] += 1;
+      if (st.kind == Step::GEMM) {
+        double ktot = 0;
+        for (int q = 0; q < st.g.n_slabs; ++q) ktot += st.g.slabs[q].c;
+        const double rows = st.g.v == 1 ? (double)n * P->T_out : (double)n * P->net.V * st.g.t_out;
+        *flops_gemm += 2.0 * rows * ktot * st.g.c_out_valid;
+      }
+      ++i;
+    }
+  }
+  for (auto e : ev) cudaEventDestroy(e);
   return TIK_OK;
 }
 

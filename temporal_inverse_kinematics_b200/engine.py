@@ -183,6 +183,18 @@ class Plan:
     def launches(self, N):
         return int(L.lib().tik_stgcn_plan_launches(self.handle, N))
 
+    def profile(self, x):
+        """One run with CUDA events around every kernel -> {'stem'|'aggregate'|'gemm': (ms, launches)}, gemm flops."""
+        p = self.packed
+        N = x.shape[0]
+        poses = torch.empty((N, self.T_out, max(p.head_out, 1)), dtype=torch.float32, device=x.device)
+        ms = (C.c_double * 3)()
+        cnt = (L.i64 * 3)()
+        fl = C.c_double(0)
+        L.check(L.lib().tik_stgcn_plan_profile(self.handle, L.ptr(x), N, L.ptr(poses), L.stream_ptr(x.device), ms, cnt,
+                                               C.byref(fl)))
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(("stem", "aggregate", "gemm"))}, fl.value
+
     def run(self, x, want_feat=False):
         p = self.packed
         N = x.shape[0]

@@ -64,7 +64,7 @@ def stage_simt():
     A = torch.rand(2, V, V, device="cuda") * (torch.rand(2, V, V, device="cuda") > 0.5)
     ok &= report("aggregate f32", ops.aggregate(x, A), torch.einsum("kvw,nvtc->knwtc", A, x), 1e-5)
     xb = x.bfloat16()
-    ok &= report("aggregate bf16", ops.aggregate(xb, A), torch.einsum("kvw,nvtc->knwtc", A, xb.float()), 2e-2)
+    ok &= report("aggregate bf16", ops.aggregate(xb, A), torch.einsum("kvw,nvtc->knwtc", A, xb.float()), 5e-2)
     w = torch.randn(128, 3 * Cc, device="cuda") * 0.1
     b = torch.randn(V, 128, device="cuda")
     h = x.view(N * V, T, Cc)
