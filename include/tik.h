@@ -79,9 +79,14 @@ int tik_fk_body(const float* pose_dev, int pose_is_rotmat, const float* rest_hos
  * and the first ConvTemporalGraphical + tcn.0/tcn.1 (gconv_origin.py:56-65, st_gcn_aaai18.py:178-179).
  *   x (N,T,V,Cin) fp32 (the reference's input layout); in_scale/in_shift (V*Cin) folded data_bn;
  *   agg (K,V,V) fp32 = A*importance; w (Cout, K*Cin) fp32 BN-folded; bias (V,Cout) fp32;
- *   out (N,V,T,Cout) dtype, ReLU applied if relu != 0. */
+ *   out (N,V,T,Cout) dtype, ReLU applied if relu != 0.
+ * If res_w_dev != NULL the block's residual branch (1x1 conv stride (s,1) + BN, st_gcn_aaai18.py:198-204)
+ * is produced in the same pass: res_out[n,w,t',:] = res_w[w] . x[n, s*t', w, :] with res_w (V,Cout,Cin)
+ * fp32 (data_bn scale folded in, constants go to the temporal conv's per-node bias),
+ * res_out (N,V,floor((T-1)/s)+1,Cout) dtype. */
 int tik_stem_gcn(int dtype, const float* x_dev, const float* in_scale_dev, const float* in_shift_dev,
                  const float* agg_dev, const float* w_dev, const float* bias_dev, void* out_dev,
+                 const float* res_w_dev, void* res_out_dev, int res_stride,
                  int64_t N, int T, int V, int Cin, int K, int Cout, int relu, void* stream);
 
 /* Adjacency aggregation: out[k][(n,w),t,c] = sum_v agg[k][v][w] * x[(n,v),t,c].
@@ -169,15 +174,16 @@ typedef struct TikPlan TikPlan;
 
 /* frames after the strided blocks: T -> floor((T-1)/s)+1 per block. */
 int tik_stgcn_out_frames(const TikNet* net, int T);
-/* bytes of device workspace a plan for chunks of n_chunk clips of T frames needs. */
-int tik_stgcn_workspace_bytes(const TikNet* net, int dtype, int64_t n_chunk, int T, int64_t* bytes);
+/* bytes of device workspace a plan needs: the backbone runs n_chunk clips at a time (L2-resident layers),
+ * the head runs once over up to n_max clips. */
+int tik_stgcn_workspace_bytes(const TikNet* net, int dtype, int64_t n_chunk, int64_t n_max, int T, int64_t* bytes);
 /* Builds the launch plan (tile shapes, TMA tensor maps over `workspace_dev`).  Host-only work. */
-int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int T, void* workspace_dev,
+int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int64_t n_max, int T, void* workspace_dev,
                           int64_t workspace_bytes, TikPlan** plan);
 /* PoseRegressor.forward: x (N,T,V,c_in) fp32 -> poses (N,T',head_out) fp32 (pose_trainer.py:94-133).
  * feat_dev, if not NULL, receives the backbone output (N,T',V*c_last) in the plan dtype
- * (StgGcn18.forward, st_gcn_aaai18.py:113-133).  N may exceed n_chunk: clips are processed
- * n_chunk at a time so that per-layer activations stay L2-resident. */
+ * (StgGcn18.forward, st_gcn_aaai18.py:113-133).  N may exceed n_chunk and n_max: the backbone
+ * processes n_chunk clips at a time and the head n_max clips at a time. */
 int tik_stgcn_plan_run(TikPlan* plan, const float* x_dev, int64_t N, float* poses_dev, void* feat_dev,
                        void* stream);
 /* Measurement aid (synchronises the stream): one run with CUDA events around every kernel.
@@ -188,6 +194,10 @@ int tik_stgcn_plan_profile(TikPlan* plan, const float* x_dev, int64_t N, float* 
 /* kernels one tik_stgcn_plan_run over N clips launches (for bench.py's gpu_launches). */
 int64_t tik_stgcn_plan_launches(const TikPlan* plan, int64_t N);
 void tik_stgcn_plan_destroy(TikPlan* plan);
+
+/* Experiment hook, not used by the product path: makes the tensor-core kernel read its A operand `rows`
+ * rows below the tile start (mode 1 also sets the descriptor's base-offset field).  See DESIGN.md. */
+int tik_debug_set_umma_shift(int rows, int mode);
 
 #ifdef __cplusplus
 }

@@ -47,17 +47,18 @@ _PROTOS = {
     "tik_batch_rodrigues": (C.c_int, [vp, vp, i64, vp]),
     "tik_rotmat_to_aa": (C.c_int, [vp, vp, i64, C.c_int, vp]),
     "tik_fk_body": (C.c_int, [vp, C.c_int, C.POINTER(f32), C.POINTER(i32), C.c_int, vp, vp, vp, vp, i64, vp]),
-    "tik_stem_gcn": (C.c_int, [C.c_int, vp, vp, vp, vp, vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int,
-                               C.c_int, C.c_int, vp]),
+    "tik_stem_gcn": (C.c_int, [C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, i64, C.c_int, C.c_int, C.c_int,
+                               C.c_int, C.c_int, C.c_int, vp]),
     "tik_aggregate": (C.c_int, [C.c_int, vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "tik_rowgemm": (C.c_int, [C.c_int, C.POINTER(TikRowGemm), vp]),
     "tik_stgcn_out_frames": (C.c_int, [C.POINTER(TikNet), C.c_int]),
-    "tik_stgcn_workspace_bytes": (C.c_int, [C.POINTER(TikNet), C.c_int, i64, C.c_int, C.POINTER(i64)]),
-    "tik_stgcn_plan_create": (C.c_int, [C.POINTER(TikNet), C.c_int, i64, C.c_int, vp, i64, C.POINTER(vp)]),
+    "tik_stgcn_workspace_bytes": (C.c_int, [C.POINTER(TikNet), C.c_int, i64, i64, C.c_int, C.POINTER(i64)]),
+    "tik_stgcn_plan_create": (C.c_int, [C.POINTER(TikNet), C.c_int, i64, i64, C.c_int, vp, i64, C.POINTER(vp)]),
     "tik_stgcn_plan_run": (C.c_int, [vp, vp, i64, vp, vp, vp]),
     "tik_stgcn_plan_profile": (C.c_int, [vp, vp, i64, vp, vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]),
     "tik_stgcn_plan_launches": (i64, [vp, i64]),
     "tik_stgcn_plan_destroy": (None, [vp]),
+    "tik_debug_set_umma_shift": (C.c_int, [C.c_int, C.c_int]),
 }
 
 _lib = None

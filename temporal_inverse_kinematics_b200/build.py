@@ -10,8 +10,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtik.so")
-SOURCES = ["geometry.cu", "fk.cu", "stgcn_simt.cu", "stgcn_umma.cu", "plan.cu"]
-HEADERS = ["tik_common.cuh", "umma_prepared.h", os.path.join("..", "..", "include", "tik.h")]
+SOURCES = ["geometry.cu", "fk.cu", "stem.cu", "stgcn_simt.cu", "stgcn_umma.cu", "plan.cu"]
+HEADERS = ["tik_common.cuh", "umma_prepared.h", "umma_ptx.cuh", os.path.join("..", "..", "include", "tik.h")]
 
 
 def _nvcc():

@@ -1,9 +1,14 @@
 // Whole-network launch plan: PoseRegressor.forward (pose_trainer.py:94-133) =
 // StgGcn18 backbone (st_gcn_aaai18.py:113-133) + Linear/LeakyReLU/Linear head, as a fixed sequence of
-// kernels over caller-owned workspace.  Clips are processed n_chunk at a time so that the per-layer
-// activations of a chunk stay resident in the 126 MB L2 between producer and consumer kernels.
+// kernels over caller-owned workspace.
+//
+// The backbone runs n_chunk clips at a time so that the per-layer activations of a chunk stay resident in
+// the 126 MB L2 between producer and consumer kernels; the last block writes its (N,T',V*C) features into a
+// batch-level buffer and the two head GEMMs then run ONCE over up to n_max clips (a per-chunk head would be
+// a handful of CTAs on a 148-SM part).
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "tik_common.cuh"
@@ -21,17 +26,19 @@ void set_error(const char* fmt, ...) {
 }
 
 static int out_frames(int t, int stride) { return (t - 1) / stride + 1; }
+static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 struct Step {
-  enum Kind { STEM, AGG, GEMM } kind;
-  TikRowGemm g;              // GEMM
+  enum Kind { STEM = 0, AGG = 1, GEMM = 2 } kind;
+  TikRowGemm g;               // GEMM
   UmmaPrepared* prep = nullptr;
-  // STEM / AGG arguments
-  const void* src = nullptr; void* dst = nullptr;
-  int t = 0, c = 0, cout = 0;
+  const void* src = nullptr;  // AGG input
+  void* dst = nullptr;        // STEM / AGG output
+  void* dst2 = nullptr;       // STEM residual output
+  int t = 0, c = 0;
   const TikBlock* blk = nullptr;
-  bool src_is_input = false;  // GEMM: residual comes from the user's input pointer (stem residual)
-  bool dst_is_output = false; // GEMM: writes the user's poses pointer
+  bool out_is_feat = false;   // GEMM: writes the batch-level feature buffer at the chunk's offset
+  bool out_is_poses = false;  // GEMM: writes the caller's poses pointer
 };
 
 }  // namespace tik
@@ -39,24 +46,24 @@ struct Step {
 struct TikPlan {
   TikNet net;
   int dtype;
-  int64_t n_chunk;
+  int64_t n_chunk, n_max;
   int T, T_out;
-  size_t es;                 // element size of activations
-  std::vector<tik::Step> steps;
-  void* feat = nullptr;      // backbone output of the current chunk, (n, T', V*C_last)
+  size_t es;                  // element size of activations
+  std::vector<tik::Step> chunk_steps, batch_steps;
+  uint8_t* feat = nullptr;    // (n_max, T', V*C_last) activation dtype
   int64_t feat_elems_per_clip = 0;
   int c_last = 0;
   ~TikPlan() {
-    for (auto& s : steps)
-      if (s.prep) tik::umma_free(s.prep);
+    for (auto* v : {&chunk_steps, &batch_steps})
+      for (auto& s : *v)
+        if (s.prep) tik::umma_free(s.prep);
   }
 };
 
 namespace tik {
 
 struct WsLayout {
-  int64_t x_elems, agg_elems, h_elems, z_elems;   // per clip
-  int64_t off_x0, off_x1, off_agg, off_h, off_z, total_bytes;
+  int64_t off_x0, off_x1, off_agg, off_h, off_r0, off_feat, off_z, total_bytes;
 };
 
 static int check_net(const TikNet* net, int dtype) {
@@ -66,7 +73,7 @@ static int check_net(const TikNet* net, int dtype) {
   TIK_CHECK_ARG(net->V >= 1 && net->V <= 32 && net->K >= 1 && net->K <= 5, "V=%d K=%d unsupported", net->V, net->K);
   TIK_CHECK_ARG(net->c_in >= 1 && net->c_in * net->K <= 40, "stem needs K*c_in <= 40 (got c_in=%d K=%d)", net->c_in, net->K);
   TIK_CHECK_ARG(net->blocks[0].c_in == net->c_in, "block 0 c_in mismatch");
-  const int cmul = dtype == TIK_BF16 ? 64 : 4;
+  const int cmul = dtype == TIK_BF16 ? 64 : 8;
   for (int i = 0; i < net->n_blocks; ++i) {
     const TikBlock& b = net->blocks[i];
     TIK_CHECK_ARG(b.kt >= 1 && (b.kt % 2) == 1 && b.kt + 1 <= TIK_MAX_SLABS, "block %d: temporal kernel %d unsupported", i, b.kt);
@@ -74,7 +81,6 @@ static int check_net(const TikNet* net, int dtype) {
     TIK_CHECK_ARG(b.c_out % cmul == 0, "block %d: c_out=%d must be a multiple of %d for this dtype", i, b.c_out, cmul);
     if (i > 0) {
       TIK_CHECK_ARG(b.c_in == net->blocks[i - 1].c_out, "block %d: c_in does not chain", i);
-      TIK_CHECK_ARG(net->K <= TIK_MAX_SLABS, "K");
       TIK_CHECK_ARG(b.res_kind == TIK_RES_NONE || b.res_kind == TIK_RES_IDENTITY || b.res_kind == TIK_RES_CONV, "block %d: res_kind", i);
     } else {
       TIK_CHECK_ARG(b.res_kind == TIK_RES_NONE || b.res_kind == TIK_RES_STEM, "block 0: residual must be none or stem-conv");
@@ -89,12 +95,10 @@ static int check_net(const TikNet* net, int dtype) {
   return TIK_OK;
 }
 
-static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
-
-static void ws_layout(const TikNet* net, int dtype, int64_t n, int T, WsLayout* L, int* t_out_final) {
+static void ws_layout(const TikNet* net, int dtype, int64_t n, int64_t n_max, int T, WsLayout* L, int* t_out_final) {
   const int64_t V = net->V;
   int t = T;
-  int64_t x = 0, a = 0, h = 0;
+  int64_t x = 0, a = 0, h = 0, r0 = 0;
   for (int i = 0; i < net->n_blocks; ++i) {
     const TikBlock& b = net->blocks[i];
     if (i > 0) {
@@ -103,26 +107,93 @@ static void ws_layout(const TikNet* net, int dtype, int64_t n, int T, WsLayout* 
     }
     h = std::max<int64_t>(h, V * t * b.c_out);
     t = out_frames(t, b.stride);
-    x = std::max<int64_t>(x, V * t * b.c_out);
+    if (i == 0 && b.res_kind == TIK_RES_STEM) r0 = V * t * b.c_out;
+    if (i + 1 < net->n_blocks) x = std::max<int64_t>(x, V * t * b.c_out);
   }
   *t_out_final = t;
-  L->x_elems = x; L->agg_elems = a; L->h_elems = h;
-  L->z_elems = net->head_hidden > 0 ? (int64_t)t * net->head_hidden : 0;
   const int64_t es = dtype == TIK_BF16 ? 2 : 4;
+  const int64_t feat = V * t * net->blocks[net->n_blocks - 1].c_out;
+  const int64_t z = net->head_hidden > 0 ? (int64_t)t * net->head_hidden : 0;
   int64_t off = 0;
   L->off_x0 = off; off = align_up(off + x * n * es, 1024);
   L->off_x1 = off; off = align_up(off + x * n * es, 1024);
   L->off_agg = off; off = align_up(off + a * n * es, 1024);
   L->off_h = off; off = align_up(off + h * n * es, 1024);
-  L->off_z = off; off = align_up(off + L->z_elems * n * es, 1024);
+  L->off_r0 = off; off = align_up(off + r0 * n * es, 1024);
+  L->off_feat = off; off = align_up(off + feat * n_max * es, 1024);
+  L->off_z = off; off = align_up(off + z * n_max * es, 1024);
   L->total_bytes = off;
+}
+
+static int run_step(TikPlan* P, Step& st, const float* xc, int64_t n, int64_t clip_off, float* poses, cudaStream_t s) {
+  const TikNet& net = P->net;
+  const int V = net.V;
+  if (st.kind == Step::STEM) {
+    const TikBlock& b = *st.blk;
+    return tik_stem_gcn(P->dtype, xc, net.in_scale_dev, net.in_shift_dev, b.agg_dev, reinterpret_cast<const float*>(b.w_gcn_dev),
+                        b.b_gcn_dev, st.dst, st.dst2 ? b.w_res_stem_dev : nullptr, st.dst2, b.stride, n, st.t, V, b.c_in, net.K,
+                        b.c_out, 1, s);
+  }
+  if (st.kind == Step::AGG) {
+    // planes are spaced for a full chunk (the tensor maps are baked for n_chunk clips)
+    return tik_aggregate(P->dtype, st.src, st.blk->agg_dev, st.dst, P->n_chunk, st.t, V, st.c, net.K, s);
+  }
+  TikRowGemm g = st.g;
+  if (g.v == 1) {             // head: rows = n * T'
+    g.t_out = (int32_t)(n * P->T_out);
+    g.slabs[0].t_in = g.t_out;
+  } else {
+    g.nv = n * V;
+  }
+  if (st.out_is_feat) g.out_dev = P->feat + clip_off * P->feat_elems_per_clip * (int64_t)P->es;
+  if (st.out_is_poses) g.out_dev = poses;
+  return P->dtype == TIK_BF16 ? umma_launch(st.prep, &g, s) : rowgemm_f32(&g, s);
+}
+
+static int run_impl(TikPlan* P, const float* x, int64_t N, float* poses, void* feat_out, cudaStream_t s,
+                    std::vector<cudaEvent_t>* events, std::vector<std::pair<Step*, int64_t>>* trace) {
+  const TikNet& net = P->net;
+  const int V = net.V, T = P->T;
+  auto mark = [&](Step* st, int64_t n) -> int {
+    if (!events) return TIK_OK;
+    cudaEvent_t e;
+    TIK_CUDA(cudaEventCreate(&e));
+    TIK_CUDA(cudaEventRecord(e, s));
+    events->push_back(e);
+    if (st) trace->push_back({st, n});
+    return TIK_OK;
+  };
+  for (int64_t b0 = 0; b0 < N; b0 += P->n_max) {
+    const int64_t nb = std::min<int64_t>(P->n_max, N - b0);
+    for (int64_t n0 = 0; n0 < nb; n0 += P->n_chunk) {
+      const int64_t n = std::min<int64_t>(P->n_chunk, nb - n0);
+      const float* xc = x + (b0 + n0) * (int64_t)T * V * net.c_in;
+      for (auto& st : P->chunk_steps) {
+        int rc = mark(&st, n);
+        if (rc != TIK_OK) return rc;
+        rc = run_step(P, st, xc, n, n0, nullptr, s);
+        if (rc != TIK_OK) return rc;
+      }
+    }
+    for (auto& st : P->batch_steps) {
+      int rc = mark(&st, nb);
+      if (rc != TIK_OK) return rc;
+      rc = run_step(P, st, nullptr, nb, 0, poses ? poses + b0 * (int64_t)P->T_out * net.head_out : nullptr, s);
+      if (rc != TIK_OK) return rc;
+    }
+    if (feat_out) {
+      TIK_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(feat_out) + b0 * P->feat_elems_per_clip * (int64_t)P->es, P->feat,
+                               (size_t)(nb * P->feat_elems_per_clip) * P->es, cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  return mark(nullptr, 0);
 }
 
 }  // namespace tik
 
 extern "C" {
 
-int tik_version(void) { return 100; }
+int tik_version(void) { return 101; }
 const char* tik_last_error(void) { return tik::g_err; }
 
 int tik_check_device(void) {
@@ -145,40 +216,43 @@ int tik_stgcn_out_frames(const TikNet* net, int T) {
   return t;
 }
 
-int tik_stgcn_workspace_bytes(const TikNet* net, int dtype, int64_t n_chunk, int T, int64_t* bytes) {
+int tik_stgcn_workspace_bytes(const TikNet* net, int dtype, int64_t n_chunk, int64_t n_max, int T, int64_t* bytes) {
   using namespace tik;
   int rc = check_net(net, dtype);
   if (rc != TIK_OK) return rc;
-  TIK_CHECK_ARG(n_chunk >= 1 && T >= 1 && bytes, "bad arguments");
+  TIK_CHECK_ARG(n_chunk >= 1 && n_max >= n_chunk && T >= 1 && bytes, "bad arguments");
   WsLayout L;
   int tf;
-  ws_layout(net, dtype, n_chunk, T, &L, &tf);
+  ws_layout(net, dtype, n_chunk, n_max, T, &L, &tf);
   *bytes = L.total_bytes;
   return TIK_OK;
 }
 
-int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int T, void* workspace, int64_t ws_bytes,
-                          TikPlan** plan_out) {
+int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int64_t n_max, int T, void* workspace,
+                          int64_t ws_bytes, TikPlan** plan_out) {
   using namespace tik;
   int rc = check_net(net, dtype);
   if (rc != TIK_OK) return rc;
-  TIK_CHECK_ARG(n_chunk >= 1 && T >= 1 && plan_out, "bad arguments");
+  TIK_CHECK_ARG(n_chunk >= 1 && n_max >= n_chunk && T >= 1 && plan_out, "bad arguments");
   WsLayout L;
   int tf;
-  ws_layout(net, dtype, n_chunk, T, &L, &tf);
+  ws_layout(net, dtype, n_chunk, n_max, T, &L, &tf);
   if (!workspace || ws_bytes < L.total_bytes) {
     set_error("workspace of %lld bytes is smaller than the %lld bytes this plan needs", (long long)ws_bytes, (long long)L.total_bytes);
     return TIK_ERR_WORKSPACE;
   }
   TIK_CHECK_ARG(((uintptr_t)workspace & 1023) == 0, "workspace must be 1024-byte aligned");
+  TIK_CHECK_ARG(n_max * tf < (1ll << 31), "n_max * T' too large for one head launch");
   TikPlan* P = new TikPlan();
-  P->net = *net; P->dtype = dtype; P->n_chunk = n_chunk; P->T = T; P->T_out = tf;
+  P->net = *net; P->dtype = dtype; P->n_chunk = n_chunk; P->n_max = n_max; P->T = T; P->T_out = tf;
   P->es = dtype == TIK_BF16 ? 2 : 4;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   void* xbuf[2] = {ws + L.off_x0, ws + L.off_x1};
   void* agg = ws + L.off_agg;
   void* hbuf = ws + L.off_h;
+  void* r0buf = ws + L.off_r0;
   void* zbuf = ws + L.off_z;
+  P->feat = ws + L.off_feat;
   const int V = net->V, K = net->K;
   const int64_t nv = n_chunk * V;
   int t = T;
@@ -190,10 +264,11 @@ int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int T, 
     const bool last = i == net->n_blocks - 1;
     if (i == 0) {
       Step s; s.kind = Step::STEM; s.dst = hbuf; s.t = t; s.blk = &b;
-      P->steps.push_back(s);
+      s.dst2 = b.res_kind == TIK_RES_STEM ? r0buf : nullptr;
+      P->chunk_steps.push_back(s);
     } else {
       Step s; s.kind = Step::AGG; s.src = xbuf[cur]; s.dst = agg; s.t = t; s.c = b.c_in; s.blk = &b;
-      P->steps.push_back(s);
+      P->chunk_steps.push_back(s);
       Step g; g.kind = Step::GEMM; memset(&g.g, 0, sizeof(g.g));
       g.g.n_slabs = K;
       for (int k = 0; k < K; ++k)
@@ -202,7 +277,7 @@ int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int T, 
       g.g.nv = nv; g.g.v = V; g.g.t_out = t; g.g.c_out = b.c_out; g.g.c_out_valid = b.c_out;
       g.g.act = TIK_ACT_RELU; g.g.res_kind = TIK_RES_NONE;
       g.g.out_dev = hbuf; g.g.out_layout = TIK_OUT_NODE_MAJOR;
-      P->steps.push_back(g);
+      P->chunk_steps.push_back(g);
     }
     Step c; c.kind = Step::GEMM; memset(&c.g, 0, sizeof(c.g));
     int ns = 0;
@@ -213,100 +288,53 @@ int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int T, 
     c.g.nv = nv; c.g.v = V; c.g.t_out = t_o; c.g.c_out = b.c_out; c.g.c_out_valid = b.c_out;
     c.g.act = TIK_ACT_RELU;
     if (b.res_kind == TIK_RES_IDENTITY) { c.g.res_kind = TIK_RES_IDENTITY; c.g.res_dev = xbuf[cur]; }
-    else if (b.res_kind == TIK_RES_STEM) {
-      c.g.res_kind = TIK_RES_STEM; c.g.res_dev = nullptr; c.src_is_input = true;
-      c.g.res_w_dev = b.w_res_stem_dev; c.g.res_cin = b.c_in; c.g.res_t_mul = b.stride; c.g.res_t_in = t;
-    } else c.g.res_kind = TIK_RES_NONE;
+    else if (b.res_kind == TIK_RES_STEM) { c.g.res_kind = TIK_RES_IDENTITY; c.g.res_dev = r0buf; }   // precomputed by the stem
+    else c.g.res_kind = TIK_RES_NONE;
     const int nxt = (i == 0) ? 0 : cur ^ 1;
-    c.g.out_dev = xbuf[nxt];
-    c.g.out_layout = last ? TIK_OUT_TIME_MAJOR : TIK_OUT_NODE_MAJOR;
-    P->steps.push_back(c);
+    if (last) {
+      c.g.out_dev = nullptr; c.out_is_feat = true; c.g.out_layout = TIK_OUT_TIME_MAJOR;
+      P->c_last = b.c_out;
+    } else {
+      c.g.out_dev = xbuf[nxt]; c.g.out_layout = TIK_OUT_NODE_MAJOR;
+    }
+    P->chunk_steps.push_back(c);
     cur = nxt;
     t = t_o;
-    if (last) { P->feat = xbuf[nxt]; P->c_last = b.c_out; }
   }
   P->feat_elems_per_clip = (int64_t)tf * V * P->c_last;
   if (net->head_hidden > 0) {
     const int feat_c = V * P->c_last;
+    const int32_t rows = (int32_t)(n_max * tf);
     Step h1; h1.kind = Step::GEMM; memset(&h1.g, 0, sizeof(h1.g));
     h1.g.n_slabs = 1;
-    h1.g.slabs[0] = {P->feat, feat_c, (int32_t)(n_chunk * tf), 1, 0};
+    h1.g.slabs[0] = {P->feat, feat_c, rows, 1, 0};
     h1.g.w_dev = net->w1_dev; h1.g.bias_dev = net->b1_dev; h1.g.bias_per_node = 0;
-    h1.g.nv = 1; h1.g.v = 1; h1.g.t_out = (int32_t)(n_chunk * tf); h1.g.c_out = net->head_hidden; h1.g.c_out_valid = net->head_hidden;
+    h1.g.nv = 1; h1.g.v = 1; h1.g.t_out = rows; h1.g.c_out = net->head_hidden; h1.g.c_out_valid = net->head_hidden;
     h1.g.act = TIK_ACT_LEAKY; h1.g.slope = net->leaky_slope; h1.g.res_kind = TIK_RES_NONE;
     h1.g.out_dev = zbuf; h1.g.out_layout = TIK_OUT_NODE_MAJOR;
-    P->steps.push_back(h1);
+    P->batch_steps.push_back(h1);
     Step h2; h2.kind = Step::GEMM; memset(&h2.g, 0, sizeof(h2.g));
     h2.g.n_slabs = 1;
-    h2.g.slabs[0] = {zbuf, net->head_hidden, (int32_t)(n_chunk * tf), 1, 0};
+    h2.g.slabs[0] = {zbuf, net->head_hidden, rows, 1, 0};
     h2.g.w_dev = net->w2_dev; h2.g.bias_dev = net->b2_dev; h2.g.bias_per_node = 0;
-    h2.g.nv = 1; h2.g.v = 1; h2.g.t_out = (int32_t)(n_chunk * tf);
+    h2.g.nv = 1; h2.g.v = 1; h2.g.t_out = rows;
     h2.g.c_out = dtype == TIK_BF16 ? (int)align_up(net->head_out, 64) : net->head_out;
     h2.g.c_out_valid = net->head_out;
     h2.g.act = TIK_ACT_NONE; h2.g.res_kind = TIK_RES_NONE;
-    h2.g.out_dev = nullptr; h2.dst_is_output = true; h2.g.out_layout = TIK_OUT_ROWS_F32;
-    P->steps.push_back(h2);
+    h2.g.out_dev = nullptr; h2.out_is_poses = true; h2.g.out_layout = TIK_OUT_ROWS_F32;
+    P->batch_steps.push_back(h2);
   }
   if (dtype == TIK_BF16) {
-    for (auto& s : P->steps) {
-      if (s.kind != Step::GEMM) continue;
-      int rc2 = umma_prepare(&s.g, s.g.nv, &s.prep);
-      if (rc2 != TIK_OK) { delete P; return rc2; }
-    }
+    for (auto* v : {&P->chunk_steps, &P->batch_steps})
+      for (auto& s : *v) {
+        if (s.kind != Step::GEMM) continue;
+        TikRowGemm g = s.g;
+        if (!g.out_dev) g.out_dev = P->feat;    // placeholder, overridden at launch
+        int rc2 = umma_prepare(&g, g.nv, &s.prep);
+        if (rc2 != TIK_OK) { delete P; return rc2; }
+      }
   }
   *plan_out = P;
-  return TIK_OK;
-}
-
-static int run_impl(TikPlan* P, const float* x, int64_t N, float* poses, void* feat_out, cudaStream_t s,
-                    std::vector<cudaEvent_t>* events) {
-  using namespace tik;
-  const TikNet& net = P->net;
-  const int V = net.V, T = P->T;
-  for (int64_t n0 = 0; n0 < N; n0 += P->n_chunk) {
-    const int64_t n = std::min<int64_t>(P->n_chunk, N - n0);
-    const float* xc = x + n0 * (int64_t)T * V * net.c_in;
-    for (auto& st : P->steps) {
-      int rc = TIK_OK;
-      if (events) {
-        cudaEvent_t e;
-        TIK_CUDA(cudaEventCreate(&e));
-        TIK_CUDA(cudaEventRecord(e, s));
-        events->push_back(e);
-      }
-      if (st.kind == Step::STEM) {
-        const TikBlock& b = *st.blk;
-        rc = tik_stem_gcn(P->dtype, xc, net.in_scale_dev, net.in_shift_dev, b.agg_dev, reinterpret_cast<const float*>(b.w_gcn_dev),
-                          b.b_gcn_dev, st.dst, n, st.t, V, b.c_in, net.K, b.c_out, 1, s);
-      } else if (st.kind == Step::AGG) {
-        // planes are spaced for the full chunk (tensor maps are baked for n_chunk), so aggregate the full
-        // chunk capacity only when it is full; a partial last chunk still uses the chunk-capacity plane stride.
-        rc = tik_aggregate(P->dtype, st.src, st.blk->agg_dev, st.dst, P->n_chunk, st.t, V, st.c, net.K, s);
-      } else {
-        TikRowGemm g = st.g;
-        if (g.v == 1) {           // head: rows = n * T'
-          g.t_out = (int32_t)(n * P->T_out);
-          g.slabs[0].t_in = g.t_out;
-        } else {
-          g.nv = n * V;
-        }
-        if (st.src_is_input) g.res_dev = xc;
-        if (st.dst_is_output) g.out_dev = poses + n0 * (int64_t)P->T_out * net.head_out;
-        rc = P->dtype == TIK_BF16 ? umma_launch(st.prep, &g, s) : rowgemm_f32(&g, s);
-      }
-      if (rc != TIK_OK) return rc;
-    }
-    if (feat_out) {
-      TIK_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(feat_out) + n0 * P->feat_elems_per_clip * P->es, P->feat,
-                               (size_t)(n * P->feat_elems_per_clip) * P->es, cudaMemcpyDeviceToDevice, s));
-    }
-  }
-  if (events) {
-    cudaEvent_t e;
-    TIK_CUDA(cudaEventCreate(&e));
-    TIK_CUDA(cudaEventRecord(e, s));
-    events->push_back(e);
-  }
   return TIK_OK;
 }
 
@@ -314,7 +342,7 @@ int tik_stgcn_plan_run(TikPlan* P, const float* x, int64_t N, float* poses, void
   using namespace tik;
   TIK_CHECK_ARG(P && x && N >= 0, "bad arguments");
   TIK_CHECK_ARG(P->net.head_hidden == 0 || poses, "poses pointer required");
-  return run_impl(P, x, N, poses, feat_out, (cudaStream_t)stream, nullptr);
+  return run_impl(P, x, N, poses, feat_out, (cudaStream_t)stream, nullptr, nullptr);
 }
 
 int tik_stgcn_plan_profile(TikPlan* P, const float* x, int64_t N, float* poses, void* stream, double* ms_by_kind,
@@ -323,28 +351,25 @@ int tik_stgcn_plan_profile(TikPlan* P, const float* x, int64_t N, float* poses, 
   TIK_CHECK_ARG(P && x && N >= 0 && ms_by_kind && launches_by_kind && flops_gemm, "bad arguments");
   TIK_CHECK_ARG(P->net.head_hidden == 0 || poses, "poses pointer required");
   std::vector<cudaEvent_t> ev;
+  std::vector<std::pair<Step*, int64_t>> trace;
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = run_impl(P, x, N, poses, nullptr, s, &ev);
+  int rc = run_impl(P, x, N, poses, nullptr, s, &ev, &trace);
   if (rc != TIK_OK) return rc;
   TIK_CUDA(cudaStreamSynchronize(s));
   for (int k = 0; k < 3; ++k) { ms_by_kind[k] = 0; launches_by_kind[k] = 0; }
   *flops_gemm = 0;
-  size_t i = 0;
-  for (int64_t n0 = 0; n0 < N; n0 += P->n_chunk) {
-    const int64_t n = std::min<int64_t>(P->n_chunk, N - n0);
-    for (auto& st : P->steps) {
-      float ms = 0;
-      TIK_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
-      const int kind = st.kind == Step::STEM ? 0 : (st.kind == Step::AGG ? 1 : 2);
-      ms_by_kind[kind] += ms;
-      launches_by_kind[kind] += 1;
-      if (st.kind == Step::GEMM) {
-        double ktot = 0;
-        for (int q = 0; q < st.g.n_slabs; ++q) ktot += st.g.slabs[q].c;
-        const double rows = st.g.v == 1 ? (double)n * P->T_out : (double)n * P->net.V * st.g.t_out;
-        *flops_gemm += 2.0 * rows * ktot * st.g.c_out_valid;
-      }
-      ++i;
+  for (size_t i = 0; i < trace.size(); ++i) {
+    float ms = 0;
+    TIK_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+    Step& st = *trace[i].first;
+    const int64_t n = trace[i].second;
+    ms_by_kind[(int)st.kind] += ms;
+    launches_by_kind[(int)st.kind] += 1;
+    if (st.kind == Step::GEMM) {
+      double ktot = 0;
+      for (int q = 0; q < st.g.n_slabs; ++q) ktot += st.g.slabs[q].c;
+      const double rows = st.g.v == 1 ? (double)n * P->T_out : (double)n * P->net.V * st.g.t_out;
+      *flops_gemm += 2.0 * rows * ktot * st.g.c_out_valid;
     }
   }
   for (auto e : ev) cudaEventDestroy(e);
@@ -353,8 +378,12 @@ int tik_stgcn_plan_profile(TikPlan* P, const float* x, int64_t N, float* poses, 
 
 int64_t tik_stgcn_plan_launches(const TikPlan* P, int64_t N) {
   if (!P || N <= 0) return 0;
-  int64_t chunks = (N + P->n_chunk - 1) / P->n_chunk;
-  return chunks * (int64_t)P->steps.size();
+  int64_t total = 0;
+  for (int64_t b0 = 0; b0 < N; b0 += P->n_max) {
+    const int64_t nb = std::min<int64_t>(P->n_max, N - b0);
+    total += ((nb + P->n_chunk - 1) / P->n_chunk) * (int64_t)P->chunk_steps.size() + (int64_t)P->batch_steps.size();
+  }
+  return total;
 }
 
 void tik_stgcn_plan_destroy(TikPlan* P) { delete P; }

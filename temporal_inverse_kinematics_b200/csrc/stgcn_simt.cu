@@ -12,64 +12,6 @@ __device__ __forceinline__ float to_float(float v) { return v; }
 __device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 // ------------------------------------------------------------------------------------------------
-// Stem: data_bn -> aggregate over the graph -> (K*Cin -> Cout) -> +bias(node,channel) -> ReLU.
-// Reference: st_gcn_aaai18.py:119-125 (data_bn on channel index v*C+c), gconv_origin.py:56-65,
-// st_gcn_aaai18.py:178-179 (tcn.0 BN + ReLU), algebra in SURVEY.md Appendix B.
-// One CTA handles kStemFrames consecutive frames of one clip so that, for each node w, the CTA
-// writes a contiguous (frames x Cout) span of the node-major output.
-constexpr int kStemFrames = 8;
-constexpr int kStemThreads = 256;
-constexpr int kStemMaxV = 32;
-constexpr int kStemMaxKC = 40;  // K * Cin
-
-template <class OutT>
-__global__ void __launch_bounds__(kStemThreads)
-stem_gcn_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, const float* __restrict__ in_shift,
-                const float* __restrict__ agg, const float* __restrict__ w, const float* __restrict__ bias,
-                OutT* __restrict__ out, int T, int V, int Cin, int K, int Cout, int relu) {
-  extern __shared__ __align__(16) float smem[];
-  const int KC = K * Cin;
-  float* s_x = smem;                                  // [frames][V*Cin]   (after data_bn)
-  float* s_a = s_x + kStemFrames * V * Cin;           // [frames][V][K*Cin] aggregated
-  float* s_w = s_a + kStemFrames * V * KC;            // [Cout][K*Cin]
-  float* s_agg = s_w + Cout * KC;                     // [K][V][V]
-  const int tiles_t = (T + kStemFrames - 1) / kStemFrames;
-  const int64_t n = blockIdx.x / tiles_t;
-  const int t0 = (blockIdx.x % tiles_t) * kStemFrames;
-  const int nf = min(kStemFrames, T - t0);
-  const int VC = V * Cin;
-
-  for (int i = threadIdx.x; i < Cout * KC; i += kStemThreads) s_w[i] = __ldg(w + i);
-  for (int i = threadIdx.x; i < K * V * V; i += kStemThreads) s_agg[i] = __ldg(agg + i);
-  const float* gx = x + (n * T + t0) * (int64_t)VC;   // (N,T,V,C): frames contiguous
-  for (int i = threadIdx.x; i < nf * VC; i += kStemThreads) {
-    int vc = i % VC;
-    s_x[i] = __ldg(gx + i) * __ldg(in_scale + vc) + __ldg(in_shift + vc);
-  }
-  __syncthreads();
-  // aggregated input: a[f][w][k*Cin+ci] = sum_v agg[k][v][w] * x[f][v][ci]
-  for (int i = threadIdx.x; i < nf * V * KC; i += kStemThreads) {
-    int kc = i % KC, wv = (i / KC) % V, f = i / (KC * V);
-    int k = kc / Cin, ci = kc % Cin;
-    float acc = 0.f;
-    for (int v = 0; v < V; ++v) acc = fmaf(s_agg[(k * V + v) * V + wv], s_x[f * VC + v * Cin + ci], acc);
-    s_a[i] = acc;
-  }
-  __syncthreads();
-  // outputs: (w, f, c) with c fastest -> contiguous stores per (w): out[((n*V+w)*T + t0+f)*Cout + c]
-  const int total = V * nf * Cout;
-  for (int i = threadIdx.x; i < total; i += kStemThreads) {
-    int c = i % Cout, f = (i / Cout) % nf, wv = i / (Cout * nf);
-    const float* a = s_a + (f * V + wv) * KC;
-    const float* ww = s_w + c * KC;
-    float acc = __ldg(bias + wv * Cout + c);
-    for (int kc = 0; kc < KC; ++kc) acc = fmaf(ww[kc], a[kc], acc);
-    if (relu) acc = fmaxf(acc, 0.f);
-    out[((n * V + wv) * (int64_t)T + t0 + f) * Cout + c] = from_float<OutT>(acc);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Aggregation: out[k][(n,w),t,:] = sum_v agg[k][v][w] * x[(n,v),t,:]   (einsum of gconv_origin.py:63,
 // moved in front of the channel GEMM).  One thread owns one 16-byte channel vector of one (n,t) and
 // keeps the V input vectors in registers; zero entries of the adjacency are skipped with a
@@ -304,28 +246,6 @@ int rowgemm_f32(const TikRowGemm* d, cudaStream_t s) {
   return TIK_OK;
 }
 
-template <class T>
-static int launch_stem(const float* x, const float* sc, const float* sh, const float* agg, const float* w,
-                       const float* bias, void* out, int64_t N, int Tn, int V, int Cin, int K, int Cout, int relu,
-                       cudaStream_t s) {
-  size_t smem = sizeof(float) * ((size_t)kStemFrames * V * Cin + (size_t)kStemFrames * V * K * Cin +
-                                 (size_t)Cout * K * Cin + (size_t)K * V * V);
-  TIK_CHECK_ARG(smem <= 200 * 1024, "stem shared memory %zu too large", smem);
-  static bool attr_set[64] = {};
-  int dev = 0;
-  TIK_CUDA(cudaGetDevice(&dev));
-  if (!attr_set[dev & 63]) {   // the attribute is per device (and per template instantiation: static is per T)
-    TIK_CUDA(cudaFuncSetAttribute(stem_gcn_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set[dev & 63] = true;
-  }
-  int64_t blocks = N * ceil_div(Tn, kStemFrames);
-  TIK_CHECK_ARG(blocks < (1ll << 31), "grid too large");
-  stem_gcn_kernel<T><<<(unsigned)blocks, kStemThreads, smem, s>>>(x, sc, sh, agg, w, bias, reinterpret_cast<T*>(out),
-                                                                   Tn, V, Cin, K, Cout, relu);
-  TIK_LAUNCH_CHECK();
-  return TIK_OK;
-}
-
 template <class T, int V>
 static int launch_agg_v(const void* x, const float* agg, void* out, int64_t N, int Tn, int C, int K, cudaStream_t s) {
   constexpr int VN = Vec16<T>::N;
@@ -352,20 +272,6 @@ static int launch_agg(const void* x, const float* agg, void* out, int64_t N, int
 }  // namespace tik
 
 extern "C" {
-
-int tik_stem_gcn(int dtype, const float* x, const float* in_scale, const float* in_shift, const float* agg,
-                 const float* w, const float* bias, void* out, int64_t N, int T, int V, int Cin, int K, int Cout,
-                 int relu, void* stream) {
-  using namespace tik;
-  TIK_CHECK_ARG(x && in_scale && in_shift && agg && w && bias && out, "null pointer");
-  TIK_CHECK_ARG(N >= 0 && T > 0 && V > 0 && V <= kStemMaxV && Cin > 0 && K > 0 && K <= 5 && K * Cin <= kStemMaxKC && Cout > 0,
-                "stem: unsupported shape N=%lld T=%d V=%d Cin=%d K=%d Cout=%d", (long long)N, T, V, Cin, K, Cout);
-  if (N == 0) return TIK_OK;
-  if (dtype == TIK_F32) return launch_stem<float>(x, in_scale, in_shift, agg, w, bias, out, N, T, V, Cin, K, Cout, relu, (cudaStream_t)stream);
-  if (dtype == TIK_BF16) return launch_stem<__nv_bfloat16>(x, in_scale, in_shift, agg, w, bias, out, N, T, V, Cin, K, Cout, relu, (cudaStream_t)stream);
-  set_error("bad dtype %d", dtype);
-  return TIK_ERR_INVALID;
-}
 
 int tik_aggregate(int dtype, const void* x, const float* agg, void* out, int64_t N, int T, int V, int C, int K, void* stream) {
   using namespace tik;

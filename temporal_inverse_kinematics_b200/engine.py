@@ -164,17 +164,17 @@ class PackedNet:
 
 
 class Plan:
-    def __init__(self, packed, n_chunk, T):
+    def __init__(self, packed, n_chunk, n_max, T):
         lib = L.lib()
         self.packed = packed
-        self.n_chunk, self.T = n_chunk, T
+        self.n_chunk, self.n_max, self.T = n_chunk, n_max, T
         nbytes = L.i64(0)
-        L.check(lib.tik_stgcn_workspace_bytes(C.byref(packed.net), packed.code, n_chunk, T, C.byref(nbytes)))
+        L.check(lib.tik_stgcn_workspace_bytes(C.byref(packed.net), packed.code, n_chunk, n_max, T, C.byref(nbytes)))
         self.workspace = torch.empty(nbytes.value + 1024, dtype=torch.uint8, device=packed.device)
         base = (self.workspace.data_ptr() + 1023) // 1024 * 1024
         handle = L.vp()
-        L.check(lib.tik_stgcn_plan_create(C.byref(packed.net), packed.code, n_chunk, T, C.c_void_p(base), nbytes.value,
-                                          C.byref(handle)))
+        L.check(lib.tik_stgcn_plan_create(C.byref(packed.net), packed.code, n_chunk, n_max, T, C.c_void_p(base),
+                                          nbytes.value, C.byref(handle)))
         self.handle = handle
         self.T_out = lib.tik_stgcn_out_frames(C.byref(packed.net), T)
         self.workspace_bytes = nbytes.value
@@ -202,6 +202,9 @@ class Plan:
         feat = torch.empty((N, self.T_out, p.V * p.c_last), dtype=p.tdtype, device=x.device) if want_feat else None
         L.check(L.lib().tik_stgcn_plan_run(self.handle, L.ptr(x), N, L.ptr(poses), L.ptr(feat), L.stream_ptr(x.device)))
         return poses, feat
+
+
+MAX_HEAD_CLIPS = 16384   # clips whose features are kept for one head launch (143 MB in bf16 at T=64)
 
 
 def default_chunk(T):
@@ -237,9 +240,12 @@ class Engine:
             self._packed[dtype_name] = PackedNet(backbone, head, dtype_name)
         n_chunk = int(chunk) if chunk else default_chunk(T)
         n_chunk = max(1, min(n_chunk, N))
-        key = (dtype_name, n_chunk, T)
+        n_max = max(n_chunk, min(N, MAX_HEAD_CLIPS))
+        key = (dtype_name, n_chunk, n_max, T)
         if key not in self._plans:
-            self._plans[key] = Plan(self._packed[dtype_name], n_chunk, T)
+            if len(self._plans) >= 8:                                    # bound the workspaces kept alive
+                self._plans.pop(next(iter(self._plans)))
+            self._plans[key] = Plan(self._packed[dtype_name], n_chunk, n_max, T)
         return self._plans[key]
 
 

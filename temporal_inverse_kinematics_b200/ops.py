@@ -46,16 +46,19 @@ def aggregate(x, A_hat):
     return out
 
 
-def stem_gcn(x, in_scale, in_shift, A_hat, w, bias, out_dtype, relu=True):
-    """x (N,T,V,Cin) fp32 -> (N,V,T,Cout) out_dtype (data_bn + aggregate + channel mix + bias [+ReLU])."""
-    _dev(x, in_scale, in_shift, A_hat, w, bias)
+def stem_gcn(x, in_scale, in_shift, A_hat, w, bias, out_dtype, relu=True, res_w=None, res_stride=1):
+    """x (N,T,V,Cin) fp32 -> (N,V,T,Cout) out_dtype (data_bn + aggregate + channel mix + bias [+ReLU]);
+    with res_w (V,Cout,Cin) also returns the residual branch (N,V,T',Cout)."""
+    _dev(x, in_scale, in_shift, A_hat, w, bias, res_w)
     N, T, V, Cin = x.shape
     K = A_hat.shape[0]
     Cout = w.shape[0]
     out = torch.empty((N, V, T, Cout), dtype=out_dtype, device=x.device)
+    res = None if res_w is None else torch.empty((N, V, (T - 1) // res_stride + 1, Cout), dtype=out_dtype, device=x.device)
     L.check(L.lib().tik_stem_gcn(_code(out), L.ptr(x), L.ptr(in_scale), L.ptr(in_shift), L.ptr(A_hat), L.ptr(w), L.ptr(bias),
-                                 L.ptr(out), N, T, V, Cin, K, Cout, int(relu), L.stream_ptr(x.device)))
-    return out
+                                 L.ptr(out), L.ptr(res_w), L.ptr(res), res_stride, N, T, V, Cin, K, Cout, int(relu),
+                                 L.stream_ptr(x.device)))
+    return out if res_w is None else (out, res)
 
 
 def rowgemm(slabs, w, bias, nv, v, t_out, act="none", slope=0.01, residual=None, out_layout="node", c_out_valid=None,

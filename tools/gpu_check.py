@@ -129,6 +129,28 @@ def stage_umma():
     return ok
 
 
+def stage_shift():
+    """Experiment: can a 128B-swizzled K-major A operand start at an arbitrary ROW (not 1024 B) offset?"""
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(1)
+    a = torch.randn(1, 128, 64, generator=g).bfloat16()
+    w = (torch.randn(64, 64, generator=g) / 8).bfloat16()
+    b = torch.zeros(1, 64)
+    full = (a[0].float() @ w.float().t())
+    for shift in (1, 2, 8, 9, 17):
+        for mode in (0, 1):
+            lib.tik_debug_set_umma_shift(shift, mode)
+            y = ops.rowgemm([(a.cuda(), 1, 0)], w.cuda(), b.cuda(), 1, 1, 128, act="none")
+            torch.cuda.synchronize()
+            lib.tik_debug_set_umma_shift(0, 0)
+            got = y[0, :128 - shift].float().cpu()
+            want = full[shift:]
+            err = float((got - want).abs().max())
+            print(f"[shift] rows={shift} base_offset_mode={mode}: max err vs shifted rows {err:.3e} "
+                  f"(vs unshifted {float((got - full[:128 - shift]).abs().max()):.3e})", flush=True)
+    return True
+
+
 def stage_net():
     from temporal_inverse_kinematics_b200.pose_regressor import PoseRegressor, default_hparams
     ok = True
@@ -164,6 +186,6 @@ def stage_net():
 
 if __name__ == "__main__":
     stage = sys.argv[1]
-    ok = {"simt": stage_simt, "umma": stage_umma, "net": stage_net}[stage]()
+    ok = {"simt": stage_simt, "umma": stage_umma, "net": stage_net, "shift": stage_shift}[stage]()
     print(f"stage {stage}: {'PASS' if ok else 'FAIL'}")
     sys.exit(0 if ok else 1)
