@@ -44,6 +44,8 @@ constexpr int kSmemBudget = 225 * 1024;
 struct UmmaParams {
   CUtensorMap map_a[TIK_MAX_SLABS];
   CUtensorMap map_w;
+  CUtensorMap map_out;             // node-major output (c_out, t_out, nv) for the TMA-store epilogue
+  int32_t tma_store, off_stage;    // epilogue stages the tile in swizzled smem and stores it with TMA
   int32_t n_slabs;
   int32_t chunks[TIK_MAX_SLABS];   // c_s / 64
   int32_t t_mul[TIK_MAX_SLABS];
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
   uint8_t* w_res = smem;                                    // resident weights: total_chunks x (BN x 64) tiles
   uint8_t* ring = smem + p.off_ring;
   float* s_bias = reinterpret_cast<float*>(smem + p.off_bias);
+  uint8_t* s_stage = smem + p.off_stage;                    // BN/64 regions of 128 rows x 128 B (swizzled)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full = empty_bar + kMaxStages;             // [2]
@@ -94,6 +97,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.n_slabs; ++s) tma_prefetch_desc(&p.map_a[s]);
     tma_prefetch_desc(&p.map_w);
+    if (p.tma_store) tma_prefetch_desc(&p.map_out);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -200,6 +204,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
       else if (p.out_layout == TIK_OUT_TIME_MAJOR) { out_off = ((n * p.t_out + t) * p.v + node) * (int64_t)p.c_out; ld = p.c_out; }
       else { out_off = row * p.c_out_valid; ld = p.c_out_valid; }
 
+      if (p.tma_store) {
+        if (threadIdx.x == 64) tma_store_wait_read0();      // previous tile's store has finished reading the staging tile
+        named_bar_sync(1, 128);
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(lane_grp * 32) << 16);
@@ -208,7 +216,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
         uint32_t a32[32];
         tmem_ld32(tmem_d + (uint32_t)c0, a32);
         tmem_ld_wait();
-        if (!valid) continue;
+        if (!valid && !p.tma_store) continue;
         const int cg = n0 + c0;                    // first global output channel of this chunk
         float v[32];
 #pragma unroll
@@ -243,7 +251,19 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act, p.slope);
-        if (p.out_layout == TIK_OUT_ROWS_F32) {
+        if (p.tma_store) {
+          // 16 B pieces at their 128B-swizzle positions: piece index j within the 64-column region, XOR (row & 7)
+          uint8_t* reg = s_stage + (size_t)(c0 >> 6) * kABytes + (size_t)r * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+            const int j = ((c0 & 63) >> 3) + q;
+            *reinterpret_cast<uint4*>(reg + ((j ^ (r & 7)) << 4)) = u;
+          }
+        } else if (p.out_layout == TIK_OUT_ROWS_F32) {
           float* o = reinterpret_cast<float*>(p.out) + out_off;
           for (int j = 0; j < 32; ++j)
             if (cg + j < ld) o[cg + j] = v[j];
@@ -262,9 +282,20 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);         // 4 epilogue warps -> accumulator free again
+      if (p.tma_store) {
+        fence_proxy_async_smem();                           // st.shared -> visible to the TMA (async proxy)
+        named_bar_sync(1, 128);
+        if (threadIdx.x == 64) {
+          const int t0s = (int)(tm % p.tiles_t) * p.tt;
+          const int nv0s = (int)((tm / p.tiles_t) * p.vv);
+          for (int c = 0; c < BN / 64; ++c) tma_store_3d(&p.map_out, s_stage + (size_t)c * kABytes, n0 + c * 64, t0s, nv0s);
+          tma_store_commit();
+        }
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
+  if (p.tma_store && threadIdx.x == 64) tma_store_wait0();
   __syncwarp();
   tc_fence_before();
   __syncthreads();
@@ -394,7 +425,9 @@ int umma_prepare(const TikRowGemm* d, int64_t nv_capacity, UmmaPrepared** out) {
   const int bias_bytes = (int)align_up_i(bias_rows * d->c_out * 4, 16);
   const int bar_bytes = 256;
   const int w_bytes = p.total_chunks * b_bytes;
-  const int fixed = bias_bytes + bar_bytes;
+  p.tma_store = (d->out_layout == TIK_OUT_NODE_MAJOR && d->out_dev != nullptr) ? 1 : 0;
+  const int stage_out_bytes = p.tma_store ? (u->bn / 64) * kABytes : 0;
+  const int fixed = bias_bytes + bar_bytes + stage_out_bytes;
   int w_res = 0, stages = 0;
   if (p.n_tiles_n == 1 && w_bytes + 3 * kABytes + fixed <= kSmemBudget) {
     w_res = 1;
@@ -406,8 +439,17 @@ int umma_prepare(const TikRowGemm* d, int64_t nv_capacity, UmmaPrepared** out) {
   if (stages < 2) { delete u; set_error("bf16 path: bias table too large for shared memory"); return TIK_ERR_UNSUPPORTED; }
   p.w_resident = w_res; p.stages = stages;
   p.off_ring = w_res ? w_bytes : 0;
-  p.off_bias = p.off_ring + stages * (kABytes + (w_res ? 0 : b_bytes));
+  p.off_stage = p.off_ring + stages * (kABytes + (w_res ? 0 : b_bytes));
+  p.off_bias = p.off_stage + stage_out_bytes;
   p.off_bar = p.off_bias + bias_bytes;
+  if (p.tma_store) {
+    uint64_t dims[3] = {(uint64_t)d->c_out, (uint64_t)d->t_out, (uint64_t)nv_capacity};
+    uint64_t strides[2] = {(uint64_t)d->c_out * 2, (uint64_t)d->c_out * 2 * (uint64_t)d->t_out};
+    uint32_t box[3] = {(uint32_t)kChunkK, (uint32_t)tt, (uint32_t)vv};
+    uint32_t estr[3] = {1, 1, 1};
+    int rc = encode_map(&p.map_out, d->out_dev, 3, dims, strides, box, estr);
+    if (rc != TIK_OK) { delete u; return rc; }
+  }
   p.bias_rows = bias_rows;
   u->smem_bytes = p.off_bar + bar_bytes + 1024;
   u->nv_capacity = nv_capacity;
