@@ -154,6 +154,8 @@ typedef struct TikBlock {
   const void* w_tcn_dev;  /* (c_out, kt*c_out [+ c_in if res conv]) dtype */
   const float* b_tcn_dev; /* (1 or V, c_out) fp32 */
   const float* w_res_stem_dev; /* (V, c_out, c_in) fp32, block 0 conv residual only */
+  int32_t res_as_slab;    /* identity / stem residual folded into w_tcn as a trailing (c_out x c_out) identity block:
+                             the plan feeds the residual tensor as one more K-slab (exact in fp32 accumulate) */
 } TikBlock;
 #define TIK_RES_CONV 3
 
@@ -198,6 +200,8 @@ void tik_stgcn_plan_destroy(TikPlan* plan);
 /* Experiment hook, not used by the product path: makes the tensor-core kernel read its A operand `rows`
  * rows below the tile start (mode 1 also sets the descriptor's base-offset field).  See DESIGN.md. */
 int tik_debug_set_umma_shift(int rows, int mode);
+/* Probe hook: device buffer of 16 uint64 receiving a clock64 timeline of CTA 0 (NULL switches it off). */
+int tik_debug_set_umma_times(void* dev_buf16);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ class TikRowGemm(C.Structure):
 class TikBlock(C.Structure):
     _fields_ = [("c_in", i32), ("c_out", i32), ("stride", i32), ("kt", i32), ("res_kind", i32),
                 ("agg_dev", vp), ("w_gcn_dev", vp), ("b_gcn_dev", vp), ("w_tcn_dev", vp), ("b_tcn_dev", vp),
-                ("w_res_stem_dev", vp)]
+                ("w_res_stem_dev", vp), ("res_as_slab", i32)]
 
 
 class TikNet(C.Structure):
@@ -59,6 +59,7 @@ _PROTOS = {
     "tik_stgcn_plan_launches": (i64, [vp, i64]),
     "tik_stgcn_plan_destroy": (None, [vp]),
     "tik_debug_set_umma_shift": (C.c_int, [C.c_int, C.c_int]),
+    "tik_debug_set_umma_times": (C.c_int, [vp]),
 }
 
 _lib = None

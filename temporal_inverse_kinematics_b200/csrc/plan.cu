@@ -39,6 +39,7 @@ struct Step {
   const TikBlock* blk = nullptr;
   bool out_is_feat = false;   // GEMM: writes the batch-level feature buffer at the chunk's offset
   bool out_is_poses = false;  // GEMM: writes the caller's poses pointer
+  int k_identity = 0;         // GEMM: K columns that only carry an identity residual (not algorithmic FLOPs)
 };
 
 }  // namespace tik
@@ -77,6 +78,7 @@ static int check_net(const TikNet* net, int dtype) {
   for (int i = 0; i < net->n_blocks; ++i) {
     const TikBlock& b = net->blocks[i];
     TIK_CHECK_ARG(b.kt >= 1 && (b.kt % 2) == 1 && b.kt + 1 <= TIK_MAX_SLABS, "block %d: temporal kernel %d unsupported", i, b.kt);
+    TIK_CHECK_ARG(!b.res_as_slab || dtype == TIK_BF16, "block %d: res_as_slab is a tensor-core packing", i);
     TIK_CHECK_ARG(b.stride >= 1 && b.stride <= 8, "block %d: stride %d", i, b.stride);
     TIK_CHECK_ARG(b.c_out % cmul == 0, "block %d: c_out=%d must be a multiple of %d for this dtype", i, b.c_out, cmul);
     if (i > 0) {
@@ -283,11 +285,14 @@ int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int64_t
     int ns = 0;
     for (int dt = 0; dt < b.kt; ++dt) c.g.slabs[ns++] = {hbuf, b.c_out, t, b.stride, dt - pad};
     if (b.res_kind == TIK_RES_CONV) c.g.slabs[ns++] = {xbuf[cur], b.c_in, t, b.stride, 0};
+    if (b.res_as_slab && b.res_kind == TIK_RES_IDENTITY) { c.g.slabs[ns++] = {xbuf[cur], b.c_out, t_o, 1, 0}; c.k_identity = b.c_out; }
+    if (b.res_as_slab && b.res_kind == TIK_RES_STEM) { c.g.slabs[ns++] = {r0buf, b.c_out, t_o, 1, 0}; c.k_identity = b.c_out; }
     c.g.n_slabs = ns;
     c.g.w_dev = b.w_tcn_dev; c.g.bias_dev = b.b_tcn_dev; c.g.bias_per_node = (b.res_kind == TIK_RES_STEM) ? 1 : 0;
     c.g.nv = nv; c.g.v = V; c.g.t_out = t_o; c.g.c_out = b.c_out; c.g.c_out_valid = b.c_out;
     c.g.act = TIK_ACT_RELU;
-    if (b.res_kind == TIK_RES_IDENTITY) { c.g.res_kind = TIK_RES_IDENTITY; c.g.res_dev = xbuf[cur]; }
+    if (b.res_as_slab) c.g.res_kind = TIK_RES_NONE;
+    else if (b.res_kind == TIK_RES_IDENTITY) { c.g.res_kind = TIK_RES_IDENTITY; c.g.res_dev = xbuf[cur]; }
     else if (b.res_kind == TIK_RES_STEM) { c.g.res_kind = TIK_RES_IDENTITY; c.g.res_dev = r0buf; }   // precomputed by the stem
     else c.g.res_kind = TIK_RES_NONE;
     const int nxt = (i == 0) ? 0 : cur ^ 1;
@@ -366,7 +371,7 @@ int tik_stgcn_plan_profile(TikPlan* P, const float* x, int64_t N, float* poses, 
     ms_by_kind[(int)st.kind] += ms;
     launches_by_kind[(int)st.kind] += 1;
     if (st.kind == Step::GEMM) {
-      double ktot = 0;
+      double ktot = -st.k_identity;
       for (int q = 0; q < st.g.n_slabs; ++q) ktot += st.g.slabs[q].c;
       const double rows = st.g.v == 1 ? (double)n * P->T_out : (double)n * P->net.V * st.g.t_out;
       *flops_gemm += 2.0 * rows * ktot * st.g.c_out_valid;

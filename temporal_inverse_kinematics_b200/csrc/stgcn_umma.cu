@@ -46,6 +46,7 @@ struct UmmaParams {
   CUtensorMap map_w;
   CUtensorMap map_out;             // node-major output (c_out, t_out, nv) for the TMA-store epilogue
   int32_t tma_store, off_stage;    // epilogue stages the tile in swizzled smem and stores it with TMA
+  int32_t stage_bufs;              // 1 or 2 staging tiles
   int32_t n_slabs;
   int32_t chunks[TIK_MAX_SLABS];   // c_s / 64
   int32_t t_mul[TIK_MAX_SLABS];
@@ -64,6 +65,8 @@ struct UmmaParams {
   int32_t act; float slope;
   int32_t res_kind; const void* res; const float* res_w; int32_t res_cin, res_t_mul, res_t_in;
   void* out; int32_t out_layout;
+  unsigned long long* dbg_times;   // probe hook: clock64 timeline of CTA 0 (tools/umma_probe.py)
+  int32_t dbg_flags;               // probe hook: 1 skip epilogue body, 2 skip residual, 4 skip MMAs, 8 skip A loads
   int32_t dbg_shift_rows, dbg_base_offset_mode;   // experiment hook: A operand read at a row offset (tik_debug_set_umma_shift)
 };
 
@@ -73,9 +76,12 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   return v;
 }
 
+#define TIK_T(i) do { if (p.dbg_times != nullptr && blockIdx.x == 0) p.dbg_times[i] = clock64(); } while (0)
+
 template <int BN>
 __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __grid_constant__ UmmaParams p) {
   constexpr int kBBytes = BN * kChunkK * 2;
+  if (threadIdx.x == 0) TIK_T(0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* w_res = smem;                                    // resident weights: total_chunks x (BN x 64) tiles
@@ -111,6 +117,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TIK_T(1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -131,13 +138,21 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
           for (int c = 0; c < p.chunks[s]; ++c, ++kw) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = ring + (size_t)stage * stage_bytes;
+            if (p.dbg_flags & 8) {
+              if (p.w_resident) { mbar_arrive(&full_bar[stage]); }
+              else { mbar_expect_tx(&full_bar[stage], (uint32_t)kBBytes); tma_load_2d(sa + kABytes, &p.map_w, &full_bar[stage], kw * kChunkK, n0); }
+              if (++stage == stages) { stage = 0; phase ^= 1; }
+              continue;
+            }
             mbar_expect_tx(&full_bar[stage], (uint32_t)(p.a_box_bytes + (p.w_resident ? 0 : kBBytes)));
             tma_load_3d(sa, &p.map_a[s], &full_bar[stage], c * kChunkK, ts, nv0);
             if (!p.w_resident) tma_load_2d(sa + kABytes, &p.map_w, &full_bar[stage], kw * kChunkK, n0);
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
         }
+        if (tile == blockIdx.x) TIK_T(2);
       }
+      TIK_T(11);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -153,13 +168,14 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
         for (int kc = 0; kc < p.total_chunks; ++kc) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (tile == blockIdx.x && kc == 0) TIK_T(3);
           const uint32_t sa = smem_u32(ring + (size_t)stage * stage_bytes);
           const uint32_t sb = p.w_resident ? smem_u32(w_res + (size_t)kc * kBBytes) : sa + kABytes;
           uint64_t da = make_smem_desc_kmajor_sw128(sa + (uint32_t)p.dbg_shift_rows * 128u);
           if (p.dbg_base_offset_mode) da |= (uint64_t)(((sa + (uint32_t)p.dbg_shift_rows * 128u) >> 7) & 7u) << 49;
           const uint64_t db = make_smem_desc_kmajor_sw128(sb);
 #pragma unroll
-          for (int k = 0; k < kChunkK / 16; ++k) {
+          for (int k = 0; k < ((p.dbg_flags & 4) ? 0 : kChunkK / 16); ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzled row: +2 in the (addr >> 4) field
             umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
           }
@@ -167,6 +183,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);                      // accumulator complete -> epilogue
+        if (tile == blockIdx.x) TIK_T(4);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -175,7 +192,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
     const int lane_grp = warp & 3;               // TMEM lanes [32*lane_grp, +32) are accessible to this warp
     const int r = lane_grp * 32 + lane;          // tile row == TMEM lane
     const int nv_l = r / p.tt, t_l = r - nv_l * p.tt;
+    const bool use_res = p.res_kind == TIK_RES_IDENTITY && !(p.dbg_flags & 2);
     int acc = 0; uint32_t acc_phase = 0;
+    int sbuf = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int64_t tm = tile / p.n_tiles_n;
       const int n0 = (int)(tile % p.n_tiles_n) * BN;
@@ -185,100 +204,72 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
       const int node = (int)(nv % p.v);
       const int64_t n = nv / p.v;
       const int64_t row = nv * p.t_out + t;
-      const float* bias = s_bias + (p.bias_per_node ? node * p.c_out : 0);
-      const __nv_bfloat16* res_row = nullptr;
-      float xin[8];
-      const float* rw = nullptr;
-      if (valid && p.res_kind == TIK_RES_IDENTITY) {
-        res_row = reinterpret_cast<const __nv_bfloat16*>(p.res) + row * p.c_out;
-      } else if (valid && p.res_kind == TIK_RES_STEM) {
-        const float* xp = reinterpret_cast<const float*>(p.res) +
-                          ((n * p.res_t_in + (int64_t)t * p.res_t_mul) * p.v + node) * p.res_cin;
-#pragma unroll
-        for (int ci = 0; ci < 8; ++ci) xin[ci] = ci < p.res_cin ? __ldg(xp + ci) : 0.f;
-        rw = p.res_w + (int64_t)node * p.c_out * p.res_cin;
-      }
+      const float* bias = s_bias + (p.bias_per_node ? node * p.c_out : 0) + n0;
+      const __nv_bfloat16* res_row = (valid && use_res) ? reinterpret_cast<const __nv_bfloat16*>(p.res) + row * p.c_out + n0 : nullptr;
       int64_t out_off;
-      int ld;
-      if (p.out_layout == TIK_OUT_NODE_MAJOR) { out_off = row * p.c_out; ld = p.c_out; }
-      else if (p.out_layout == TIK_OUT_TIME_MAJOR) { out_off = ((n * p.t_out + t) * p.v + node) * (int64_t)p.c_out; ld = p.c_out; }
-      else { out_off = row * p.c_out_valid; ld = p.c_out_valid; }
+      if (p.out_layout == TIK_OUT_NODE_MAJOR) out_off = row * p.c_out + n0;
+      else if (p.out_layout == TIK_OUT_TIME_MAJOR) out_off = ((n * p.t_out + t) * p.v + node) * (int64_t)p.c_out + n0;
+      else out_off = row * p.c_out_valid + n0;
+      uint8_t* stage_row = s_stage + (size_t)sbuf * (BN / 64) * kABytes + (size_t)r * 128;
 
       if (p.tma_store) {
-        if (threadIdx.x == 64) tma_store_wait_read0();      // previous tile's store has finished reading the staging tile
+        // the store issued from this staging buffer (stage_bufs tiles ago) must have finished reading it
+        if (threadIdx.x == 64) { if (p.stage_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read0(); }
         named_bar_sync(1, 128);
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (tile == blockIdx.x && threadIdx.x == 64) TIK_T(5);
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(lane_grp * 32) << 16);
+      if (!(p.dbg_flags & 1)) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t a32[32];
-        tmem_ld32(tmem_d + (uint32_t)c0, a32);
-        tmem_ld_wait();
-        if (!valid && !p.tma_store) continue;
-        const int cg = n0 + c0;                    // first global output channel of this chunk
-        float v[32];
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          uint32_t a32[64];
+          tmem_ld32(tmem_d + (uint32_t)c0, a32);
+          tmem_ld32(tmem_d + (uint32_t)c0 + 32u, a32 + 32);
+          tmem_ld_wait();
+          if (!valid && !p.tma_store) continue;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias + cg + 4 * q);
-          v[4 * q + 0] = __uint_as_float(a32[4 * q + 0]) + b4.x;
-          v[4 * q + 1] = __uint_as_float(a32[4 * q + 1]) + b4.y;
-          v[4 * q + 2] = __uint_as_float(a32[4 * q + 2]) + b4.z;
-          v[4 * q + 3] = __uint_as_float(a32[4 * q + 3]) + b4.w;
-        }
-        if (res_row != nullptr) {
+          for (int q = 0; q < 8; ++q) {          // 8 columns = one 16-byte bf16 piece
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + c0 + 8 * q);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias + c0 + 8 * q + 4);
+            float v[8] = {__uint_as_float(a32[8 * q + 0]) + b0.x, __uint_as_float(a32[8 * q + 1]) + b0.y,
+                          __uint_as_float(a32[8 * q + 2]) + b0.z, __uint_as_float(a32[8 * q + 3]) + b0.w,
+                          __uint_as_float(a32[8 * q + 4]) + b1.x, __uint_as_float(a32[8 * q + 5]) + b1.y,
+                          __uint_as_float(a32[8 * q + 6]) + b1.z, __uint_as_float(a32[8 * q + 7]) + b1.w};
+            if (res_row != nullptr) {            // slow path (scattered 16 B loads); the plan folds residuals into a K-slab
+              const uint4 u = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + 8 * q));
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 u = __ldg(reinterpret_cast<const uint4*>(res_row + cg) + q);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float2 f = __bfloat1622float2(h[e]);
-              v[q * 8 + 2 * e] += f.x;
-              v[q * 8 + 2 * e + 1] += f.y;
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h[e]);
+                v[2 * e] += f.x;
+                v[2 * e + 1] += f.y;
+              }
             }
-          }
-        } else if (rw != nullptr) {
-          for (int j = 0; j < 32; ++j) {
-            const float* wj = rw + (int64_t)(cg + j) * p.res_cin;
-            float a = v[j];
 #pragma unroll
-            for (int ci = 0; ci < 8; ++ci)
-              if (ci < p.res_cin) a = fmaf(__ldg(wj + ci), xin[ci], a);
-            v[j] = a;
-          }
-        }
+            for (int e = 0; e < 8; ++e) v[e] = apply_act(v[e], p.act, p.slope);
+            if (p.out_layout == TIK_OUT_ROWS_F32) {
+              float* o = reinterpret_cast<float*>(p.out) + out_off + c0 + 8 * q;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act, p.slope);
-        if (p.tma_store) {
-          // 16 B pieces at their 128B-swizzle positions: piece index j within the 64-column region, XOR (row & 7)
-          uint8_t* reg = s_stage + (size_t)(c0 >> 6) * kABytes + (size_t)r * 128;
+              for (int e = 0; e < 8; ++e)
+                if (n0 + c0 + 8 * q + e < p.c_out_valid) o[e] = v[e];
+            } else {
+              uint4 u;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 u;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
-            const int j = ((c0 & 63) >> 3) + q;
-            *reinterpret_cast<uint4*>(reg + ((j ^ (r & 7)) << 4)) = u;
-          }
-        } else if (p.out_layout == TIK_OUT_ROWS_F32) {
-          float* o = reinterpret_cast<float*>(p.out) + out_off;
-          for (int j = 0; j < 32; ++j)
-            if (cg + j < ld) o[cg + j] = v[j];
-        } else {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + cg;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 u;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
-            reinterpret_cast<uint4*>(o)[q] = u;
+              for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+              if (p.tma_store) {
+                // 16 B piece q of this row's 128 B line in region c0/64, at its 128B-swizzle position
+                *reinterpret_cast<uint4*>(stage_row + (size_t)(c0 >> 6) * kABytes + ((q ^ (r & 7)) << 4)) = u;
+              } else {
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + c0 + 8 * q) = u;
+              }
+            }
           }
         }
       }
+      if (tile == blockIdx.x && threadIdx.x == 64) TIK_T(6);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);         // 4 epilogue warps -> accumulator free again
@@ -288,14 +279,19 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
         if (threadIdx.x == 64) {
           const int t0s = (int)(tm % p.tiles_t) * p.tt;
           const int nv0s = (int)((tm / p.tiles_t) * p.vv);
-          for (int c = 0; c < BN / 64; ++c) tma_store_3d(&p.map_out, s_stage + (size_t)c * kABytes, n0 + c * 64, t0s, nv0s);
+          for (int c = 0; c < BN / 64; ++c)
+            tma_store_3d(&p.map_out, s_stage + ((size_t)sbuf * (BN / 64) + c) * kABytes, n0 + c * 64, t0s, nv0s);
           tma_store_commit();
+          if (tile == blockIdx.x) TIK_T(7);
         }
+        if (p.stage_bufs == 2) sbuf ^= 1;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
+  if (threadIdx.x == 64) TIK_T(8);
   if (p.tma_store && threadIdx.x == 64) tma_store_wait0();
+  if (threadIdx.x == 64) TIK_T(9);
   __syncwarp();
   tc_fence_before();
   __syncthreads();
@@ -303,6 +299,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
     tc_fence_after();
     tmem_dealloc<2 * BN>(tmem_base);
   }
+  if (threadIdx.x == 64) TIK_T(10);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -378,6 +375,10 @@ static int launch_variant(const UmmaParams& p, int smem_bytes, unsigned grid, cu
 int umma_prepare(const TikRowGemm* d, int64_t nv_capacity, UmmaPrepared** out) {
   TIK_CHECK_ARG(d->c_out % 64 == 0, "bf16 path: c_out=%d must be a multiple of 64", d->c_out);
   TIK_CHECK_ARG(nv_capacity >= d->nv && nv_capacity > 0, "nv capacity");
+  if (d->res_kind == TIK_RES_STEM) {
+    set_error("bf16 path: TIK_RES_STEM is only implemented by the fp32 kernel (the stem kernel precomputes that branch)");
+    return TIK_ERR_UNSUPPORTED;
+  }
   UmmaPrepared* u = new UmmaPrepared();
   UmmaParams& p = u->p;
   memset(&p, 0, sizeof(p));
@@ -426,7 +427,8 @@ int umma_prepare(const TikRowGemm* d, int64_t nv_capacity, UmmaPrepared** out) {
   const int bar_bytes = 256;
   const int w_bytes = p.total_chunks * b_bytes;
   p.tma_store = (d->out_layout == TIK_OUT_NODE_MAJOR && d->out_dev != nullptr) ? 1 : 0;
-  const int stage_out_bytes = p.tma_store ? (u->bn / 64) * kABytes : 0;
+  p.stage_bufs = u->bn >= 256 ? 1 : 2;
+  const int stage_out_bytes = p.tma_store ? p.stage_bufs * (u->bn / 64) * kABytes : 0;
   const int fixed = bias_bytes + bar_bytes + stage_out_bytes;
   int w_res = 0, stages = 0;
   if (p.n_tiles_n == 1 && w_bytes + 3 * kABytes + fixed <= kSmemBudget) {
@@ -457,11 +459,12 @@ int umma_prepare(const TikRowGemm* d, int64_t nv_capacity, UmmaPrepared** out) {
   return TIK_OK;
 }
 
-static int g_dbg_shift_rows = 0, g_dbg_base_offset_mode = 0;
+static int g_dbg_shift_rows = 0, g_dbg_base_offset_mode = 0, g_dbg_flags = 0;
+static unsigned long long* g_dbg_times = nullptr;
 
 int umma_launch(UmmaPrepared* u, const TikRowGemm* d, cudaStream_t s) {
   UmmaParams& p = u->p;
-  p.dbg_shift_rows = g_dbg_shift_rows; p.dbg_base_offset_mode = g_dbg_base_offset_mode;
+  p.dbg_shift_rows = g_dbg_shift_rows; p.dbg_base_offset_mode = g_dbg_base_offset_mode; p.dbg_flags = g_dbg_flags; p.dbg_times = g_dbg_times;
   TIK_CHECK_ARG(d->nv <= u->nv_capacity, "nv exceeds prepared capacity");
   p.nv = d->nv; p.v = d->v; p.t_out = d->t_out; p.c_out = d->c_out; p.c_out_valid = d->c_out_valid;
   p.bias = d->bias_dev; p.bias_per_node = d->bias_per_node;
@@ -496,6 +499,11 @@ int rowgemm_bf16(const TikRowGemm* d, cudaStream_t s) {
 // descriptor's base-offset field either 0 (mode 0) or (start_address >> 7) & 7 (mode 1).
 extern "C" int tik_debug_set_umma_shift(int rows, int mode) {
   tik::g_dbg_shift_rows = rows;
-  tik::g_dbg_base_offset_mode = mode;
+  tik::g_dbg_base_offset_mode = mode & 0xff;
+  tik::g_dbg_flags = mode >> 8;      // probe flags ride in the upper bits (tools/umma_probe.py)
+  return TIK_OK;
+}
+extern "C" int tik_debug_set_umma_times(void* dev_buf16) {
+  tik::g_dbg_times = reinterpret_cast<unsigned long long*>(dev_buf16);
   return TIK_OK;
 }

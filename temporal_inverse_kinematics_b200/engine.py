@@ -111,12 +111,19 @@ class PackedNet:
             if blk.residual_kind == "conv":
                 res_conv, res_bn = blk.residual[0], blk.residual[1]
             wt, bt, wr = fold_tcn(blk.tcn[2], blk.tcn[3], res_conv, res_bn)
+            # tensor-core path: identity-type residuals ride through the MMA as one more K-slab against an
+            # identity weight block (bf16 x 1.0 accumulated in fp32 is exact) instead of scattered epilogue loads
+            fold_identity = self.code == L.TIK_BF16
+            eye = torch.eye(blk.out_channels, dtype=torch.float64, device=dev)
             if blk.residual_kind == "none":
                 b.res_kind = L.RES_NONE
             elif blk.residual_kind == "identity":
                 if i == 0:
                     raise NotImplementedError("an identity residual on the first block is not supported by the CUDA path")
                 b.res_kind = L.RES_IDENTITY
+                if fold_identity:
+                    wt = torch.cat([wt, eye], dim=1)
+                    b.res_as_slab = 1
             elif i == 0:
                 if cin0 > 8:
                     raise NotImplementedError("first-block residual convolution needs in_channels <= 8")
@@ -124,6 +131,9 @@ class PackedNet:
                 s0v, o0v = s0.view(V, cin0), o0.view(V, cin0)
                 b.w_res_stem_dev = self._f32(wr[None, :, :] * s0v[:, None, :], f"b{i}.w_res_stem")  # (V, Cout, Cin)
                 bt = bt[None, :] + torch.einsum("ci,vi->vc", wr, o0v)                    # (V, Cout)
+                if fold_identity:
+                    wt = torch.cat([wt, eye], dim=1)
+                    b.res_as_slab = 1
             else:
                 b.res_kind = L.RES_CONV
                 wt = torch.cat([wt, wr], dim=1)

@@ -65,7 +65,10 @@ def forward(packed, x):
             residual = cur
         elif b.res_kind == 2:
             xs = x[:, torch.arange(t_out) * b.stride]                                        # raw input frames
-            residual = torch.einsum("vci,ntvi->nvtc", t["b0.w_res_stem"], xs).reshape(N * V, t_out, b.c_out)
+            residual = torch.einsum("vci,ntvi->nvtc", t["b0.w_res_stem"], xs).reshape(N * V, t_out, b.c_out).to(q)
+        if b.res_as_slab:                                                                    # identity block in w_tcn
+            slabs.append((residual, 1, 0))
+            residual = None
         cur = rowgemm(slabs, t[f"b{i}.w_tcn"], t[f"b{i}.b_tcn"], V, t_out, "relu", residual, quant=q)
         T = t_out
     feat = cur.view(N, V, T, -1).permute(0, 2, 1, 3).reshape(N * T, -1)

@@ -45,8 +45,8 @@ def test_conversions_match_oracle(M):
     assert np.abs(back - gp.rotation_matrix_to_angle_axis(Rr.reshape(-1, 3, 3))).max() < TOL
     # size-independent properties: orthonormal, det +1, aa -> R -> aa round trip for |aa| < pi
     RtR = np.einsum("mab,mac->mbc", R, R)
-    assert np.abs(RtR - np.eye(3)).max() < 1e-5
-    assert np.abs(np.linalg.det(R.astype(np.float64)) - 1).max() < 1e-5
+    assert np.abs(RtR - np.eye(3)).max() < TOL
+    assert np.abs(np.linalg.det(R.astype(np.float64)) - 1).max() < TOL
     small = np.linalg.norm(aa, axis=1) < 3.0
     assert np.abs(back[small] - aa[small]).max() < 2e-3
 

@@ -58,7 +58,7 @@ def test_bf16_within_stated_tolerance(n, t, chunk):
     from temporal_inverse_kinematics_b200 import engine
     mc, _ = _model(dtype="bf16", cuda=False)
     emu = packed_emulator.forward(engine.PackedNet(mc.backbone, mc._head(), "bf16"), x)
-    assert float((y - emu).abs().max()) < 0.03
+    assert float((y - emu).abs().max()) < 0.05
 
 
 def test_dance_config1(golden):

@@ -94,4 +94,4 @@ def test_c_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(dll, name), name
     assert _lib.lib().tik_version() >= 100
-    assert ctypes.sizeof(_lib.TikSlab) == 24 and ctypes.sizeof(_lib.TikBlock) == 72
+    assert ctypes.sizeof(_lib.TikSlab) == 24 and ctypes.sizeof(_lib.TikBlock) == 80

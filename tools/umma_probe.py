@@ -1,0 +1,67 @@
+"""Where does a tensor-core tile spend its time?  Times one layer-shaped launch with parts switched off
+(probe flags of tik_debug_set_umma_shift): 1 = epilogue body off, 2 = residual off, 4 = MMAs off, 8 = A loads off."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from temporal_inverse_kinematics_b200 import _lib, ops  # noqa: E402
+
+
+def bench(fn, reps=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+def case(name, n, t_in, t_out, cin_slabs, c_out, stride, residual):
+    V = 17
+    nv = n * V
+    g = torch.Generator(device="cuda").manual_seed(0)
+    srcs = [torch.randn(nv, t_in, c, device="cuda", generator=g).bfloat16() for c in sorted(set(cin_slabs))]
+    by_c = {s.shape[-1]: s for s in srcs}
+    pad = (len(cin_slabs) - 1) // 2 if len(cin_slabs) >= 3 else 0
+    slabs = []
+    for i, c in enumerate(cin_slabs):
+        off = (i - 1) if (len(cin_slabs) >= 3 and i < 3) else 0
+        slabs.append((by_c[c], stride, off))
+    w = (torch.randn(c_out, sum(cin_slabs), device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.zeros(1, c_out, device="cuda")
+    res = torch.randn(nv, t_out, c_out, device="cuda", generator=g).bfloat16() if residual else None
+    lib = _lib.lib()
+    out = []
+    for flags in (0, 2, 1, 1 | 4, 1 | 8, 1 | 4 | 8):
+        lib.tik_debug_set_umma_shift(0, flags << 8)
+        us = bench(lambda: ops.rowgemm(slabs, w, b, nv, V, t_out, act="relu", residual=res))
+        out.append(f"flags={flags}: {us:7.1f}us")
+    lib.tik_debug_set_umma_shift(0, 0)
+    tb = torch.zeros(16, dtype=torch.int64, device="cuda")
+    lib.tik_debug_set_umma_times(_lib.ptr(tb))
+    for _ in range(3):
+        ops.rowgemm(slabs, w, b, nv, V, t_out, act="relu", residual=res)
+    torch.cuda.synchronize()
+    lib.tik_debug_set_umma_times(None)
+    tl = tb.cpu().tolist()
+    names = ["entry", "setup", "prod_tile0", "mma_full0", "mma_done0", "epi_full0", "epi_body0", "epi_store0", "epi_end", "store_wait",
+             "exit", "prod_end"]
+    print("   timeline(cycles from entry): " + ", ".join(f"{n}={tl[i] - tl[0]}" for i, n in enumerate(names) if tl[i]), flush=True)
+    tiles = -(-nv * t_out // 128)
+    print(f"{name}: tiles={tiles} | " + " | ".join(out), flush=True)
+
+
+if __name__ == "__main__":
+    case("b1 gcn  64->64  T64", 128, 64, 64, [64], 64, 1, False)
+    case("b1 tcn  3x64    T64 +res", 128, 64, 64, [64, 64, 64], 64, 1, True)
+    case("b3 gcn 128->128 T32", 128, 32, 32, [128], 128, 1, False)
+    case("b3 tcn  3x128   T32 +res", 128, 32, 32, [128, 128, 128], 128, 1, True)
+    case("b6 tcn  3x256+128 s2 T16->8", 128, 16, 8, [256, 256, 256, 128], 256, 2, False)
+    case("b3 tcn x4 clips", 512, 32, 32, [128, 128, 128], 128, 1, True)
