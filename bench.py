@@ -144,6 +144,7 @@ def run_ours(args):
     model = model.to(dev).set_compute_dtype(args.dtype)
     if args.chunk:
         model.chunk_clips = args.chunk
+    model.use_cuda_graph = not args.no_graph
     rest, parents = synth.make_rest_skeleton(), synth.SMPLX_BODY_PARENTS
 
     x_host = synth.make_clips(B, T, seed=1234 + rank).pin_memory()
@@ -227,7 +228,7 @@ def run_ours(args):
                 "dtype": args.dtype, "data": "synthetic",
                 "config": {"workload": f"configs[2]: B={B} clips/GPU, T={T}, {args.dtype} ST-GCN fwd (PoseRegressor, random-init "
                                        f"weights) + 22-joint body FK on {B * T_out} solved poses/GPU",
-                           "global_batch": world * B, "frames_per_step": world * B * T, "chunk_clips": plan.n_chunk,
+                           "global_batch": world * B, "frames_per_step": world * B * T, "chunk_clips": plan.n_chunk, "cuda_graph": bool(model.use_cuda_graph),
                            "l2": "flushed between timed steps (256 MiB memset)", "parallelism": f"dp{world}",
                            "gather": "NCCL all_gather of poses each step" if world > 1 else "none"},
                 "e2e": {"value": world * B * T / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
@@ -254,6 +255,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -37,7 +37,8 @@ namespace tik {
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                       // bf16 elements per K chunk = one 128 B swizzle row
 constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KB
-constexpr int kUmmaThreads = 192;
+constexpr int kEpiWarps = 8;                      // two warps per TMEM lane group, each takes half of the columns
+constexpr int kUmmaThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 225 * 1024;
 
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
   } else {
     // ===================== epilogue =====================
     const int lane_grp = warp & 3;               // TMEM lanes [32*lane_grp, +32) are accessible to this warp
+    const int half = (warp - 2) >> 2;            // which half of the tile's columns this warp handles
     const int r = lane_grp * 32 + lane;          // tile row == TMEM lane
     const int nv_l = r / p.tt, t_l = r - nv_l * p.tt;
     const bool use_res = p.res_kind == TIK_RES_IDENTITY && !(p.dbg_flags & 2);
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
       if (p.tma_store) {
         // the store issued from this staging buffer (stage_bufs tiles ago) must have finished reading it
         if (threadIdx.x == 64) { if (p.stage_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read0(); }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 32 * kEpiWarps);
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -223,14 +225,13 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(lane_grp * 32) << 16);
       if (!(p.dbg_flags & 1)) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 64) {
-          uint32_t a32[64];
+        for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+          uint32_t a32[32];
           tmem_ld32(tmem_d + (uint32_t)c0, a32);
-          tmem_ld32(tmem_d + (uint32_t)c0 + 32u, a32 + 32);
           tmem_ld_wait();
           if (!valid && !p.tma_store) continue;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {          // 8 columns = one 16-byte bf16 piece
+          for (int q = 0; q < 4; ++q) {          // 8 columns = one 16-byte bf16 piece
             const float4 b0 = *reinterpret_cast<const float4*>(bias + c0 + 8 * q);
             const float4 b1 = *reinterpret_cast<const float4*>(bias + c0 + 8 * q + 4);
             float v[8] = {__uint_as_float(a32[8 * q + 0]) + b0.x, __uint_as_float(a32[8 * q + 1]) + b0.y,
@@ -261,7 +262,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
               for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
               if (p.tma_store) {
                 // 16 B piece q of this row's 128 B line in region c0/64, at its 128B-swizzle position
-                *reinterpret_cast<uint4*>(stage_row + (size_t)(c0 >> 6) * kABytes + ((q ^ (r & 7)) << 4)) = u;
+                const int j = ((c0 & 63) >> 3) + q;
+                *reinterpret_cast<uint4*>(stage_row + (size_t)(c0 >> 6) * kABytes + ((j ^ (r & 7)) << 4)) = u;
               } else {
                 *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + c0 + 8 * q) = u;
               }
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);         // 4 epilogue warps -> accumulator free again
       if (p.tma_store) {
         fence_proxy_async_smem();                           // st.shared -> visible to the TMA (async proxy)
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 32 * kEpiWarps);
         if (threadIdx.x == 64) {
           const int t0s = (int)(tm % p.tiles_t) * p.tt;
           const int nv0s = (int)((tm / p.tiles_t) * p.vv);
@@ -427,17 +429,23 @@ int umma_prepare(const TikRowGemm* d, int64_t nv_capacity, UmmaPrepared** out) {
   const int bar_bytes = 256;
   const int w_bytes = p.total_chunks * b_bytes;
   p.tma_store = (d->out_layout == TIK_OUT_NODE_MAJOR && d->out_dev != nullptr) ? 1 : 0;
-  p.stage_bufs = u->bn >= 256 ? 1 : 2;
-  const int stage_out_bytes = p.tma_store ? p.stage_bufs * (u->bn / 64) * kABytes : 0;
-  const int fixed = bias_bytes + bar_bytes + stage_out_bytes;
-  int w_res = 0, stages = 0;
-  if (p.n_tiles_n == 1 && w_bytes + 3 * kABytes + fixed <= kSmemBudget) {
-    w_res = 1;
-    stages = (kSmemBudget - fixed - w_bytes) / kABytes;
-  } else {
-    stages = (kSmemBudget - fixed) / (kABytes + b_bytes);
+  // smem policy: a deep A ring matters most (>= 4 stages), then resident weights, then a second staging tile
+  const int one_stage_tile = p.tma_store ? (u->bn / 64) * kABytes : 0;
+  int w_res = 0, stages = 0, sbufs = 1;
+  auto ring_stages = [&](int wres, int sb) {
+    const int fixed_ = bias_bytes + bar_bytes + sb * one_stage_tile;
+    const int st = wres ? (kSmemBudget - fixed_ - w_bytes) / kABytes : (kSmemBudget - fixed_) / (kABytes + b_bytes);
+    return st > kMaxStages ? kMaxStages : st;
+  };
+  const int options[4][2] = {{1, 2}, {1, 1}, {0, 2}, {0, 1}};
+  for (int o = 0; o < 4; ++o) {
+    const int wres = options[o][0], sb = options[o][1];
+    if (wres && p.n_tiles_n != 1) continue;
+    const int st = ring_stages(wres, sb);
+    if (st >= (wres ? 4 : 3) || o == 3) { w_res = wres; sbufs = sb; stages = st; break; }
   }
-  if (stages > kMaxStages) stages = kMaxStages;
+  p.stage_bufs = sbufs;
+  const int stage_out_bytes = sbufs * one_stage_tile;
   if (stages < 2) { delete u; set_error("bf16 path: bias table too large for shared memory"); return TIK_ERR_UNSUPPORTED; }
   p.w_resident = w_res; p.stages = stages;
   p.off_ring = w_res ? w_bytes : 0;

@@ -188,6 +188,7 @@ class Plan:
         self.handle = handle
         self.T_out = lib.tik_stgcn_out_frames(C.byref(packed.net), T)
         self.workspace_bytes = nbytes.value
+        self._graphs = {}
         self._fin = weakref.finalize(self, lib.tik_stgcn_plan_destroy, handle)
 
     def launches(self, N):
@@ -204,6 +205,29 @@ class Plan:
         L.check(L.lib().tik_stgcn_plan_profile(self.handle, L.ptr(x), N, L.ptr(poses), L.stream_ptr(x.device), ms, cnt,
                                                C.byref(fl)))
         return {k: (ms[i], int(cnt[i])) for i, k in enumerate(("stem", "aggregate", "gemm"))}, fl.value
+
+    def run_graphed(self, x):
+        """Same as run(x)[0] but replays a CUDA graph of the launch sequence (one graph per input address and
+        batch size, at most 4 kept).  The result is copied out of the graph's static output, so callers own it."""
+        p = self.packed
+        key = (x.data_ptr(), x.shape[0])
+        entry = self._graphs.get(key)
+        if entry is None:
+            N = x.shape[0]
+            poses = torch.empty((N, self.T_out, p.head_out), dtype=torch.float32, device=x.device)
+
+            def enqueue():
+                L.check(L.lib().tik_stgcn_plan_run(self.handle, L.ptr(x), N, L.ptr(poses), None, L.stream_ptr(x.device)))
+            enqueue()                                                 # eager warm-up (function attributes, lazy init)
+            torch.cuda.current_stream(x.device).synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                enqueue()
+            if len(self._graphs) >= 4:
+                self._graphs.pop(next(iter(self._graphs)))
+            entry = self._graphs[key] = (graph, poses, x)             # x kept alive: the graph reads its address
+        entry[0].replay()
+        return entry[1].clone()
 
     def run(self, x, want_feat=False):
         p = self.packed

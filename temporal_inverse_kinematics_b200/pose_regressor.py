@@ -5,6 +5,7 @@ Mirrors reference pose_trainer.py:66-133 (PoseRegressor) and :136-144 (IKPoseTra
 (pose_trainer.py:146-260) is out of scope: the CUDA path is eval-only.
 """
 import argparse
+import os
 
 import torch
 import torch.nn as nn
@@ -38,6 +39,7 @@ class PoseRegressor(nn.Module, _ComputeDtypeMixin):
                                             nn.Linear(512, self.pose_dim))
         self.compute_dtype = _default_dtype()
         self.chunk_clips = None
+        self.use_cuda_graph = os.environ.get("TIK_CUDA_GRAPH", "0") == "1"   # replay the launch sequence as one graph
         self._engine = None
 
     def _head(self):
@@ -57,7 +59,8 @@ class PoseRegressor(nn.Module, _ComputeDtypeMixin):
         N, T = x.shape[0], x.shape[1]
         if N == 0:
             return {"poses": x.new_zeros((0, self.backbone.out_frames(T), self.pose_dim))}
-        poses, _ = self.plan_for(N, T).run(x)
+        plan = self.plan_for(N, T)
+        poses = plan.run_graphed(x) if self.use_cuda_graph else plan.run(x)[0]
         return {"poses": poses}
 
 

@@ -141,3 +141,16 @@ def test_errors_surface_as_exceptions():
     with pytest.raises(ValueError):
         m(torch.zeros(2, 9, 16, 3).cuda())                            # wrong node count
     assert m(torch.zeros(0, 9, 17, 3).cuda())["poses"].shape == (0, 1, 66)
+
+
+def test_cuda_graph_replay_matches_eager():
+    m, sd = _model(dtype="bf16")
+    x = synth.make_clips(6, 32, seed=5).cuda()
+    y0 = m(x)["poses"].clone()
+    m.use_cuda_graph = True
+    y1 = m(x)["poses"]
+    y2 = m(x)["poses"]
+    assert torch.equal(y0, y1) and torch.equal(y1, y2) and y1.data_ptr() != y2.data_ptr()
+    x2 = synth.make_clips(6, 32, seed=6).cuda()                          # new address -> new graph
+    want = sp.regressor_forward(sd, x2.cpu())["poses"]
+    assert float((m(x2)["poses"].cpu() - want).abs().max()) < TOL_BF16_ABS
