@@ -37,7 +37,7 @@ namespace tik {
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                       // bf16 elements per K chunk = one 128 B swizzle row
 constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KB
-constexpr int kEpiWarps = 8;                      // two warps per TMEM lane group, each takes half of the columns
+constexpr int kEpiWarps = 16;                     // four warps per TMEM lane group, each takes a quarter of the columns
 constexpr int kUmmaThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 225 * 1024;
@@ -79,7 +79,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
 
 #define TIK_T(i) do { if (p.dbg_times != nullptr && blockIdx.x == 0) p.dbg_times[i] = clock64(); } while (0)
 
-template <int BN>
+template <int BN, int ACT>
 __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __grid_constant__ UmmaParams p) {
   constexpr int kBBytes = BN * kChunkK * 2;
   if (threadIdx.x == 0) TIK_T(0);
@@ -128,11 +128,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
         for (int kc = 0; kc < p.total_chunks; ++kc) tma_load_2d(w_res + (size_t)kc * kBBytes, &p.map_w, w_full, kc * kChunkK, 0);
       }
       int stage = 0; uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int64_t tm = tile / p.n_tiles_n;
-        const int n0 = (int)(tile % p.n_tiles_n) * BN;
-        const int t0 = (int)(tm % p.tiles_t) * p.tt;
-        const int nv0 = (int)((tm / p.tiles_t) * p.vv);
+      for (int tile = blockIdx.x; tile < (int)num_tiles; tile += gridDim.x) {
+        const int tm = tile / p.n_tiles_n;
+        const int n0 = (tile - tm * p.n_tiles_n) * BN;
+        const int t0 = (tm % p.tiles_t) * p.tt;
+        const int nv0 = (tm / p.tiles_t) * p.vv;
         int kw = 0;
         for (int s = 0; s < p.n_slabs; ++s) {
           const int ts = t0 * p.t_mul[s] + p.t_off[s];
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
       if (p.w_resident) mbar_wait(w_full, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < (int)num_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);        // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -190,28 +190,33 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
     }
   } else {
     // ===================== epilogue =====================
+    // 16 warps: TMEM lane group (warp & 3) x column quarter; thread = one tile row x BN/4 columns.
+    constexpr int CW = BN / 4;
     const int lane_grp = warp & 3;               // TMEM lanes [32*lane_grp, +32) are accessible to this warp
-    const int half = (warp - 2) >> 2;            // which half of the tile's columns this warp handles
+    const int cq = (warp - 2) >> 2;              // column quarter
     const int r = lane_grp * 32 + lane;          // tile row == TMEM lane
     const int nv_l = r / p.tt, t_l = r - nv_l * p.tt;
     const bool use_res = p.res_kind == TIK_RES_IDENTITY && !(p.dbg_flags & 2);
+    const int ntn = p.n_tiles_n, tiles_t = p.tiles_t;
+    const int n_tiles = (int)num_tiles;
     int acc = 0; uint32_t acc_phase = 0;
     int sbuf = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int64_t tm = tile / p.n_tiles_n;
-      const int n0 = (int)(tile % p.n_tiles_n) * BN;
-      const int t = (int)(tm % p.tiles_t) * p.tt + t_l;
-      const int64_t nv = (tm / p.tiles_t) * p.vv + nv_l;
-      const bool valid = (nv_l < p.vv) && (nv < p.nv) && (t < p.t_out);
-      const int node = (int)(nv % p.v);
-      const int64_t n = nv / p.v;
-      const int64_t row = nv * p.t_out + t;
-      const float* bias = s_bias + (p.bias_per_node ? node * p.c_out : 0) + n0;
-      const __nv_bfloat16* res_row = (valid && use_res) ? reinterpret_cast<const __nv_bfloat16*>(p.res) + row * p.c_out + n0 : nullptr;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int tm = tile / ntn;
+      const int n0 = (tile - tm * ntn) * BN;
+      const int tile_nv = tm / tiles_t, tile_t = tm - tile_nv * tiles_t;
+      const int t = tile_t * p.tt + t_l;
+      const int nv = tile_nv * p.vv + nv_l;
+      const bool valid = (nv_l < p.vv) && (nv < (int)p.nv) && (t < p.t_out);
+      const int n = nv / p.v, node = nv - n * p.v;
+      const int64_t row = (int64_t)nv * p.t_out + t;
+      const int cb = cq * CW;                    // first column (within the tile) this thread handles
+      const float* bias = s_bias + (p.bias_per_node ? node * p.c_out : 0) + n0 + cb;
+      const __nv_bfloat16* res_row = (valid && use_res) ? reinterpret_cast<const __nv_bfloat16*>(p.res) + row * p.c_out + n0 + cb : nullptr;
       int64_t out_off;
-      if (p.out_layout == TIK_OUT_NODE_MAJOR) out_off = row * p.c_out + n0;
-      else if (p.out_layout == TIK_OUT_TIME_MAJOR) out_off = ((n * p.t_out + t) * p.v + node) * (int64_t)p.c_out + n0;
-      else out_off = row * p.c_out_valid + n0;
+      if (p.out_layout == TIK_OUT_NODE_MAJOR) out_off = row * p.c_out + n0 + cb;
+      else if (p.out_layout == TIK_OUT_TIME_MAJOR) out_off = (((int64_t)n * p.t_out + t) * p.v + node) * (int64_t)p.c_out + n0 + cb;
+      else out_off = row * p.c_out_valid + n0 + cb;
       uint8_t* stage_row = s_stage + (size_t)sbuf * (BN / 64) * kABytes + (size_t)r * 128;
 
       if (p.tma_store) {
@@ -219,72 +224,82 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
         if (threadIdx.x == 64) { if (p.stage_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read0(); }
         named_bar_sync(1, 32 * kEpiWarps);
       }
+      const bool t3 = (tile == (int)blockIdx.x + 3 * (int)gridDim.x) && threadIdx.x == 64;   // 4th tile of CTA 0: steady state
+      if (t3) TIK_T(12);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (t3) TIK_T(13);
       if (tile == blockIdx.x && threadIdx.x == 64) TIK_T(5);
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(lane_grp * 32) << 16);
-      if (!(p.dbg_flags & 1)) {
-#pragma unroll 1
-        for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
-          uint32_t a32[32];
-          tmem_ld32(tmem_d + (uint32_t)c0, a32);
-          tmem_ld_wait();
-          if (!valid && !p.tma_store) continue;
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN + cb) + ((uint32_t)(lane_grp * 32) << 16);
+      uint32_t a[CW];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {          // 8 columns = one 16-byte bf16 piece
-            const float4 b0 = *reinterpret_cast<const float4*>(bias + c0 + 8 * q);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias + c0 + 8 * q + 4);
-            float v[8] = {__uint_as_float(a32[8 * q + 0]) + b0.x, __uint_as_float(a32[8 * q + 1]) + b0.y,
-                          __uint_as_float(a32[8 * q + 2]) + b0.z, __uint_as_float(a32[8 * q + 3]) + b0.w,
-                          __uint_as_float(a32[8 * q + 4]) + b1.x, __uint_as_float(a32[8 * q + 5]) + b1.y,
-                          __uint_as_float(a32[8 * q + 6]) + b1.z, __uint_as_float(a32[8 * q + 7]) + b1.w};
-            if (res_row != nullptr) {            // slow path (scattered 16 B loads); the plan folds residuals into a K-slab
-              const uint4 u = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + 8 * q));
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+      for (int i = 0; i < CW / 16; ++i) tmem_ld16(tmem_d + (uint32_t)(16 * i), a + 16 * i);
+      tmem_ld_wait();
+      // the accumulator now lives in registers: hand the TMEM buffer back to the MMA warp right away
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if ((valid || p.tma_store) && !(p.dbg_flags & 1)) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(h[e]);
-                v[2 * e] += f.x;
-                v[2 * e + 1] += f.y;
-              }
+        for (int q = 0; q < CW / 8; ++q) {       // 8 columns = one 16-byte bf16 piece
+          const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * q);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * q + 4);
+          float v[8] = {__uint_as_float(a[8 * q + 0]) + b0.x, __uint_as_float(a[8 * q + 1]) + b0.y,
+                        __uint_as_float(a[8 * q + 2]) + b0.z, __uint_as_float(a[8 * q + 3]) + b0.w,
+                        __uint_as_float(a[8 * q + 4]) + b1.x, __uint_as_float(a[8 * q + 5]) + b1.y,
+                        __uint_as_float(a[8 * q + 6]) + b1.z, __uint_as_float(a[8 * q + 7]) + b1.w};
+          if (res_row != nullptr) {              // slow path (scattered 16 B loads); the plan folds residuals into a K-slab
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(res_row + 8 * q));
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(h[e]);
+              v[2 * e] += f.x;
+              v[2 * e + 1] += f.y;
             }
+          }
+          if (ACT == TIK_ACT_LEAKY) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = apply_act(v[e], p.act, p.slope);
-            if (p.out_layout == TIK_OUT_ROWS_F32) {
-              float* o = reinterpret_cast<float*>(p.out) + out_off + c0 + 8 * q;
+            for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * p.slope;
+          }
+          if (p.out_layout == TIK_OUT_ROWS_F32) {
+            float* o = reinterpret_cast<float*>(p.out) + out_off + 8 * q;
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if (n0 + c0 + 8 * q + e < p.c_out_valid) o[e] = v[e];
+            for (int e = 0; e < 8; ++e)
+              if (valid && n0 + cb + 8 * q + e < p.c_out_valid) o[e] = (ACT == TIK_ACT_RELU) ? fmaxf(v[e], 0.f) : v[e];
+          } else {
+            uint4 u;
+            if (ACT == TIK_ACT_RELU) {
+              u.x = pack_bf16x2_relu(v[0], v[1]); u.y = pack_bf16x2_relu(v[2], v[3]);
+              u.z = pack_bf16x2_relu(v[4], v[5]); u.w = pack_bf16x2_relu(v[6], v[7]);
             } else {
-              uint4 u;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-              if (p.tma_store) {
-                // 16 B piece q of this row's 128 B line in region c0/64, at its 128B-swizzle position
-                const int j = ((c0 & 63) >> 3) + q;
-                *reinterpret_cast<uint4*>(stage_row + (size_t)(c0 >> 6) * kABytes + ((j ^ (r & 7)) << 4)) = u;
-              } else {
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + c0 + 8 * q) = u;
-              }
+              u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+              u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+            }
+            if (p.tma_store) {
+              // 16 B piece j of this row's 128 B line in 64-column region (cb+8q)/64, at its 128B-swizzle position
+              const int col = cb + 8 * q;
+              const int j = (col & 63) >> 3;
+              *reinterpret_cast<uint4*>(stage_row + (size_t)(col >> 6) * kABytes + ((j ^ (r & 7)) << 4)) = u;
+            } else if (valid) {
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + 8 * q) = u;
             }
           }
         }
       }
       if (tile == blockIdx.x && threadIdx.x == 64) TIK_T(6);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);         // 4 epilogue warps -> accumulator free again
+      if (t3) TIK_T(14);
       if (p.tma_store) {
         fence_proxy_async_smem();                           // st.shared -> visible to the TMA (async proxy)
         named_bar_sync(1, 32 * kEpiWarps);
         if (threadIdx.x == 64) {
-          const int t0s = (int)(tm % p.tiles_t) * p.tt;
-          const int nv0s = (int)((tm / p.tiles_t) * p.vv);
-          for (int c = 0; c < BN / 64; ++c)
+          const int t0s = tile_t * p.tt;
+          const int nv0s = tile_nv * p.vv;
+          for (int c = 0; c < ((p.dbg_flags & 16) ? 0 : BN / 64); ++c)
             tma_store_3d(&p.map_out, s_stage + ((size_t)sbuf * (BN / 64) + c) * kABytes, n0 + c * 64, t0s, nv0s);
-          tma_store_commit();
+          if (!(p.dbg_flags & 16)) tma_store_commit();
           if (tile == blockIdx.x) TIK_T(7);
+          if (t3) TIK_T(15);
         }
         if (p.stage_bufs == 2) sbuf ^= 1;
       }
@@ -360,16 +375,16 @@ static int num_sms() {
   return sms[dev & 63];
 }
 
-template <int BN>
+template <int BN, int ACT>
 static int launch_variant(const UmmaParams& p, int smem_bytes, unsigned grid, cudaStream_t s) {
   static int attr_done[64] = {};
   int dev = 0;
   TIK_CUDA(cudaGetDevice(&dev));
   if (attr_done[dev & 63] < smem_bytes) {   // the attribute is per device
-    TIK_CUDA(cudaFuncSetAttribute(rowgemm_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048));
+    TIK_CUDA(cudaFuncSetAttribute(rowgemm_umma_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048));
     attr_done[dev & 63] = kSmemBudget + 2048;
   }
-  rowgemm_umma_kernel<BN><<<grid, kUmmaThreads, smem_bytes, s>>>(p);
+  rowgemm_umma_kernel<BN, ACT><<<grid, kUmmaThreads, smem_bytes, s>>>(p);
   TIK_LAUNCH_CHECK();
   return TIK_OK;
 }
@@ -485,9 +500,17 @@ int umma_launch(UmmaPrepared* u, const TikRowGemm* d, cudaStream_t s) {
   p.tiles_t = (int)ceil_div(d->t_out, p.tt);
   const int64_t tiles = p.tiles_m * p.n_tiles_n;
   const unsigned grid = (unsigned)std::min<int64_t>(tiles, num_sms());
-  if (u->bn == 64) return launch_variant<64>(p, u->smem_bytes, grid, s);
-  if (u->bn == 128) return launch_variant<128>(p, u->smem_bytes, grid, s);
-  return launch_variant<256>(p, u->smem_bytes, grid, s);
+  TIK_CHECK_ARG(tiles < (1ll << 31), "too many tiles");
+#define TIK_LAUNCH_BN(BN_)                                                                          \
+  do {                                                                                              \
+    if (d->act == TIK_ACT_RELU) return launch_variant<BN_, TIK_ACT_RELU>(p, u->smem_bytes, grid, s);    \
+    if (d->act == TIK_ACT_LEAKY) return launch_variant<BN_, TIK_ACT_LEAKY>(p, u->smem_bytes, grid, s);  \
+    return launch_variant<BN_, TIK_ACT_NONE>(p, u->smem_bytes, grid, s);                              \
+  } while (0)
+  if (u->bn == 64) TIK_LAUNCH_BN(64);
+  if (u->bn == 128) TIK_LAUNCH_BN(128);
+  TIK_LAUNCH_BN(256);
+#undef TIK_LAUNCH_BN
 }
 
 void umma_free(UmmaPrepared* u) { delete u; }

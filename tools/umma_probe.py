@@ -23,6 +23,14 @@ def bench(fn, reps=20):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
+NAMES = ["entry", "setup", "prod_tile0", "mma_full0", "mma_done0", "epi_full0", "epi_body0", "epi_store0", "epi_end", "store_wait",
+         "exit", "prod_end", "t3_start", "t3_full", "t3_body", "t3_store"]
+
+
+def _print_tl(fl, tl):
+    print(f"   flags={fl} timeline: " + ", ".join(f"{n}={tl[i] - tl[0]}" for i, n in enumerate(NAMES) if tl[i]), flush=True)
+
+
 def case(name, n, t_in, t_out, cin_slabs, c_out, stride, residual):
     V = 17
     nv = n * V
@@ -39,20 +47,29 @@ def case(name, n, t_in, t_out, cin_slabs, c_out, stride, residual):
     res = torch.randn(nv, t_out, c_out, device="cuda", generator=g).bfloat16() if residual else None
     lib = _lib.lib()
     out = []
-    for flags in (0, 2, 1, 1 | 4, 1 | 8, 1 | 4 | 8):
+    for flags in (0, 16, 1, 1 | 4 | 8):
         lib.tik_debug_set_umma_shift(0, flags << 8)
         us = bench(lambda: ops.rowgemm(slabs, w, b, nv, V, t_out, act="relu", residual=res))
         out.append(f"flags={flags}: {us:7.1f}us")
     lib.tik_debug_set_umma_shift(0, 0)
-    tb = torch.zeros(16, dtype=torch.int64, device="cuda")
-    lib.tik_debug_set_umma_times(_lib.ptr(tb))
-    for _ in range(3):
-        ops.rowgemm(slabs, w, b, nv, V, t_out, act="relu", residual=res)
-    torch.cuda.synchronize()
-    lib.tik_debug_set_umma_times(None)
-    tl = tb.cpu().tolist()
+    for fl in (0, 16):
+        tb = torch.zeros(16, dtype=torch.int64, device="cuda")
+        lib.tik_debug_set_umma_times(_lib.ptr(tb))
+        lib.tik_debug_set_umma_shift(0, fl << 8)
+        for _ in range(3):
+            ops.rowgemm(slabs, w, b, nv, V, t_out, act="relu", residual=res)
+        torch.cuda.synchronize()
+        lib.tik_debug_set_umma_times(None)
+        lib.tik_debug_set_umma_shift(0, 0)
+        tl = tb.cpu().tolist()
+        _print_tl(fl, tl)
+    tiles = -(-nv * t_out // 128)
+    print(f"{name}: tiles={tiles} | " + " | ".join(out), flush=True)
+    return
+    if True:
+        tl = []
     names = ["entry", "setup", "prod_tile0", "mma_full0", "mma_done0", "epi_full0", "epi_body0", "epi_store0", "epi_end", "store_wait",
-             "exit", "prod_end"]
+             "exit", "prod_end", "t3_start", "t3_full", "t3_body", "t3_store"]
     print("   timeline(cycles from entry): " + ", ".join(f"{n}={tl[i] - tl[0]}" for i, n in enumerate(names) if tl[i]), flush=True)
     tiles = -(-nv * t_out // 128)
     print(f"{name}: tiles={tiles} | " + " | ".join(out), flush=True)
