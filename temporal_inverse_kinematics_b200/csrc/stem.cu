@@ -13,7 +13,7 @@
 
 namespace tik {
 
-constexpr int kStemFrames = 8;
+constexpr int kStemFrames = 32;
 constexpr int kStemThreads = 256;
 constexpr int kStemMaxV = 32;
 constexpr int kStemMaxKC = 40;  // K * Cin
@@ -62,18 +62,21 @@ stem_gcn_kernel(const float* __restrict__ x, const float* __restrict__ in_scale,
       s_rw[(v * Cin + ci) * Cout + c] = __ldg(res_w + i);
     }
   }
+  float* s_bn = s_rw + (res_w != nullptr ? V * Cin * Cout : 0);   // [frames][V*Cin] after data_bn
   const float* gx = x + (n * T + t0) * (int64_t)VC;   // (N,T,V,C): frames contiguous
-  for (int i = threadIdx.x; i < nf * VC; i += kStemThreads) s_raw[i] = __ldg(gx + i);
+  for (int i = threadIdx.x; i < nf * VC; i += kStemThreads) {
+    const float raw = __ldg(gx + i);
+    const int vc = i % VC;
+    s_raw[i] = raw;
+    s_bn[i] = fmaf(raw, __ldg(in_scale + vc), __ldg(in_shift + vc));
+  }
   __syncthreads();
-  // aggregated input: a[f][w][k*Cin+ci] = sum_v agg[k][v][w] * (scale*x + shift)[f][v][ci]
+  // aggregated input: a[f][w][k*Cin+ci] = sum_v agg[k][v][w] * data_bn(x)[f][v][ci]
   for (int i = threadIdx.x; i < nf * V * KC; i += kStemThreads) {
     const int kc = i % KC, wv = (i / KC) % V, f = i / (KC * V);
     const int k = kc / Cin, ci = kc - k * Cin;
     float acc = 0.f;
-    for (int v = 0; v < V; ++v) {
-      const float xv = fmaf(s_raw[f * VC + v * Cin + ci], __ldg(in_scale + v * Cin + ci), __ldg(in_shift + v * Cin + ci));
-      acc = fmaf(s_agg[(k * V + v) * V + wv], xv, acc);
-    }
+    for (int v = 0; v < V; ++v) acc = fmaf(s_agg[(k * V + v) * V + wv], s_bn[f * VC + v * Cin + ci], acc);
     s_a[i] = acc;
   }
   __syncthreads();
@@ -81,7 +84,9 @@ stem_gcn_kernel(const float* __restrict__ x, const float* __restrict__ in_scale,
   const int cg = Cout / 8;
   const int total = V * nf * cg;
   for (int i = threadIdx.x; i < total; i += kStemThreads) {
-    const int g = i % cg, f = (i / cg) % nf, wv = i / (cg * nf);
+    const int g = i % cg;
+    const int pair = i / cg;                        // (w, f) with f fastest -> adjacent threads write adjacent rows
+    const int wv = pair / nf, f = pair - wv * nf;
     const int c0 = g * 8;
     float acc[8];
 #pragma unroll
@@ -120,7 +125,7 @@ static int launch_stem(const float* x, const float* sc, const float* sh, const f
                        const float* bias, void* out, const float* res_w, void* res_out, int res_stride, int64_t N,
                        int Tn, int V, int Cin, int K, int Cout, int relu, cudaStream_t s) {
   const size_t KC = (size_t)K * Cin;
-  size_t smem = sizeof(float) * ((size_t)kStemFrames * V * Cin + (size_t)kStemFrames * V * KC + KC * Cout +
+  size_t smem = sizeof(float) * (2 * (size_t)kStemFrames * V * Cin + (size_t)kStemFrames * V * KC + KC * Cout +
                                  (size_t)V * Cout + (size_t)K * V * V + (res_w ? (size_t)V * Cin * Cout : 0));
   TIK_CHECK_ARG(smem <= 200 * 1024, "stem shared memory %zu too large", smem);
   static bool attr_set[64] = {};

@@ -22,25 +22,25 @@ template <> struct Vec16<float> {
   __device__ __forceinline__ void load(const float* p) { float4 t = __ldg(reinterpret_cast<const float4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
   __device__ __forceinline__ static void store(float* p, const float* a) { *reinterpret_cast<float4*>(p) = make_float4(a[0], a[1], a[2], a[3]); }
 };
-template <> struct Vec16<__nv_bfloat16> {
-  static constexpr int N = 8;
-  float v[8];
+template <> struct Vec16<__nv_bfloat16> {   // 4 bf16 = 8 bytes per thread: half the registers of a 16-byte vector, twice the warps
+  static constexpr int N = 4;
+  float v[4];
   __device__ __forceinline__ void load(const __nv_bfloat16* p) {
-    uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+    for (int i = 0; i < 2; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
   }
   __device__ __forceinline__ static void store(__nv_bfloat16* p, const float* a) {
-    uint4 t;
+    uint2 t;
     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]);
-    *reinterpret_cast<uint4*>(p) = t;
+    for (int i = 0; i < 2; ++i) h[i] = __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]);
+    *reinterpret_cast<uint2*>(p) = t;
   }
 };
 
-constexpr int kAggThreads = 128;
+constexpr int kAggThreads = 256;
 
 template <class T, int V>
 __global__ void __launch_bounds__(kAggThreads)
@@ -248,7 +248,7 @@ static int launch_agg_v(const void* x, const float* agg, void* out, int64_t N, i
   constexpr int VN = Vec16<T>::N;
   int64_t total = N * Tn * (C / VN);
   int64_t blocks = ceil_div(total, kAggThreads);
-  if (blocks > 148 * 64) blocks = 148 * 64;
+  if (blocks > 148 * 32) blocks = 148 * 32;
   aggregate_kernel<T, V><<<(unsigned)blocks, kAggThreads, 0, s>>>(reinterpret_cast<const T*>(x), agg,
                                                                    reinterpret_cast<T*>(out), N, Tn, C, K);
   TIK_LAUNCH_CHECK();
@@ -280,7 +280,7 @@ int tik_aggregate(int dtype, const void* x, const float* agg, void* out, int64_t
     return launch_agg<float>(x, agg, out, N, T, V, C, K, (cudaStream_t)stream);
   }
   if (dtype == TIK_BF16) {
-    TIK_CHECK_ARG(C % 8 == 0, "aggregate bf16: C=%d must be a multiple of 8", C);
+    TIK_CHECK_ARG(C % 4 == 0, "aggregate bf16: C=%d must be a multiple of 4", C);
     return launch_agg<__nv_bfloat16>(x, agg, out, N, T, V, C, K, (cudaStream_t)stream);
   }
   set_error("bad dtype %d", dtype);
