@@ -245,9 +245,10 @@ MAX_HEAD_CLIPS = 16384   # clips whose features are kept for one head launch (14
 
 
 def default_chunk(T):
-    """Clips per chunk: about 8K frames (~140K activation rows), so a chunk's widest layer (bf16) is ~36 MB
-    and producer->consumer traffic stays in the 126 MB L2."""
-    return max(1, 8192 // max(T, 1))
+    """Clips per backbone pass: up to 256K frames (4096 clips at T=64, ~2.9 GB of bf16 workspace).  Measured on
+    B200 (profiles/r1_notes.md): with the current per-layer kernels, launches that fill the machine for longer beat
+    L2-sized chunks (128 clips: 23 M frames/s, 1024: 34 M, 4096: 37 M), so chunks are as large as memory allows."""
+    return max(1, 262144 // max(T, 1))
 
 
 class Engine:
