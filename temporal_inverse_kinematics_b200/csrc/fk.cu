@@ -134,6 +134,151 @@ fk_kernel(const float* __restrict__ pose, const float* __restrict__ transl, floa
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Specialisation for the tree that is actually on the path: the 22-joint SMPL-X body
+// (parents -1,0,0,0,1,2,3,4,5,6,7,8,9,9,9,12,13,14,16,17,18,19).  The shuffle kernel above spends ~450 warp
+// instructions per frame (32 lanes march through every level), which caps it near 2 G frames/s; here one
+// THREAD owns one frame and walks the tree as fully unrolled straight-line code (compile-time parents, so every
+// transform lives in registers; ~70 warp-instructions per frame), which puts the kernel back on the HBM roofline.
+// A CTA stages 64 frames through shared memory so that all global traffic is contiguous 128-bit accesses; a
+// thread's pose row is overwritten in place by its joint positions.
+constexpr int kB22 = 22;
+constexpr int kB22Threads = 64;
+__device__ constexpr int kB22Parent[kB22] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19};
+constexpr int kB22ParentHost[kB22] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19};
+
+struct Fk22Params { float rest[kB22 * 3]; };   // offset to parent (root: rest position)
+
+template <bool kRotIn, bool kLocalOut>
+__global__ void __launch_bounds__(kB22Threads)
+fk_body22_kernel(const float* __restrict__ pose, const float* __restrict__ transl, float* __restrict__ joints,
+                 float* __restrict__ localR, int64_t F, const __grid_constant__ Fk22Params p) {
+  constexpr int IN = kRotIn ? 9 : 3;
+  constexpr int IO_LD = kB22 * IN + 1;          // odd row pitch: conflict-free per-thread rows
+  constexpr int ROT_LD = kB22 * 9 + 1;
+  extern __shared__ __align__(16) float fk_smem[];
+  float* s_io = fk_smem;                         // [64][IO_LD]: pose in, joints out (first 66 floats of the row)
+  float* s_rot = fk_smem + kB22Threads * IO_LD;  // [64][ROT_LD]: local rotations out (aa input only)
+  const int tid = threadIdx.x;
+  const int64_t tiles = (F + kB22Threads - 1) / kB22Threads;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t f0 = tile * kB22Threads;
+    const int nf = (int)min((int64_t)kB22Threads, F - f0);
+    // ---- coalesced load: nf * 22 * IN floats, contiguous in global memory
+    const float* gp = pose + f0 * (kB22 * IN);
+    const int n_in = nf * kB22 * IN;
+    if (nf == kB22Threads) {
+      const float4* g4 = reinterpret_cast<const float4*>(gp);
+#pragma unroll 4
+      for (int i = tid; i < kB22Threads * kB22 * IN / 4; i += kB22Threads) {
+        const float4 v = __ldg(g4 + i);
+        const int e = i * 4;
+        s_io[(e + 0) / (kB22 * IN) * IO_LD + (e + 0) % (kB22 * IN)] = v.x;
+        s_io[(e + 1) / (kB22 * IN) * IO_LD + (e + 1) % (kB22 * IN)] = v.y;
+        s_io[(e + 2) / (kB22 * IN) * IO_LD + (e + 2) % (kB22 * IN)] = v.z;
+        s_io[(e + 3) / (kB22 * IN) * IO_LD + (e + 3) % (kB22 * IN)] = v.w;
+      }
+    } else {
+      for (int i = tid; i < n_in; i += kB22Threads) s_io[i / (kB22 * IN) * IO_LD + i % (kB22 * IN)] = __ldg(gp + i);
+    }
+    __syncthreads();
+    if (tid < nf) {
+      float* row = s_io + tid * IO_LD;
+      float GR[kB22][9];
+      float Gt[kB22][3];
+#pragma unroll
+      for (int j = 0; j < kB22; ++j) {
+        float R[9];
+        if (kRotIn) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) R[k] = row[j * 9 + k];
+        } else {
+          rodrigues_q(row[j * 3], row[j * 3 + 1], row[j * 3 + 2], R);
+          if (kLocalOut) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) s_rot[tid * ROT_LD + j * 9 + k] = R[k];
+          }
+        }
+        const float dx = p.rest[j * 3], dy = p.rest[j * 3 + 1], dz = p.rest[j * 3 + 2];
+        const int par = kB22Parent[j];
+        if (par < 0) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) GR[j][k] = R[k];
+          Gt[j][0] = dx; Gt[j][1] = dy; Gt[j][2] = dz;
+        } else {
+          const float* A = GR[par];
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) GR[j][a * 3 + b] = A[a * 3] * R[b] + A[a * 3 + 1] * R[3 + b] + A[a * 3 + 2] * R[6 + b];
+          Gt[j][0] = A[0] * dx + A[1] * dy + A[2] * dz + Gt[par][0];
+          Gt[j][1] = A[3] * dx + A[4] * dy + A[5] * dz + Gt[par][1];
+          Gt[j][2] = A[6] * dx + A[7] * dy + A[8] * dz + Gt[par][2];
+        }
+      }
+      float tx = 0.f, ty = 0.f, tz = 0.f;
+      if (transl != nullptr) {
+        tx = __ldg(transl + (f0 + tid) * 3); ty = __ldg(transl + (f0 + tid) * 3 + 1); tz = __ldg(transl + (f0 + tid) * 3 + 2);
+      }
+      // the pose row is dead now: overwrite it with the joint positions
+#pragma unroll
+      for (int j = 0; j < kB22; ++j) {
+        row[j * 3] = Gt[j][0] + tx; row[j * 3 + 1] = Gt[j][1] + ty; row[j * 3 + 2] = Gt[j][2] + tz;
+      }
+    }
+    __syncthreads();
+    // ---- coalesced stores
+    float* gj = joints + f0 * (kB22 * 3);
+    const int n_out = nf * kB22 * 3;
+    if (nf == kB22Threads) {
+      float4* g4 = reinterpret_cast<float4*>(gj);
+#pragma unroll 4
+      for (int i = tid; i < kB22Threads * kB22 * 3 / 4; i += kB22Threads) {
+        const int e = i * 4;
+        g4[i] = make_float4(s_io[(e + 0) / 66 * IO_LD + (e + 0) % 66], s_io[(e + 1) / 66 * IO_LD + (e + 1) % 66],
+                            s_io[(e + 2) / 66 * IO_LD + (e + 2) % 66], s_io[(e + 3) / 66 * IO_LD + (e + 3) % 66]);
+      }
+    } else {
+      for (int i = tid; i < n_out; i += kB22Threads) gj[i] = s_io[i / 66 * IO_LD + i % 66];
+    }
+    if (kLocalOut) {
+      float* gr = localR + f0 * (kB22 * 9);
+      if (nf == kB22Threads) {
+        float4* g4 = reinterpret_cast<float4*>(gr);
+#pragma unroll 4
+        for (int i = tid; i < kB22Threads * kB22 * 9 / 4; i += kB22Threads) {
+          const int e = i * 4;
+          g4[i] = make_float4(s_rot[(e + 0) / 198 * ROT_LD + (e + 0) % 198], s_rot[(e + 1) / 198 * ROT_LD + (e + 1) % 198],
+                              s_rot[(e + 2) / 198 * ROT_LD + (e + 2) % 198], s_rot[(e + 3) / 198 * ROT_LD + (e + 3) % 198]);
+        }
+      } else {
+        for (int i = tid; i < nf * 198; i += kB22Threads) gr[i] = s_rot[i / 198 * ROT_LD + i % 198];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <bool kRotIn, bool kLocalOut>
+static int launch_body22(const float* pose, const float* transl, float* joints, float* localR, int64_t F,
+                         const Fk22Params& p, cudaStream_t s) {
+  constexpr int IN = kRotIn ? 9 : 3;
+  const size_t smem = sizeof(float) * ((size_t)kB22Threads * (kB22 * IN + 1) + (kLocalOut ? (size_t)kB22Threads * (kB22 * 9 + 1) : 0));
+  static bool attr_set[64] = {};
+  int dev = 0;
+  TIK_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    TIK_CUDA(cudaFuncSetAttribute(fk_body22_kernel<kRotIn, kLocalOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_set[dev & 63] = true;
+  }
+  int64_t blocks = ceil_div(F, kB22Threads);
+  const int64_t cap = 148 * 12;
+  if (blocks > cap) blocks = cap;
+  fk_body22_kernel<kRotIn, kLocalOut><<<(unsigned)blocks, kB22Threads, smem, s>>>(pose, transl, joints, localR, F, p);
+  TIK_LAUNCH_CHECK();
+  return TIK_OK;
+}
 }  // namespace tik
 
 extern "C" int tik_fk_body(const float* pose_dev, int pose_is_rotmat, const float* rest_host,
@@ -156,6 +301,17 @@ extern "C" int tik_fk_body(const float* pose_dev, int pose_is_rotmat, const floa
       p.rest[i * 3 + k] = par < 0 ? rest_host[i * 3 + k] : rest_host[i * 3 + k] - rest_host[par * 3 + k];
   }
   for (int i = J; i < TIK_MAX_JOINTS; ++i) { p.parent[i] = -1; p.rest[i * 3] = p.rest[i * 3 + 1] = p.rest[i * 3 + 2] = 0.f; }
+  cudaStream_t s = (cudaStream_t)stream;
+  // fast path: the SMPL-X body tree (the one on the IK path), no global rotations requested
+  bool body22 = J == kB22 && global_R_dev == nullptr && (!pose_is_rotmat || local_R_dev == nullptr);
+  for (int i = 0; body22 && i < J; ++i) body22 = parents_host[i] == kB22ParentHost[i];
+  if (body22 && (((uintptr_t)pose_dev | (uintptr_t)joints_dev | (uintptr_t)local_R_dev) & 15) == 0) {
+    Fk22Params q;
+    for (int i = 0; i < kB22 * 3; ++i) q.rest[i] = p.rest[i];
+    if (pose_is_rotmat) return launch_body22<true, false>(pose_dev, transl_dev, joints_dev, nullptr, F, q, s);
+    if (local_R_dev) return launch_body22<false, true>(pose_dev, transl_dev, joints_dev, local_R_dev, F, q, s);
+    return launch_body22<false, false>(pose_dev, transl_dev, joints_dev, nullptr, F, q, s);
+  }
   p.J = J;
   p.rounds = 0;
   while ((1 << p.rounds) < maxd + 1) ++p.rounds;
@@ -163,7 +319,6 @@ extern "C" int tik_fk_body(const float* pose_dev, int pose_is_rotmat, const floa
   int64_t blocks = ceil_div(F, kFkWarps);
   int64_t cap = (int64_t)sms * 8 * 4;   // persistent-ish: grid-stride over frames
   if (blocks > cap) blocks = cap;
-  cudaStream_t s = (cudaStream_t)stream;
   if (pose_is_rotmat)
     fk_kernel<true><<<(unsigned)blocks, kFkWarps * 32, 0, s>>>(pose_dev, transl_dev, joints_dev, local_R_dev, global_R_dev, F, p);
   else

@@ -60,7 +60,7 @@ def test_conversion_edge_cases():
         G.batch_rodrigues(np.zeros((4, 3), np.float32))
 
 
-@pytest.mark.parametrize("F", [1, 7, 16384])
+@pytest.mark.parametrize("F", [1, 7, 63, 64, 65, 16384])
 def test_fk_matches_oracle(F):
     from temporal_inverse_kinematics_b200 import smpl_util as SU
     parents = synth.SMPLX_BODY_PARENTS
@@ -72,6 +72,10 @@ def test_fk_matches_oracle(F):
     assert np.abs(j.cpu().numpy() - ej).max() < TOL
     assert np.abs(lr.cpu().numpy() - eR).max() < TOL
     assert np.abs(gr.cpu().numpy() - egR).max() < TOL
+    # SMPL-X body fast path (thread per frame): joints only, and joints + local rotations
+    j3, lr3 = SU.fk_body(_cuda(aa), rest, parents, _cuda(transl), want_local=True)
+    assert np.abs(j3.cpu().numpy() - ej).max() < TOL and np.abs(lr3.cpu().numpy() - eR).max() < TOL
+    assert np.abs(SU.fk_body(_cuda(aa), rest, parents).cpu().numpy() - (ej - transl[:, None, :])).max() < TOL
     # rotation-matrix input path (the rot6d head variant feeds matrices)
     j2 = SU.fk_body(lr, rest, parents, _cuda(transl))
     assert np.abs(j2.cpu().numpy() - ej).max() < TOL
