@@ -26,12 +26,13 @@ __device__ __forceinline__ void rodrigues_q(float ax, float ay, float az, float*
   // common/geometry.py:22-65
   float ex = ax + 1e-8f, ey = ay + 1e-8f, ez = az + 1e-8f;
   float ang = sqrtf(ex * ex + ey * ey + ez * ez);
-  float nx = ax / ang, ny = ay / ang, nz = az / ang;
+  float ia = 1.0f / ang;
+  float nx = ax * ia, ny = ay * ia, nz = az * ia;
   float s, c;
   sincosf(ang * 0.5f, &s, &c);
   float w = c, x = s * nx, y = s * ny, z = s * nz;
-  float qn = sqrtf(w * w + x * x + y * y + z * z);
-  w /= qn; x /= qn; y /= qn; z /= qn;
+  float iq = rsqrtf(w * w + x * x + y * y + z * z);   // quaternion re-normalisation (quat2mat, geometry.py:49)
+  w *= iq; x *= iq; y *= iq; z *= iq;
   float w2 = w * w, x2 = x * x, y2 = y * y, z2 = z * z;
   float wx = w * x, wy = w * y, wz = w * z, xy = x * y, xz = x * z, yz = y * z;
   R[0] = w2 + x2 - y2 - z2; R[1] = 2.f * xy - 2.f * wz;   R[2] = 2.f * wy + 2.f * xz;
@@ -144,7 +145,7 @@ fk_kernel(const float* __restrict__ pose, const float* __restrict__ transl, floa
 // A CTA stages 64 frames through shared memory so that all global traffic is contiguous 128-bit accesses; a
 // thread's pose row is overwritten in place by its joint positions.
 constexpr int kB22 = 22;
-constexpr int kB22Threads = 64;
+constexpr int kB22Threads = 128;
 __device__ constexpr int kB22Parent[kB22] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19};
 constexpr int kB22ParentHost[kB22] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19};
 
@@ -168,20 +169,9 @@ fk_body22_kernel(const float* __restrict__ pose, const float* __restrict__ trans
     // ---- coalesced load: nf * 22 * IN floats, contiguous in global memory
     const float* gp = pose + f0 * (kB22 * IN);
     const int n_in = nf * kB22 * IN;
-    if (nf == kB22Threads) {
-      const float4* g4 = reinterpret_cast<const float4*>(gp);
-#pragma unroll 4
-      for (int i = tid; i < kB22Threads * kB22 * IN / 4; i += kB22Threads) {
-        const float4 v = __ldg(g4 + i);
-        const int e = i * 4;
-        s_io[(e + 0) / (kB22 * IN) * IO_LD + (e + 0) % (kB22 * IN)] = v.x;
-        s_io[(e + 1) / (kB22 * IN) * IO_LD + (e + 1) % (kB22 * IN)] = v.y;
-        s_io[(e + 2) / (kB22 * IN) * IO_LD + (e + 2) % (kB22 * IN)] = v.z;
-        s_io[(e + 3) / (kB22 * IN) * IO_LD + (e + 3) % (kB22 * IN)] = v.w;
-      }
-    } else {
-      for (int i = tid; i < n_in; i += kB22Threads) s_io[i / (kB22 * IN) * IO_LD + i % (kB22 * IN)] = __ldg(gp + i);
-    }
+    // consecutive threads -> consecutive floats: 128 B per warp-load, consecutive shared-memory banks
+#pragma unroll 8
+    for (int i = tid; i < n_in; i += kB22Threads) s_io[i / (kB22 * IN) * IO_LD + i % (kB22 * IN)] = __ldg(gp + i);
     __syncthreads();
     if (tid < nf) {
       float* row = s_io + tid * IO_LD;
@@ -231,30 +221,12 @@ fk_body22_kernel(const float* __restrict__ pose, const float* __restrict__ trans
     // ---- coalesced stores
     float* gj = joints + f0 * (kB22 * 3);
     const int n_out = nf * kB22 * 3;
-    if (nf == kB22Threads) {
-      float4* g4 = reinterpret_cast<float4*>(gj);
-#pragma unroll 4
-      for (int i = tid; i < kB22Threads * kB22 * 3 / 4; i += kB22Threads) {
-        const int e = i * 4;
-        g4[i] = make_float4(s_io[(e + 0) / 66 * IO_LD + (e + 0) % 66], s_io[(e + 1) / 66 * IO_LD + (e + 1) % 66],
-                            s_io[(e + 2) / 66 * IO_LD + (e + 2) % 66], s_io[(e + 3) / 66 * IO_LD + (e + 3) % 66]);
-      }
-    } else {
-      for (int i = tid; i < n_out; i += kB22Threads) gj[i] = s_io[i / 66 * IO_LD + i % 66];
-    }
+#pragma unroll 8
+    for (int i = tid; i < n_out; i += kB22Threads) gj[i] = s_io[i / 66 * IO_LD + i % 66];
     if (kLocalOut) {
       float* gr = localR + f0 * (kB22 * 9);
-      if (nf == kB22Threads) {
-        float4* g4 = reinterpret_cast<float4*>(gr);
-#pragma unroll 4
-        for (int i = tid; i < kB22Threads * kB22 * 9 / 4; i += kB22Threads) {
-          const int e = i * 4;
-          g4[i] = make_float4(s_rot[(e + 0) / 198 * ROT_LD + (e + 0) % 198], s_rot[(e + 1) / 198 * ROT_LD + (e + 1) % 198],
-                              s_rot[(e + 2) / 198 * ROT_LD + (e + 2) % 198], s_rot[(e + 3) / 198 * ROT_LD + (e + 3) % 198]);
-        }
-      } else {
-        for (int i = tid; i < nf * 198; i += kB22Threads) gr[i] = s_rot[i / 198 * ROT_LD + i % 198];
-      }
+#pragma unroll 8
+      for (int i = tid; i < nf * 198; i += kB22Threads) gr[i] = s_rot[i / 198 * ROT_LD + i % 198];
     }
     __syncthreads();
   }
@@ -269,7 +241,7 @@ static int launch_body22(const float* pose, const float* transl, float* joints, 
   int dev = 0;
   TIK_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    TIK_CUDA(cudaFuncSetAttribute(fk_body22_kernel<kRotIn, kLocalOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    TIK_CUDA(cudaFuncSetAttribute(fk_body22_kernel<kRotIn, kLocalOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set[dev & 63] = true;
   }
   int64_t blocks = ceil_div(F, kB22Threads);
@@ -309,7 +281,14 @@ extern "C" int tik_fk_body(const float* pose_dev, int pose_is_rotmat, const floa
     Fk22Params q;
     for (int i = 0; i < kB22 * 3; ++i) q.rest[i] = p.rest[i];
     if (pose_is_rotmat) return launch_body22<true, false>(pose_dev, transl_dev, joints_dev, nullptr, F, q, s);
-    if (local_R_dev) return launch_body22<false, true>(pose_dev, transl_dev, joints_dev, local_R_dev, F, q, s);
+    if (local_R_dev) {
+      // local rotations are an element-wise conversion: the streaming Rodrigues kernel (81 % of HBM peak) writes
+      // them, the joints-only FK kernel keeps its small shared-memory footprint (measured: 3.4 ms vs 8.0 ms fused
+      // at 8.4 M frames, profiles/r1_notes.md)
+      int rc = launch_batch_rodrigues(pose_dev, local_R_dev, F * kB22, s);
+      if (rc != TIK_OK) return rc;
+      return launch_body22<false, false>(pose_dev, transl_dev, joints_dev, nullptr, F, q, s);
+    }
     return launch_body22<false, false>(pose_dev, transl_dev, joints_dev, nullptr, F, q, s);
   }
   p.J = J;

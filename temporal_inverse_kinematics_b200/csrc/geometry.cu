@@ -184,6 +184,10 @@ static int launch_conv(K kernel, const void* in, void* out, int64_t M, cudaStrea
   return TIK_OK;
 }
 
+int launch_batch_rodrigues(const float* aa, float* R9, int64_t M, cudaStream_t s) {
+  return launch_conv(rodrigues_kernel, aa, R9, M, s);
+}
+
 }  // namespace tik
 
 extern "C" {

@@ -45,5 +45,6 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // internal entry points shared between translation units
 int rowgemm_f32(const TikRowGemm* d, cudaStream_t s);
 int rowgemm_bf16(const TikRowGemm* d, cudaStream_t s);
+int launch_batch_rodrigues(const float* aa, float* R9, int64_t M, cudaStream_t s);
 
 }  // namespace tik
