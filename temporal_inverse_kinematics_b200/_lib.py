@@ -51,6 +51,7 @@ _PROTOS = {
                                C.c_int, C.c_int, C.c_int, vp]),
     "tik_aggregate": (C.c_int, [C.c_int, vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "tik_rowgemm": (C.c_int, [C.c_int, C.POINTER(TikRowGemm), vp]),
+    "tik_gcn_fused": (C.c_int, [vp, vp, vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "tik_stgcn_out_frames": (C.c_int, [C.POINTER(TikNet), C.c_int]),
     "tik_stgcn_workspace_bytes": (C.c_int, [C.POINTER(TikNet), C.c_int, i64, i64, C.c_int, C.POINTER(i64)]),
     "tik_stgcn_plan_create": (C.c_int, [C.POINTER(TikNet), C.c_int, i64, i64, C.c_int, vp, i64, C.POINTER(vp)]),

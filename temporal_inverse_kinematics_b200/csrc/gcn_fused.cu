@@ -1,0 +1,403 @@
+// Fused graph convolution on tcgen05: adjacency aggregation + 1x1 channel GEMM + BN + ReLU in ONE kernel.
+//
+//   H[n,w,t,:] = relu( Wg' . ( sum_v A^[v,w] X[n,v,t,:] ) + b1[w,:] )          (K = 1 partition)
+//
+// Replaces the aggregate kernel + channel GEMM pair (gconv_origin.py:56-65 with the einsum moved in front of the
+// conv, st_gcn_aaai18.py:178-179), i.e. two full activation passes through HBM per block.
+//
+// A tile is 7 frames x 17 nodes of one clip = 119 rows (row r = v*7 + t_local), fetched as ONE 4-D TMA box
+// (64 channels, 7 frames, 17 nodes, 1 clip) per 64-channel slab of the node-major activations.
+//   MMA 1 (aggregation as a dense block-structured GEMM):   D1[128 x Cin] = Abd[128 x 128] . Xtile[128 x Cin]
+//          Abd[(w,t),(v,t')] = A^[v,w] * delta(t,t'), bf16, K-major, resident in shared memory;
+//          the X tile is used in place as the MN-major B operand (rows = K, channels contiguous).
+//   mid pass: 16 warps move D1 TMEM -> registers -> bf16 -> the SAME shared-memory tile, now a K-major A operand.
+//   MMA 2 (channel mix):                                      D2[128 x Cout] = Xagg[128 x Cin] . Wg'[Cout x Cin]^T
+//   final pass: D2 + bias[node] -> ReLU -> bf16 -> swizzled staging -> 4-D TMA store (box clipped at the clip end).
+// The dense Abd multiply costs 128/Cout of the channel GEMM in tensor time, far less than a round trip of the
+// aggregated tensor through HBM.  Warp roles as in stgcn_umma.cu: warp 0 TMA producer, warp 1 MMA issuer,
+// 16 epilogue warps (TMEM lane group x column quarter).
+#include <string.h>
+
+#include <algorithm>
+
+#include "tik_common.cuh"
+#include "umma_ptx.cuh"
+
+namespace tik {
+
+constexpr int kGfThreads = 64 + 32 * 16;
+constexpr int kGfTile = 16384;                     // one 128-row x 64-channel swizzled slab
+constexpr int kGfSmemBudget = 225 * 1024;
+
+// MN-major operand, 128-byte swizzle: 64 contiguous elements per row, 8-row groups 1024 B apart (SBO),
+// next 64-element block of the MN dimension `lbo` bytes away (LBO).
+__device__ __forceinline__ uint64_t make_smem_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+struct GcnFusedParams {
+  CUtensorMap map_x, map_out, map_abd, map_w;
+  int32_t n_clips, T, V, ttg, tiles_t;   // ttg = frames per tile (min(T, 7))
+  int32_t xbufs;                          // 1 or 2 input tiles in flight
+  int32_t off_w, off_x, off_stage, off_bias, off_bar;
+  const float* bias;                      // (V, COUT)
+  int32_t relu;
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_constant__ GcnFusedParams p) {
+  constexpr int KC1 = CIN / 64;                       // 64-channel slabs of the input
+  constexpr int KC2 = COUT / 64;
+  constexpr int TMEM_COLS = (CIN + COUT) <= 128 ? 128 : ((CIN + COUT) <= 256 ? 256 : 512);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_abd = smem;                              // 2 slabs (K = 0..63, 64..127) of 128 rows
+  uint8_t* s_w = smem + p.off_w;                      // KC1 slabs of COUT rows x 128 B
+  uint8_t* s_x = smem + p.off_x;                      // xbufs x KC1 slabs
+  uint8_t* s_stage = smem + p.off_stage;              // KC2 slabs
+  float* s_bias = reinterpret_cast<float*>(smem + p.off_bias);
+  uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [2]
+  uint64_t* x_empty = x_full + 2;                     // [2]
+  uint64_t* w_full = x_empty + 2;
+  uint64_t* d1_full = w_full + 1;
+  uint64_t* xagg_full = d1_full + 1;
+  uint64_t* d2_full = xagg_full + 1;
+  uint64_t* d2_empty = d2_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = p.n_clips * p.tiles_t;
+  const int rows_valid = p.ttg * p.V;                 // rows the TMA box fills (<= 128)
+  const uint32_t x_bytes = (uint32_t)(KC1 * rows_valid * 128);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_x); tma_prefetch_desc(&p.map_out); tma_prefetch_desc(&p.map_abd); tma_prefetch_desc(&p.map_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    mbar_init(w_full, 1); mbar_init(d1_full, 1); mbar_init(xagg_full, 16); mbar_init(d2_full, 1); mbar_init(d2_empty, 16);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  for (int i = threadIdx.x; i < p.V * COUT; i += kGfThreads) s_bias[i] = __ldg(p.bias + i);
+  // rows the TMA box never writes must not hold NaN bit patterns (they meet zero columns of Abd in MMA 1)
+  {
+    const int pad_rows = 128 - rows_valid;
+    const int total16 = p.xbufs * KC1 * pad_rows * 8;
+    for (int i = threadIdx.x; i < total16; i += kGfThreads) {
+      const int piece = i & 7, rr = (i >> 3) % pad_rows, slab = (i >> 3) / pad_rows;
+      *reinterpret_cast<uint4*>(s_x + (size_t)slab * kGfTile + (size_t)(rows_valid + rr) * 128 + piece * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + CIN;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(w_full, (uint32_t)(2 * kGfTile + KC1 * COUT * 128));
+      tma_load_2d(s_abd, &p.map_abd, w_full, 0, 0);
+      tma_load_2d(s_abd + kGfTile, &p.map_abd, w_full, 64, 0);
+      for (int kc = 0; kc < KC1; ++kc) tma_load_2d(s_w + (size_t)kc * COUT * 128, &p.map_w, w_full, kc * 64, 0);
+      int b = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int n = tile / p.tiles_t, tt = tile - n * p.tiles_t;
+        const int t0 = min(tt * p.ttg, p.T - p.ttg);          // the last tile of a clip is shifted back, never out of range
+        mbar_wait(&x_empty[b], phase ^ 1);
+        mbar_expect_tx(&x_full[b], x_bytes);
+        for (int kc = 0; kc < KC1; ++kc)
+          tma_load_4d(s_x + ((size_t)b * KC1 + kc) * kGfTile, &p.map_x, &x_full[b], kc * 64, t0, 0, n);
+        if (p.xbufs == 2) { if (++b == 2) { b = 0; phase ^= 1; } } else { phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_idesc_bf16(128, CIN) | (1u << 16);   // B operand MN-major
+      constexpr uint32_t idesc2 = make_idesc_bf16(128, COUT);
+      mbar_wait(w_full, 0);
+      int b = 0; uint32_t phase = 0, tphase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t xb = smem_u32(s_x + (size_t)b * KC1 * kGfTile);
+        mbar_wait(&x_full[b], phase);
+        tc_fence_after();
+        // ---- MMA 1: D1 = Abd . X   (K = 128 tile rows, 16 per instruction)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t da = make_smem_desc_kmajor_sw128(smem_u32(s_abd) + (uint32_t)(k >> 2) * kGfTile + (uint32_t)(k & 3) * 32u);
+          const uint64_t db = make_smem_desc_mnmajor_sw128(xb + (uint32_t)k * 2048u, (uint32_t)kGfTile);
+          umma_bf16(tmem_d1, da, db, idesc1, k != 0 ? 1u : 0u);
+        }
+        umma_commit(d1_full);
+        // ---- MMA 2: D2 = Xagg . Wg^T once the epilogue warps have rewritten the tile as bf16 Xagg
+        mbar_wait(xagg_full, tphase);
+        mbar_wait(d2_empty, tphase ^ 1);                     // previous tile's D2 has been read
+        tc_fence_after();
+#pragma unroll
+        for (int kc = 0; kc < KC1; ++kc) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_smem_desc_kmajor_sw128(xb + (uint32_t)kc * kGfTile + (uint32_t)k * 32u);
+            const uint64_t db = make_smem_desc_kmajor_sw128(smem_u32(s_w) + (uint32_t)kc * (COUT * 128) + (uint32_t)k * 32u);
+            umma_bf16(tmem_d2, da, db, idesc2, (kc | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(d2_full);
+        umma_commit(&x_empty[b]);                            // the tile buffer may be refilled once MMA 2 has read it
+        tphase ^= 1;
+        if (p.xbufs == 2) { if (++b == 2) { b = 0; phase ^= 1; } } else { phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps: mid pass (D1 -> bf16 Xagg) and final pass (D2 -> H) =====================
+    constexpr int CW1 = CIN / 4, CW2 = COUT / 4;
+    const int lane_grp = warp & 3;
+    const int cq = (warp - 2) >> 2;
+    const int r = lane_grp * 32 + lane;
+    const int node = r / p.ttg;                              // tile row r = node * ttg + t_local
+    const float* bias = s_bias + (node < p.V ? node : 0) * COUT + cq * CW2;
+    const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
+    int b = 0; uint32_t tphase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int n = tile / p.tiles_t, tt = tile - n * p.tiles_t;
+      const int t0 = min(tt * p.ttg, p.T - p.ttg);
+      uint8_t* xrow = s_x + (size_t)b * KC1 * kGfTile + (size_t)r * 128;
+      // ---- mid pass
+      mbar_wait(d1_full, tphase);
+      tc_fence_after();
+      {
+        uint32_t a[CW1];
+#pragma unroll
+        for (int i = 0; i < CW1 / 16; ++i) tmem_ld16(tmem_d1 + lane_off + (uint32_t)(cq * CW1 + 16 * i), a + 16 * i);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < CW1 / 8; ++q) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(a[8 * q + 0]), __uint_as_float(a[8 * q + 1]));
+          u.y = pack_bf16x2(__uint_as_float(a[8 * q + 2]), __uint_as_float(a[8 * q + 3]));
+          u.z = pack_bf16x2(__uint_as_float(a[8 * q + 4]), __uint_as_float(a[8 * q + 5]));
+          u.w = pack_bf16x2(__uint_as_float(a[8 * q + 6]), __uint_as_float(a[8 * q + 7]));
+          const int col = cq * CW1 + 8 * q;
+          const int j = (col & 63) >> 3;
+          *reinterpret_cast<uint4*>(xrow + (size_t)(col >> 6) * kGfTile + ((j ^ (r & 7)) << 4)) = u;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(xagg_full);
+      // ---- final pass
+      if (threadIdx.x == 64) tma_store_wait_read0();          // previous tile's store has finished reading the staging tile
+      mbar_wait(d2_full, tphase);
+      tc_fence_after();
+      {
+        uint32_t a[CW2];
+#pragma unroll
+        for (int i = 0; i < CW2 / 16; ++i) tmem_ld16(tmem_d2 + lane_off + (uint32_t)(cq * CW2 + 16 * i), a + 16 * i);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d2_empty);
+        named_bar_sync(1, 512);                               // staging tile free (store issuer passed wait_read)
+#pragma unroll
+        for (int q = 0; q < CW2 / 8; ++q) {
+          const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * q);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * q + 4);
+          const float v0 = __uint_as_float(a[8 * q + 0]) + b0.x, v1 = __uint_as_float(a[8 * q + 1]) + b0.y;
+          const float v2 = __uint_as_float(a[8 * q + 2]) + b0.z, v3 = __uint_as_float(a[8 * q + 3]) + b0.w;
+          const float v4 = __uint_as_float(a[8 * q + 4]) + b1.x, v5 = __uint_as_float(a[8 * q + 5]) + b1.y;
+          const float v6 = __uint_as_float(a[8 * q + 6]) + b1.z, v7 = __uint_as_float(a[8 * q + 7]) + b1.w;
+          uint4 u;
+          if (p.relu) { u.x = pack_bf16x2_relu(v0, v1); u.y = pack_bf16x2_relu(v2, v3); u.z = pack_bf16x2_relu(v4, v5); u.w = pack_bf16x2_relu(v6, v7); }
+          else { u.x = pack_bf16x2(v0, v1); u.y = pack_bf16x2(v2, v3); u.z = pack_bf16x2(v4, v5); u.w = pack_bf16x2(v6, v7); }
+          const int col = cq * CW2 + 8 * q;
+          const int j = (col & 63) >> 3;
+          *reinterpret_cast<uint4*>(s_stage + (size_t)(col >> 6) * kGfTile + (size_t)r * 128 + ((j ^ (r & 7)) << 4)) = u;
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(2, 512);
+      if (threadIdx.x == 64) {
+        for (int c = 0; c < KC2; ++c) tma_store_4d(&p.map_out, s_stage + (size_t)c * kGfTile, c * 64, t0, 0, n);
+        tma_store_commit();
+      }
+      tphase ^= 1;
+      if (p.xbufs == 2) b ^= 1;
+    }
+    if (threadIdx.x == 64) tma_store_wait0();
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int gf_encode(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !q) {
+      set_error("cuTensorMapEncodeTiled not available from the driver");
+      return TIK_ERR_CUDA;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(q);
+  }
+  const uint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fused gcn) failed with CUresult %d", (int)r);
+    return TIK_ERR_CUDA;
+  }
+  return TIK_OK;
+}
+
+struct GcnFusedPrepared {
+  GcnFusedParams p;
+  int cin, cout, smem_bytes;
+};
+
+bool gcn_fused_supported(int cin, int cout, int V, int K) {
+  if (K != 1 || V * 7 > 128 || V < 1) return false;
+  return (cin == 64 && (cout == 64 || cout == 128)) || (cin == 128 && (cout == 128 || cout == 256));
+}
+
+int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float* bias, void* out, int64_t n_clips, int T, int V,
+                      int cin, int cout, int relu, GcnFusedPrepared** outp) {
+  TIK_CHECK_ARG(gcn_fused_supported(cin, cout, V, 1), "fused gcn: unsupported shape cin=%d cout=%d V=%d", cin, cout, V);
+  TIK_CHECK_ARG(x && abd && w && bias && out && n_clips > 0 && T > 0, "fused gcn: bad arguments");
+  GcnFusedPrepared* g = new GcnFusedPrepared();
+  GcnFusedParams& p = g->p;
+  memset(&p, 0, sizeof(p));
+  g->cin = cin; g->cout = cout;
+  p.n_clips = (int32_t)n_clips; p.T = T; p.V = V;
+  p.ttg = T < 7 ? T : 7;
+  p.tiles_t = (T + p.ttg - 1) / p.ttg;
+  p.bias = bias; p.relu = relu;
+  int rc = TIK_OK;
+  {
+    uint64_t dims[4] = {(uint64_t)cin, (uint64_t)T, (uint64_t)V, (uint64_t)n_clips};
+    uint64_t strides[3] = {(uint64_t)cin * 2, (uint64_t)cin * 2 * T, (uint64_t)cin * 2 * T * V};
+    uint32_t box[4] = {64, (uint32_t)p.ttg, (uint32_t)V, 1};
+    rc = gf_encode(&p.map_x, x, 4, dims, strides, box);
+  }
+  if (rc == TIK_OK) {
+    uint64_t dims[4] = {(uint64_t)cout, (uint64_t)T, (uint64_t)V, (uint64_t)n_clips};
+    uint64_t strides[3] = {(uint64_t)cout * 2, (uint64_t)cout * 2 * T, (uint64_t)cout * 2 * T * V};
+    uint32_t box[4] = {64, (uint32_t)p.ttg, (uint32_t)V, 1};
+    rc = gf_encode(&p.map_out, out, 4, dims, strides, box);
+  }
+  if (rc == TIK_OK) {
+    uint64_t dims[2] = {128, 128};
+    uint64_t strides[1] = {256};
+    uint32_t box[2] = {64, 128};
+    rc = gf_encode(&p.map_abd, abd, 2, dims, strides, box);
+  }
+  if (rc == TIK_OK) {
+    uint64_t dims[2] = {(uint64_t)cin, (uint64_t)cout};
+    uint64_t strides[1] = {(uint64_t)cin * 2};
+    uint32_t box[2] = {64, (uint32_t)cout};
+    rc = gf_encode(&p.map_w, w, 2, dims, strides, box);
+  }
+  if (rc != TIK_OK) { delete g; return rc; }
+  const int kc1 = cin / 64, kc2 = cout / 64;
+  const int w_bytes = kc1 * cout * 128;
+  const int bias_bytes = (V * cout * 4 + 1023) / 1024 * 1024;
+  const int fixed = 2 * kGfTile + w_bytes + kc2 * kGfTile + bias_bytes + 256;
+  p.xbufs = (fixed + 2 * kc1 * kGfTile <= kGfSmemBudget) ? 2 : 1;
+  if (fixed + p.xbufs * kc1 * kGfTile > kGfSmemBudget) {
+    delete g;
+    set_error("fused gcn: shared memory plan does not fit");
+    return TIK_ERR_UNSUPPORTED;
+  }
+  p.off_w = 2 * kGfTile;
+  p.off_x = p.off_w + (w_bytes + 1023) / 1024 * 1024;
+  p.off_stage = p.off_x + p.xbufs * kc1 * kGfTile;
+  p.off_bias = p.off_stage + kc2 * kGfTile;
+  p.off_bar = p.off_bias + bias_bytes;
+  g->smem_bytes = p.off_bar + 256 + 1024;
+  *outp = g;
+  return TIK_OK;
+}
+
+template <int CIN, int COUT>
+static int gf_launch_variant(const GcnFusedPrepared* g, unsigned grid, cudaStream_t s) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  TIK_CUDA(cudaGetDevice(&dev));
+  if (!attr_done[dev & 63]) {
+    TIK_CUDA(cudaFuncSetAttribute(gcn_fused_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGfSmemBudget + 2048));
+    attr_done[dev & 63] = true;
+  }
+  gcn_fused_kernel<CIN, COUT><<<grid, kGfThreads, g->smem_bytes, s>>>(g->p);
+  TIK_LAUNCH_CHECK();
+  return TIK_OK;
+}
+
+int gcn_fused_launch(GcnFusedPrepared* g, int64_t n_clips, cudaStream_t s) {
+  TIK_CHECK_ARG(n_clips <= g->p.n_clips || true, "n_clips");
+  GcnFusedParams& p = g->p;
+  const int32_t cap = p.n_clips;
+  if (n_clips <= 0) return TIK_OK;
+  TIK_CHECK_ARG(n_clips <= cap, "fused gcn: n_clips exceeds the prepared capacity");
+  const int32_t saved = p.n_clips;
+  p.n_clips = (int32_t)n_clips;            // tiles only over the valid clips (tensor maps keep the full capacity)
+  int sms = 148;
+  { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int64_t tiles = n_clips * p.tiles_t;
+  const unsigned grid = (unsigned)std::min<int64_t>(tiles, sms);
+  int rc;
+  if (g->cin == 64 && g->cout == 64) rc = gf_launch_variant<64, 64>(g, grid, s);
+  else if (g->cin == 64 && g->cout == 128) rc = gf_launch_variant<64, 128>(g, grid, s);
+  else if (g->cin == 128 && g->cout == 128) rc = gf_launch_variant<128, 128>(g, grid, s);
+  else rc = gf_launch_variant<128, 256>(g, grid, s);
+  p.n_clips = saved;
+  return rc;
+}
+
+void gcn_fused_free(GcnFusedPrepared* g) { delete g; }
+
+}  // namespace tik
+
+extern "C" int tik_gcn_fused(const void* x_dev, const void* abd_dev, const void* w_dev, const float* bias_dev, void* out_dev,
+                             int64_t N, int T, int V, int Cin, int Cout, int relu, void* stream) {
+  using namespace tik;
+  GcnFusedPrepared* g = nullptr;
+  int rc = gcn_fused_prepare(x_dev, abd_dev, w_dev, bias_dev, out_dev, N, T, V, Cin, Cout, relu, &g);
+  if (rc != TIK_OK) return rc;
+  rc = gcn_fused_launch(g, N, (cudaStream_t)stream);
+  gcn_fused_free(g);
+  return rc;
+}

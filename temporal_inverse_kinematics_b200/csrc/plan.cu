@@ -6,6 +6,7 @@
 // the 126 MB L2 between producer and consumer kernels; the last block writes its (N,T',V*C) features into a
 // batch-level buffer and the two head GEMMs then run ONCE over up to n_max clips (a per-chunk head would be
 // a handful of CTAs on a 148-SM part).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -29,7 +30,9 @@ static int out_frames(int t, int stride) { return (t - 1) / stride + 1; }
 static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 struct Step {
-  enum Kind { STEM = 0, AGG = 1, GEMM = 2 } kind;
+  enum Kind { STEM = 0, AGG = 1, GEMM = 2, FUSED_GCN = 3 } kind;
+  GcnFusedPrepared* fused = nullptr;
+  double fused_flops_per_clip = 0;
   TikRowGemm g;               // GEMM
   UmmaPrepared* prep = nullptr;
   const void* src = nullptr;  // AGG input
@@ -57,14 +60,17 @@ struct TikPlan {
   ~TikPlan() {
     for (auto* v : {&chunk_steps, &batch_steps})
       for (auto& s : *v)
+      {
         if (s.prep) tik::umma_free(s.prep);
+        if (s.fused) tik::gcn_fused_free(s.fused);
+      }
   }
 };
 
 namespace tik {
 
 struct WsLayout {
-  int64_t off_x0, off_x1, off_agg, off_h, off_r0, off_feat, off_z, total_bytes;
+  int64_t off_x0, off_x1, off_agg, off_h, off_r0, off_feat, off_z, off_abd, total_bytes;
 };
 
 static int check_net(const TikNet* net, int dtype) {
@@ -124,6 +130,7 @@ static void ws_layout(const TikNet* net, int dtype, int64_t n, int64_t n_max, in
   L->off_r0 = off; off = align_up(off + r0 * n * es, 1024);
   L->off_feat = off; off = align_up(off + feat * n_max * es, 1024);
   L->off_z = off; off = align_up(off + z * n_max * es, 1024);
+  L->off_abd = off; off = align_up(off + (int64_t)net->n_blocks * 128 * 128 * 2, 1024);
   L->total_bytes = off;
 }
 
@@ -140,6 +147,7 @@ static int run_step(TikPlan* P, Step& st, const float* xc, int64_t n, int64_t cl
     // planes are spaced for a full chunk (the tensor maps are baked for n_chunk clips)
     return tik_aggregate(P->dtype, st.src, st.blk->agg_dev, st.dst, P->n_chunk, st.t, V, st.c, net.K, s);
   }
+  if (st.kind == Step::FUSED_GCN) return gcn_fused_launch(st.fused, n, s);
   TikRowGemm g = st.g;
   if (g.v == 1) {             // head: rows = n * T'
     g.t_out = (int32_t)(n * P->T_out);
@@ -268,6 +276,23 @@ int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int64_t
       Step s; s.kind = Step::STEM; s.dst = hbuf; s.t = t; s.blk = &b;
       s.dst2 = b.res_kind == TIK_RES_STEM ? r0buf : nullptr;
       P->chunk_steps.push_back(s);
+    } else if (dtype == TIK_BF16 && gcn_fused_supported(b.c_in, b.c_out, V, K) && !getenv("TIK_NO_FUSED_GCN")) {
+      // aggregation + channel GEMM in one kernel: build the block-structured bf16 operand Abd in the workspace
+      const int f = t < 7 ? t : 7;
+      std::vector<float> a_host((size_t)V * V);
+      cudaError_t ce = cudaMemcpy(a_host.data(), b.agg_dev, a_host.size() * sizeof(float), cudaMemcpyDeviceToHost);
+      std::vector<__nv_bfloat16> abd_host(128 * 128, __float2bfloat16_rn(0.f));
+      for (int w = 0; w < V; ++w)
+        for (int v = 0; v < V; ++v)
+          for (int q = 0; q < f; ++q) abd_host[(size_t)(w * f + q) * 128 + (v * f + q)] = __float2bfloat16_rn(a_host[(size_t)v * V + w]);
+      void* abd_dev = ws + L.off_abd + (int64_t)i * 128 * 128 * 2;
+      if (ce == cudaSuccess) ce = cudaMemcpy(abd_dev, abd_host.data(), abd_host.size() * 2, cudaMemcpyHostToDevice);
+      if (ce != cudaSuccess) { set_error("plan: Abd upload failed: %s", cudaGetErrorString(ce)); delete P; return TIK_ERR_CUDA; }
+      Step s; s.kind = Step::FUSED_GCN; s.blk = &b; s.t = t;
+      int rcf = gcn_fused_prepare(xbuf[cur], abd_dev, b.w_gcn_dev, b.b_gcn_dev, hbuf, n_chunk, t, V, b.c_in, b.c_out, 1, &s.fused);
+      if (rcf != TIK_OK) { delete P; return rcf; }
+      s.fused_flops_per_clip = 2.0 * V * t * (double)b.c_in * b.c_out;
+      P->chunk_steps.push_back(s);
     } else {
       Step s; s.kind = Step::AGG; s.src = xbuf[cur]; s.dst = agg; s.t = t; s.c = b.c_in; s.blk = &b;
       P->chunk_steps.push_back(s);
@@ -368,8 +393,10 @@ int tik_stgcn_plan_profile(TikPlan* P, const float* x, int64_t N, float* poses, 
     TIK_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
     Step& st = *trace[i].first;
     const int64_t n = trace[i].second;
-    ms_by_kind[(int)st.kind] += ms;
-    launches_by_kind[(int)st.kind] += 1;
+    const int kind = st.kind == Step::FUSED_GCN ? (int)Step::GEMM : (int)st.kind;   // fused gcn counts with the tensor-core family
+    ms_by_kind[kind] += ms;
+    launches_by_kind[kind] += 1;
+    if (st.kind == Step::FUSED_GCN) *flops_gemm += st.fused_flops_per_clip * (double)n;
     if (st.kind == Step::GEMM) {
       double ktot = -st.k_identity;
       for (int q = 0; q < st.g.n_slabs; ++q) ktot += st.g.slabs[q].c;

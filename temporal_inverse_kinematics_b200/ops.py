@@ -61,6 +61,28 @@ def stem_gcn(x, in_scale, in_shift, A_hat, w, bias, out_dtype, relu=True, res_w=
     return out if res_w is None else (out, res)
 
 
+def build_abd(A_hat, T):
+    """(128,128) bf16 block-structured aggregation operand of the fused graph conv: rows (w, t), columns (v, t'),
+    entry A_hat[v, w] * (t == t'), f = min(T, 7) frames per tile, zero padding."""
+    V = A_hat.shape[-1]
+    f = min(int(T), 7)
+    a = A_hat.reshape(V, V).float()
+    abd = torch.zeros(128, 128, dtype=torch.float32, device=A_hat.device)
+    abd[: V * f, : V * f] = torch.kron(a.t().contiguous(), torch.eye(f, device=A_hat.device))
+    return abd.to(torch.bfloat16).contiguous()
+
+
+def gcn_fused(x, abd, w, bias, relu=True):
+    """x (N,V,T,Cin) bf16 -> (N,V,T,Cout) bf16: relu(W . aggregate(x) + bias[node]) in one tensor-core kernel."""
+    _dev(x, abd, w, bias)
+    N, V, T, Cin = x.shape
+    Cout = w.shape[0]
+    out = torch.empty((N, V, T, Cout), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().tik_gcn_fused(L.ptr(x), L.ptr(abd), L.ptr(w), L.ptr(bias), L.ptr(out), N, T, V, Cin, Cout, int(relu),
+                                  L.stream_ptr(x.device)))
+    return out
+
+
 def rowgemm(slabs, w, bias, nv, v, t_out, act="none", slope=0.01, residual=None, out_layout="node", c_out_valid=None,
             stem_residual=None):
     """Generic implicit GEMM (TikRowGemm).

@@ -151,6 +151,27 @@ def stage_shift():
     return True
 
 
+def stage_fused():
+    """Fused graph conv (aggregation as a block-structured MMA with an MN-major B operand) vs a torch emulation."""
+    ok = True
+    V = 17
+    for (n, t, cin, cout) in [(2, 7, 64, 64), (3, 64, 64, 64), (2, 9, 64, 128), (3, 32, 128, 128), (2, 16, 128, 256), (4, 5, 128, 128),
+                              (2, 3, 64, 64), (150, 64, 64, 128)]:
+        g = torch.Generator().manual_seed(n * 1000 + t)
+        x = torch.randn(n, V, t, cin, generator=g).bfloat16()
+        A = (torch.rand(1, V, V, generator=g) * (torch.rand(1, V, V, generator=g) > 0.6)).float()
+        w = (torch.randn(cout, cin, generator=g) / np.sqrt(cin)).bfloat16()
+        b = torch.randn(V, cout, generator=g)
+        abd = ops.build_abd(A, t)
+        y = ops.gcn_fused(x.cuda(), abd.cuda(), w.cuda(), b.cuda())
+        torch.cuda.synchronize()
+        Ab = A[0].bfloat16().float()                                      # the kernel sees bf16 adjacency entries
+        xa = torch.einsum("vw,nvtc->nwtc", Ab, x.float()).bfloat16().float()
+        want = torch.relu(torch.einsum("nwtc,oc->nwto", xa, w.float()) + b.view(1, V, 1, cout))
+        ok &= report(f"fused gcn n={n} t={t} {cin}->{cout}", y, want, 6e-2)
+    return ok
+
+
 def stage_net():
     from temporal_inverse_kinematics_b200.pose_regressor import PoseRegressor, default_hparams
     ok = True
@@ -186,6 +207,6 @@ def stage_net():
 
 if __name__ == "__main__":
     stage = sys.argv[1]
-    ok = {"simt": stage_simt, "umma": stage_umma, "net": stage_net, "shift": stage_shift}[stage]()
+    ok = {"simt": stage_simt, "umma": stage_umma, "net": stage_net, "shift": stage_shift, "fused": stage_fused}[stage]()
     print(f"stage {stage}: {'PASS' if ok else 'FAIL'}")
     sys.exit(0 if ok else 1)
