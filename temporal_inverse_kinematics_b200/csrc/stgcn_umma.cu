@@ -38,7 +38,7 @@ constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                       // bf16 elements per K chunk = one 128 B swizzle row
 constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KB
 constexpr int kEpiWarps = 16;                     // four warps per TMEM lane group, each takes a quarter of the columns
-constexpr int kUmmaThreads = 64 + 32 * kEpiWarps;
+constexpr int kUmmaThreads = 64 + 32 * kEpiWarps + 32;   // + one TMA-store warp
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 225 * 1024;
 
@@ -94,7 +94,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
   uint64_t* tmem_full = empty_bar + kMaxStages;             // [2]
   uint64_t* tmem_empty = tmem_full + 2;                     // [2]
   uint64_t* w_full = tmem_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  uint64_t* stage_full = w_full + 1;                        // [2] staging tile written by the 16 epilogue warps
+  uint64_t* stage_empty = stage_full + 2;                   // [2] staging tile read by the TMA store
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stages = p.stages;
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
     for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
     mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&stage_full[i], kEpiWarps); mbar_init(&stage_empty[i], 1); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
@@ -188,6 +191,34 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (warp == 2 + kEpiWarps) {
+    // ===================== TMA-store warp =====================
+    // Takes the store issue and its completion waits off the epilogue warps' critical path.
+    if (lane == 0 && p.tma_store) {
+      const int ntn = p.n_tiles_n, tiles_t = p.tiles_t;
+      int sbuf = 0; uint32_t sphase = 0;
+      int prev = -1;
+      for (int tile = blockIdx.x; tile < (int)num_tiles; tile += gridDim.x) {
+        const int tm = tile / ntn;
+        const int n0 = (tile - tm * ntn) * BN;
+        const int tile_nv = tm / tiles_t, tile_t = tm - tile_nv * tiles_t;
+        mbar_wait(&stage_full[sbuf], sphase);
+        for (int c = 0; c < BN / 64; ++c)
+          tma_store_3d(&p.map_out, s_stage + ((size_t)sbuf * (BN / 64) + c) * kABytes, n0 + c * 64, tile_t * p.tt, tile_nv * p.vv);
+        tma_store_commit();
+        if (p.stage_bufs == 2) {
+          tma_store_wait_read1();                           // every store but the newest has finished reading smem
+          if (prev >= 0) mbar_arrive(&stage_empty[prev]);
+          prev = sbuf;
+          if (++sbuf == 2) { sbuf = 0; sphase ^= 1; }
+        } else {
+          tma_store_wait_read0();
+          mbar_arrive(&stage_empty[0]);
+          sphase ^= 1;
+        }
+      }
+      tma_store_wait0();
+    }
   } else {
     // ===================== epilogue =====================
     // 16 warps: TMEM lane group (warp & 3) x column quarter; thread = one tile row x BN/4 columns.
@@ -200,7 +231,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
     const int ntn = p.n_tiles_n, tiles_t = p.tiles_t;
     const int n_tiles = (int)num_tiles;
     int acc = 0; uint32_t acc_phase = 0;
-    int sbuf = 0;
+    int sbuf = 0; uint32_t sphase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int tm = tile / ntn;
       const int n0 = (tile - tm * ntn) * BN;
@@ -219,11 +250,6 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
       else out_off = row * p.c_out_valid + n0 + cb;
       uint8_t* stage_row = s_stage + (size_t)sbuf * (BN / 64) * kABytes + (size_t)r * 128;
 
-      if (p.tma_store) {
-        // the store issued from this staging buffer (stage_bufs tiles ago) must have finished reading it
-        if (threadIdx.x == 64) { if (p.stage_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read0(); }
-        named_bar_sync(1, 32 * kEpiWarps);
-      }
       const bool t3 = (tile == (int)blockIdx.x + 3 * (int)gridDim.x) && threadIdx.x == 64;   // 4th tile of CTA 0: steady state
       if (t3) TIK_T(12);
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -239,6 +265,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      // the store issued from this staging tile (stage_bufs tiles ago) must have finished reading it
+      if (p.tma_store) mbar_wait(&stage_empty[sbuf], sphase ^ 1);
       if ((valid || p.tma_store) && !(p.dbg_flags & 1)) {
 #pragma unroll
         for (int q = 0; q < CW / 8; ++q) {       // 8 columns = one 16-byte bf16 piece
@@ -291,24 +319,16 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
       if (t3) TIK_T(14);
       if (p.tma_store) {
         fence_proxy_async_smem();                           // st.shared -> visible to the TMA (async proxy)
-        named_bar_sync(1, 32 * kEpiWarps);
-        if (threadIdx.x == 64) {
-          const int t0s = tile_t * p.tt;
-          const int nv0s = tile_nv * p.vv;
-          for (int c = 0; c < ((p.dbg_flags & 16) ? 0 : BN / 64); ++c)
-            tma_store_3d(&p.map_out, s_stage + ((size_t)sbuf * (BN / 64) + c) * kABytes, n0 + c * 64, t0s, nv0s);
-          if (!(p.dbg_flags & 16)) tma_store_commit();
-          if (tile == blockIdx.x) TIK_T(7);
-          if (t3) TIK_T(15);
-        }
-        if (p.stage_bufs == 2) sbuf ^= 1;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stage_full[sbuf]);      // 16 warps -> the store warp issues the tile
+        if (tile == blockIdx.x && threadIdx.x == 64) TIK_T(7);
+        if (t3) TIK_T(15);
+        if (p.stage_bufs == 2) { if (++sbuf == 2) { sbuf = 0; sphase ^= 1; } } else { sphase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
   if (threadIdx.x == 64) TIK_T(8);
-  if (p.tma_store && threadIdx.x == 64) tma_store_wait0();
-  if (threadIdx.x == 64) TIK_T(9);
   __syncwarp();
   tc_fence_before();
   __syncthreads();
