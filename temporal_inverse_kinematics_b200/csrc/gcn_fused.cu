@@ -28,6 +28,7 @@ namespace tik {
 constexpr int kGfThreads = 64 + 32 * 16;
 constexpr int kGfTile = 16384;                     // one 128-row x 64-channel swizzled slab
 constexpr int kGfSmemBudget = 225 * 1024;
+constexpr int kGfMaxBufs = 8;                      // input tiles in flight: the kernel is HBM-latency bound otherwise
 
 // MN-major operand, 128-byte swizzle: 64 contiguous elements per row, 8-row groups 1024 B apart (SBO),
 // next 64-element block of the MN dimension `lbo` bytes away (LBO).
@@ -74,9 +75,9 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
   uint8_t* s_x = smem + p.off_x;                      // xbufs x KC1 slabs
   uint8_t* s_stage = smem + p.off_stage;              // KC2 slabs
   float* s_bias = reinterpret_cast<float*>(smem + p.off_bias);
-  uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [2]
-  uint64_t* x_empty = x_full + 2;                     // [2]
-  uint64_t* w_full = x_empty + 2;
+  uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [kGfMaxBufs]
+  uint64_t* x_empty = x_full + kGfMaxBufs;            // [kGfMaxBufs]
+  uint64_t* w_full = x_empty + kGfMaxBufs;
   uint64_t* d1_full = w_full + 1;
   uint64_t* xagg_full = d1_full + 1;
   uint64_t* d2_full = xagg_full + 1;
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
     tma_prefetch_desc(&p.map_x); tma_prefetch_desc(&p.map_out); tma_prefetch_desc(&p.map_abd); tma_prefetch_desc(&p.map_w);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < kGfMaxBufs; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
     mbar_init(w_full, 1); mbar_init(d1_full, 1); mbar_init(xagg_full, 16); mbar_init(d2_full, 1); mbar_init(d2_empty, 16);
     fence_barrier_init();
   }
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
         mbar_expect_tx(&x_full[b], x_bytes);
         for (int kc = 0; kc < KC1; ++kc)
           tma_load_4d(s_x + ((size_t)b * KC1 + kc) * kGfTile, &p.map_x, &x_full[b], kc * 64, t0, 0, n);
-        if (p.xbufs == 2) { if (++b == 2) { b = 0; phase ^= 1; } } else { phase ^= 1; }
+        if (++b == p.xbufs) { b = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
         umma_commit(d2_full);
         umma_commit(&x_empty[b]);                            // the tile buffer may be refilled once MMA 2 has read it
         tphase ^= 1;
-        if (p.xbufs == 2) { if (++b == 2) { b = 0; phase ^= 1; } } else { phase ^= 1; }
+        if (++b == p.xbufs) { b = 0; phase ^= 1; }
       }
     }
   } else {
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
         tma_store_commit();
       }
       tphase ^= 1;
-      if (p.xbufs == 2) b ^= 1;
+      if (++b == p.xbufs) b = 0;
     }
     if (threadIdx.x == 64) tma_store_wait0();
   }
@@ -336,8 +337,9 @@ int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float
   const int w_bytes = kc1 * cout * 128;
   const int bias_bytes = (V * cout * 4 + 1023) / 1024 * 1024;
   const int fixed = 2 * kGfTile + w_bytes + kc2 * kGfTile + bias_bytes + 256;
-  p.xbufs = (fixed + 2 * kc1 * kGfTile <= kGfSmemBudget) ? 2 : 1;
-  if (fixed + p.xbufs * kc1 * kGfTile > kGfSmemBudget) {
+  p.xbufs = (kGfSmemBudget - fixed) / (kc1 * kGfTile);
+  if (p.xbufs > kGfMaxBufs) p.xbufs = kGfMaxBufs;
+  if (p.xbufs < 1) {
     delete g;
     set_error("fused gcn: shared memory plan does not fit");
     return TIK_ERR_UNSUPPORTED;

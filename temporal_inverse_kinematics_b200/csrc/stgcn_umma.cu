@@ -39,7 +39,7 @@ constexpr int kChunkK = 64;                       // bf16 elements per K chunk =
 constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KB
 constexpr int kEpiWarps = 16;                     // four warps per TMEM lane group, each takes a quarter of the columns
 constexpr int kUmmaThreads = 64 + 32 * kEpiWarps + 32;   // + one TMA-store warp
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 constexpr int kSmemBudget = 225 * 1024;
 
 struct UmmaParams {
