@@ -125,71 +125,101 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      if (p.w_resident) {
-        mbar_expect_tx(w_full, (uint32_t)(p.total_chunks * kBBytes));
-        for (int kc = 0; kc < p.total_chunks; ++kc) tma_load_2d(w_res + (size_t)kc * kBBytes, &p.map_w, w_full, kc * kChunkK, 0);
-      }
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < (int)num_tiles; tile += gridDim.x) {
-        const int tm = tile / p.n_tiles_n;
-        const int n0 = (tile - tm * p.n_tiles_n) * BN;
-        const int t0 = (tm % p.tiles_t) * p.tt;
-        const int nv0 = (tm / p.tiles_t) * p.vv;
-        int kw = 0;
-        for (int s = 0; s < p.n_slabs; ++s) {
-          const int ts = t0 * p.t_mul[s] + p.t_off[s];
-          for (int c = 0; c < p.chunks[s]; ++c, ++kw) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = ring + (size_t)stage * stage_bytes;
-            if (p.dbg_flags & 8) {
+    // The whole warp runs the loop (warp-uniform control flow keeps addresses / coordinates in uniform registers);
+    // lane 0 issues.
+    const bool leader = lane == 0;
+    if (p.w_resident && leader) {
+      mbar_expect_tx(w_full, (uint32_t)(p.total_chunks * kBBytes));
+      for (int kc = 0; kc < p.total_chunks; ++kc) tma_load_2d(w_res + (size_t)kc * kBBytes, &p.map_w, w_full, kc * kChunkK, 0);
+    }
+    const uint32_t tx_bytes = (uint32_t)(p.a_box_bytes + (p.w_resident ? 0 : kBBytes));
+    const bool skip_a = (p.dbg_flags & 8) != 0;
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < (int)num_tiles; tile += gridDim.x) {
+      const int tm = tile / p.n_tiles_n;
+      const int n0 = (tile - tm * p.n_tiles_n) * BN;
+      const int tile_nv = tm / p.tiles_t;
+      const int t0 = (tm - tile_nv * p.tiles_t) * p.tt;
+      const int nv0 = tile_nv * p.vv;
+      int kw = 0;
+      for (int s = 0; s < p.n_slabs; ++s) {
+        const int ts = t0 * p.t_mul[s] + p.t_off[s];
+        const int nc = p.chunks[s];
+        for (int c = 0; c < nc; ++c, ++kw) {
+          const bool p3 = leader && kw == 0 && tile == (int)blockIdx.x + 3 * (int)gridDim.x;
+          if (p3) TIK_T(25);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (p3) TIK_T(26);
+          uint8_t* sa = ring + (size_t)stage * stage_bytes;
+          if (leader) {
+            if (skip_a) {
               if (p.w_resident) { mbar_arrive(&full_bar[stage]); }
               else { mbar_expect_tx(&full_bar[stage], (uint32_t)kBBytes); tma_load_2d(sa + kABytes, &p.map_w, &full_bar[stage], kw * kChunkK, n0); }
-              if (++stage == stages) { stage = 0; phase ^= 1; }
-              continue;
+            } else {
+              mbar_expect_tx(&full_bar[stage], tx_bytes);
+              tma_load_3d(sa, &p.map_a[s], &full_bar[stage], c * kChunkK, ts, nv0);
+              if (!p.w_resident) tma_load_2d(sa + kABytes, &p.map_w, &full_bar[stage], kw * kChunkK, n0);
             }
-            mbar_expect_tx(&full_bar[stage], (uint32_t)(p.a_box_bytes + (p.w_resident ? 0 : kBBytes)));
-            tma_load_3d(sa, &p.map_a[s], &full_bar[stage], c * kChunkK, ts, nv0);
-            if (!p.w_resident) tma_load_2d(sa + kABytes, &p.map_w, &full_bar[stage], kw * kChunkK, n0);
-            if (++stage == stages) { stage = 0; phase ^= 1; }
           }
-        }
-        if (tile == blockIdx.x) TIK_T(2);
-      }
-      TIK_T(11);
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN);
-      if (p.w_resident) mbar_wait(w_full, 0);
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < (int)num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);        // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kc = 0; kc < p.total_chunks; ++kc) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          if (tile == blockIdx.x && kc == 0) TIK_T(3);
-          const uint32_t sa = smem_u32(ring + (size_t)stage * stage_bytes);
-          const uint32_t sb = p.w_resident ? smem_u32(w_res + (size_t)kc * kBBytes) : sa + kABytes;
-          uint64_t da = make_smem_desc_kmajor_sw128(sa + (uint32_t)p.dbg_shift_rows * 128u);
-          if (p.dbg_base_offset_mode) da |= (uint64_t)(((sa + (uint32_t)p.dbg_shift_rows * 128u) >> 7) & 7u) << 49;
-          const uint64_t db = make_smem_desc_kmajor_sw128(sb);
-#pragma unroll
-          for (int k = 0; k < ((p.dbg_flags & 4) ? 0 : kChunkK / 16); ++k) {
-            // advance 16 bf16 = 32 B along K inside the swizzled row: +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);                  // frees this ring slot once the MMAs have read it
+          if (p3) TIK_T(27);
+          __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
+      }
+      if (tile == blockIdx.x && leader) TIK_T(2);
+    }
+    if (leader) TIK_T(11);
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // Warp-uniform loop, one lane issues tcgen05.mma / tcgen05.commit.
+    constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN);
+    const bool leader = lane == 0;
+    const bool skip_mma = (p.dbg_flags & 4) != 0;
+    if (p.w_resident) mbar_wait(w_full, 0);
+    const uint32_t ring_u32 = smem_u32(ring), wres_u32 = smem_u32(w_res);
+    const uint64_t desc_hi = make_smem_desc_kmajor_sw128(0);          // everything but the start address
+    const uint32_t shift_bytes = (uint32_t)p.dbg_shift_rows * 128u;
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    const int total_chunks = p.total_chunks;
+    for (int tile = blockIdx.x; tile < (int)num_tiles; tile += gridDim.x) {
+      const bool m3 = leader && tile == (int)blockIdx.x + 3 * (int)gridDim.x;
+      if (m3) TIK_T(16);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);        // epilogue has drained this accumulator
+      tc_fence_after();
+      if (m3) TIK_T(17);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      for (int kc = 0; kc < total_chunks; ++kc) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (m3 && kc < 2) TIK_T(18 + 3 * kc);
+        if (tile == blockIdx.x && kc == 0 && leader) TIK_T(3);
+        const uint32_t sa = ring_u32 + (uint32_t)stage * (uint32_t)stage_bytes;
+        const uint32_t sb = p.w_resident ? wres_u32 + (uint32_t)kc * (uint32_t)kBBytes : sa + kABytes;
+        // descriptor = constant high part | (address >> 4); +2 per 16-element (32 B) K step inside the swizzled row
+        uint64_t da = desc_hi | (uint64_t)(((sa + shift_bytes) >> 4) & 0x3FFF);
+        if (p.dbg_base_offset_mode) da |= (uint64_t)(((sa + shift_bytes) >> 7) & 7u) << 49;
+        const uint64_t db = desc_hi | (uint64_t)((sb >> 4) & 0x3FFF);
+        if (leader) {
+          if (!skip_mma) {
+#pragma unroll
+            for (int k = 0; k < kChunkK / 16; ++k)
+              umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+          }
+          if (m3 && kc < 2) TIK_T(19 + 3 * kc);
+          umma_commit(&empty_bar[stage]);                  // frees this ring slot once the MMAs have read it
+          if (m3 && kc < 2) TIK_T(20 + 3 * kc);
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+      if (leader) {
         umma_commit(&tmem_full[acc]);                      // accumulator complete -> epilogue
         if (tile == blockIdx.x) TIK_T(4);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (m3) TIK_T(24);
       }
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp == 2 + kEpiWarps) {
     // ===================== TMA-store warp =====================
@@ -203,7 +233,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
         const int n0 = (tile - tm * ntn) * BN;
         const int tile_nv = tm / tiles_t, tile_t = tm - tile_nv * tiles_t;
         mbar_wait(&stage_full[sbuf], sphase);
-        for (int c = 0; c < BN / 64; ++c)
+        for (int c = 0; c < ((p.dbg_flags & 16) ? 0 : BN / 64); ++c)
           tma_store_3d(&p.map_out, s_stage + ((size_t)sbuf * (BN / 64) + c) * kABytes, n0 + c * 64, tile_t * p.tt, tile_nv * p.vv);
         tma_store_commit();
         if (p.stage_bufs == 2) {

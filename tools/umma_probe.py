@@ -24,7 +24,9 @@ def bench(fn, reps=20):
 
 
 NAMES = ["entry", "setup", "prod_tile0", "mma_full0", "mma_done0", "epi_full0", "epi_body0", "epi_store0", "epi_end", "store_wait",
-         "exit", "prod_end", "t3_start", "t3_full", "t3_body", "t3_store"]
+         "exit", "prod_end", "t3_start", "t3_full", "t3_body", "t3_store",
+         "M.top", "M.tmem_empty", "M.full0", "M.issued0", "M.commit0", "M.full1", "M.issued1", "M.commit1", "M.done", "P.top", "P.empty", "P.issued",
+         "x28", "x29", "x30", "x31"]
 
 
 def _print_tl(fl, tl):
@@ -41,7 +43,7 @@ def case(name, n, t_in, t_out, cin_slabs, c_out, stride, residual):
     slabs = []
     for i, c in enumerate(cin_slabs):
         off = (i - 1) if (len(cin_slabs) >= 3 and i < 3) else 0
-        slabs.append((by_c[c], stride, off))
+        slabs.append((by_c[c], stride if t_in != t_out or i < 3 else 1, off))
     w = (torch.randn(c_out, sum(cin_slabs), device="cuda", generator=g) * 0.05).bfloat16()
     b = torch.zeros(1, c_out, device="cuda")
     res = torch.randn(nv, t_out, c_out, device="cuda", generator=g).bfloat16() if residual else None
@@ -53,7 +55,7 @@ def case(name, n, t_in, t_out, cin_slabs, c_out, stride, residual):
         out.append(f"flags={flags}: {us:7.1f}us")
     lib.tik_debug_set_umma_shift(0, 0)
     for fl in (0, 16):
-        tb = torch.zeros(16, dtype=torch.int64, device="cuda")
+        tb = torch.zeros(32, dtype=torch.int64, device="cuda")
         lib.tik_debug_set_umma_times(_lib.ptr(tb))
         lib.tik_debug_set_umma_shift(0, fl << 8)
         for _ in range(3):
@@ -75,7 +77,37 @@ def case(name, n, t_in, t_out, cin_slabs, c_out, stride, residual):
     print(f"{name}: tiles={tiles} | " + " | ".join(out), flush=True)
 
 
+def big():
+    """Whole-batch sized b1 temporal conv (4096 clips): which resource binds when everything streams from HBM?"""
+    V, n, T, C = 17, 4096, 64, 64
+    nv = n * V
+    g = torch.Generator(device="cuda").manual_seed(0)
+    h = torch.randn(nv, T, C, device="cuda", generator=g).bfloat16()
+    r0 = torch.randn(nv, T, C, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(C, 4 * C, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.zeros(1, C, device="cuda")
+    lib = _lib.lib()
+    for name, slabs in [("3 taps + residual slab", [(h, 1, -1), (h, 1, 0), (h, 1, 1), (r0, 1, 0)]),
+                        ("1 tap + residual slab (x2 K)", [(h, 1, 0), (r0, 1, 0), (h, 1, 0), (r0, 1, 0)]),
+                        ("1 tap only (K=64)", [(h, 1, 0)])]:
+        ww = w[:, : 64 * len(slabs)].contiguous()
+        res = []
+        for flags in (0, 16, 1, 1 | 16, 8, 8 | 1 | 16):
+            lib.tik_debug_set_umma_shift(0, flags << 8)
+            us = bench(lambda: ops.rowgemm(slabs, ww, b, nv, V, T, act="relu"), reps=5)
+            res.append(f"flags={flags}: {us:7.1f}us")
+        lib.tik_debug_set_umma_shift(0, 0)
+        print(f"big {name}: " + " | ".join(res), flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "big":
+        big()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "tl":
+        case("b1 tcn  3x64    T64 +slab", 128, 64, 64, [64, 64, 64, 64], 64, 1, False)
+        case("b3 tcn  3x128+128 T32", 128, 32, 32, [128, 128, 128, 128], 128, 1, False)
+        sys.exit(0)
     case("b1 gcn  64->64  T64", 128, 64, 64, [64], 64, 1, False)
     case("b1 tcn  3x64    T64 +res", 128, 64, 64, [64, 64, 64], 64, 1, True)
     case("b3 gcn 128->128 T32", 128, 32, 32, [128], 128, 1, False)
