@@ -36,8 +36,26 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def _ncu_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum per tensor-core launch, averaged over one step of the committed
+    ncu capture (profiles/r1_launches_final.csv); None if the capture is absent."""
+    import csv
+    p = os.path.join(ROOT, "profiles", "r1_launches_final.csv")
+    if not os.path.exists(p):
+        return None
+    per = {}
+    with open(p) as f:
+        rows = [r for r in csv.reader(l for l in f if l.startswith('"'))]
+    hdr = rows[0]
+    ki, mi, vi, ii = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
+    for r in rows[1:]:
+        if ("rowgemm_umma" in r[ki] or "gcn_fused" in r[ki]) and r[mi].startswith("dram__bytes"):
+            per[r[ii]] = per.get(r[ii], 0.0) + float(r[vi].replace(",", ""))
+    return sum(per.values()) / len(per) if per else None
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -47,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -222,7 +240,7 @@ def run_ours(args):
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_source": (peak_src + " bf16_tflops_sustained (kernel timed inside a long step)") if args.dtype == "bf16" else "nominal fp32 SIMT 148 SM x 128 FMA x 2 x 1.965 GHz",
                     "launches": g_n, "avg_launch_us": g_ms * 1e3 / max(g_n, 1), "flops_per_step": gemm_flops,
-                    "kernel_ms_per_step": {k: v[0] for k, v in kinds.items()}, "traffic": None}
+                    "kernel_ms_per_step": {k: v[0] for k, v in kinds.items()}, "traffic": _ncu_traffic_per_launch()}
         line = {"metric": METRIC, "value": world * B * T / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.dtype, "data": "synthetic",
@@ -232,7 +250,8 @@ def run_ours(args):
                            "l2": "flushed between timed steps (256 MiB memset)", "parallelism": f"dp{world}",
                            "gather": "NCCL all_gather of poses each step" if world > 1 else "none"},
                 "e2e": {"value": world * B * T / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                        "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": (out_p.numel() + out_j.numel()) * 4},
+                        "h2d_bytes_per_step": world * x_host.numel() * 4,
+                        "d2h_bytes_per_step": world * (out_p.numel() + out_j.numel()) * 4},
                 "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline}
         if world == 1 and not args.no_cpu:
             torch.set_num_threads(os.cpu_count() or 1)
