@@ -89,6 +89,15 @@ int tik_stem_gcn(int dtype, const float* x_dev, const float* in_scale_dev, const
                  const float* res_w_dev, void* res_out_dev, int res_stride,
                  int64_t N, int T, int V, int Cin, int K, int Cout, int relu, void* stream);
 
+/* Window mode of the stem: instead of materialised (N,T,V,C) clips the stem reads one
+ * resident sequence (frames,V,C); clip n, frame t is sequence frame clamp(n*stride + t + offset, 0, frames-1) --
+ * the edge padding of sample_window (mmskeleton/datasets/data_amass.py:18-42) -- minus the root
+ * 0.5*(kp[root_a] + kp[root_b]) of that frame (InferenceDataset, data_amass.py:232-235; root_a < 0: no centring). */
+typedef struct TikWindowing {
+  int64_t frames;
+  int32_t offset, stride, root_a, root_b;
+} TikWindowing;
+
 /* Adjacency aggregation: out[k][(n,w),t,c] = sum_v agg[k][v][w] * x[(n,v),t,c].
  * The einsum 'nkctv,kvw->nctw' of gconv_origin.py:63 moved in front of the 1x1 convolution
  * (SURVEY.md Appendix B).  x (N,V,T,C) dtype -> out (K,N,V,T,C) dtype. */
@@ -195,6 +204,11 @@ int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int64_t
  * processes n_chunk clips at a time and the head n_max clips at a time. */
 int tik_stgcn_plan_run(TikPlan* plan, const float* x_dev, int64_t N, float* poses_dev, void* feat_dev,
                        void* stream);
+/* Same network over sliding windows of ONE sequence: seq_dev (frames,V,c_in) fp32 replaces the (N,T,V,c_in) batch,
+ * n_windows windows of the plan's T frames each (see TikWindowing).  Replaces InferenceDataset + DataLoader +
+ * model(...) of inference.py:37-52 without materialising the windows. */
+int tik_stgcn_plan_run_windows(TikPlan* plan, const float* seq_dev, const TikWindowing* win, int64_t n_windows,
+                               float* poses_dev, void* feat_dev, void* stream);
 /* Measurement aid (synchronises the stream): one run with CUDA events around every kernel.
  * ms_by_kind[3] / launches_by_kind[3] = {stem, aggregate, implicit-GEMM}; flops_gemm = algorithmic
  * 2*rows*K*c_out summed over the implicit-GEMM launches. */

@@ -26,6 +26,10 @@ class TikRowGemm(C.Structure):
                 ("out_layout", i32)]
 
 
+class TikWindowing(C.Structure):
+    _fields_ = [("frames", i64), ("offset", i32), ("stride", i32), ("root_a", i32), ("root_b", i32)]
+
+
 class TikBlock(C.Structure):
     _fields_ = [("c_in", i32), ("c_out", i32), ("stride", i32), ("kt", i32), ("res_kind", i32),
                 ("agg_dev", vp), ("w_gcn_dev", vp), ("b_gcn_dev", vp), ("w_tcn_dev", vp), ("b_tcn_dev", vp),
@@ -56,6 +60,7 @@ _PROTOS = {
     "tik_stgcn_workspace_bytes": (C.c_int, [C.POINTER(TikNet), C.c_int, i64, i64, C.c_int, C.POINTER(i64)]),
     "tik_stgcn_plan_create": (C.c_int, [C.POINTER(TikNet), C.c_int, i64, i64, C.c_int, vp, i64, C.POINTER(vp)]),
     "tik_stgcn_plan_run": (C.c_int, [vp, vp, i64, vp, vp, vp]),
+    "tik_stgcn_plan_run_windows": (C.c_int, [vp, vp, C.POINTER(TikWindowing), i64, vp, vp, vp]),
     "tik_stgcn_plan_profile": (C.c_int, [vp, vp, i64, vp, vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]),
     "tik_stgcn_plan_launches": (i64, [vp, i64]),
     "tik_stgcn_plan_destroy": (None, [vp]),

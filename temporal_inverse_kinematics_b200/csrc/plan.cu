@@ -134,14 +134,15 @@ static void ws_layout(const TikNet* net, int dtype, int64_t n, int64_t n_max, in
   L->total_bytes = off;
 }
 
-static int run_step(TikPlan* P, Step& st, const float* xc, int64_t n, int64_t clip_off, float* poses, cudaStream_t s) {
+static int run_step(TikPlan* P, Step& st, const float* xc, int64_t n, int64_t clip_off, float* poses, cudaStream_t s,
+                    const TikWindowing* win = nullptr, int64_t win_n0 = 0) {
   const TikNet& net = P->net;
   const int V = net.V;
   if (st.kind == Step::STEM) {
     const TikBlock& b = *st.blk;
-    return tik_stem_gcn(P->dtype, xc, net.in_scale_dev, net.in_shift_dev, b.agg_dev, reinterpret_cast<const float*>(b.w_gcn_dev),
-                        b.b_gcn_dev, st.dst, st.dst2 ? b.w_res_stem_dev : nullptr, st.dst2, b.stride, n, st.t, V, b.c_in, net.K,
-                        b.c_out, 1, s);
+    return stem_gcn_impl(P->dtype, xc, net.in_scale_dev, net.in_shift_dev, b.agg_dev, reinterpret_cast<const float*>(b.w_gcn_dev),
+                         b.b_gcn_dev, st.dst, st.dst2 ? b.w_res_stem_dev : nullptr, st.dst2, b.stride, n, st.t, V, b.c_in, net.K,
+                         b.c_out, 1, win, win_n0, s);
   }
   if (st.kind == Step::AGG) {
     // planes are spaced for a full chunk (the tensor maps are baked for n_chunk clips)
@@ -161,7 +162,8 @@ static int run_step(TikPlan* P, Step& st, const float* xc, int64_t n, int64_t cl
 }
 
 static int run_impl(TikPlan* P, const float* x, int64_t N, float* poses, void* feat_out, cudaStream_t s,
-                    std::vector<cudaEvent_t>* events, std::vector<std::pair<Step*, int64_t>>* trace) {
+                    std::vector<cudaEvent_t>* events, std::vector<std::pair<Step*, int64_t>>* trace,
+                    const TikWindowing* win = nullptr) {
   const TikNet& net = P->net;
   const int V = net.V, T = P->T;
   auto mark = [&](Step* st, int64_t n) -> int {
@@ -177,11 +179,11 @@ static int run_impl(TikPlan* P, const float* x, int64_t N, float* poses, void* f
     const int64_t nb = std::min<int64_t>(P->n_max, N - b0);
     for (int64_t n0 = 0; n0 < nb; n0 += P->n_chunk) {
       const int64_t n = std::min<int64_t>(P->n_chunk, nb - n0);
-      const float* xc = x + (b0 + n0) * (int64_t)T * V * net.c_in;
+      const float* xc = win ? x : x + (b0 + n0) * (int64_t)T * V * net.c_in;   // window mode: x is the whole sequence
       for (auto& st : P->chunk_steps) {
         int rc = mark(&st, n);
         if (rc != TIK_OK) return rc;
-        rc = run_step(P, st, xc, n, n0, nullptr, s);
+        rc = run_step(P, st, xc, n, n0, nullptr, s, win, b0 + n0);
         if (rc != TIK_OK) return rc;
       }
     }
@@ -373,6 +375,16 @@ int tik_stgcn_plan_run(TikPlan* P, const float* x, int64_t N, float* poses, void
   TIK_CHECK_ARG(P && x && N >= 0, "bad arguments");
   TIK_CHECK_ARG(P->net.head_hidden == 0 || poses, "poses pointer required");
   return run_impl(P, x, N, poses, feat_out, (cudaStream_t)stream, nullptr, nullptr);
+}
+
+int tik_stgcn_plan_run_windows(TikPlan* P, const float* seq, const TikWindowing* win, int64_t n_windows, float* poses,
+                               void* feat_out, void* stream) {
+  using namespace tik;
+  TIK_CHECK_ARG(P && seq && win && n_windows >= 0, "bad arguments");
+  TIK_CHECK_ARG(win->frames > 0 && win->stride >= 1, "windowing needs frames > 0 and stride >= 1");
+  TIK_CHECK_ARG(P->net.blocks[0].res_kind != TIK_RES_STEM || P->net.blocks[0].c_in <= 8, "window mode needs the stem path");
+  TIK_CHECK_ARG(P->net.head_hidden == 0 || poses, "poses pointer required");
+  return run_impl(P, seq, n_windows, poses, feat_out, (cudaStream_t)stream, nullptr, nullptr, win);
 }
 
 int tik_stgcn_plan_profile(TikPlan* P, const float* x, int64_t N, float* poses, void* stream, double* ms_by_kind,

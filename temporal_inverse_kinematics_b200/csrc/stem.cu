@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kStemThreads)
 stem_gcn_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, const float* __restrict__ in_shift,
                 const float* __restrict__ agg, const float* __restrict__ w, const float* __restrict__ bias,
                 OutT* __restrict__ out, const float* __restrict__ res_w, OutT* __restrict__ res_out, int res_stride,
-                int T, int V, int Cin, int K, int Cout, int relu) {
+                int T, int V, int Cin, int K, int Cout, int relu, const TikWindowing win, long long win_n0) {
   extern __shared__ __align__(16) float smem[];
   const int KC = K * Cin, VC = V * Cin;
   float* s_raw = smem;                                // [frames][V*Cin] raw input
@@ -65,8 +65,22 @@ stem_gcn_kernel(const float* __restrict__ x, const float* __restrict__ in_scale,
   float* s_bn = s_rw + (res_w != nullptr ? V * Cin * Cout : 0);   // [frames][V*Cin] after data_bn
   const float* gx = x + (n * T + t0) * (int64_t)VC;   // (N,T,V,C): frames contiguous
   for (int i = threadIdx.x; i < nf * VC; i += kStemThreads) {
-    const float raw = __ldg(gx + i);
     const int vc = i % VC;
+    float raw;
+    if (win.frames > 0) {
+      // window mode: clip n is a window of one resident sequence (F,V,C); frame = clamp(n*stride + t + offset),
+      // i.e. sample_window's edge padding (data_amass.py:18-42), root-centred on 0.5*(kp[a]+kp[b]) (:232-235)
+      long long fi = (win_n0 + (long long)n) * win.stride + (t0 + i / VC) + win.offset;
+      fi = fi < 0 ? 0 : (fi >= win.frames ? win.frames - 1 : fi);
+      const float* fr = x + fi * VC;
+      raw = __ldg(fr + vc);
+      if (win.root_a >= 0) {
+        const int c = vc % Cin;
+        raw -= 0.5f * (__ldg(fr + win.root_a * Cin + c) + __ldg(fr + win.root_b * Cin + c));
+      }
+    } else {
+      raw = __ldg(gx + i);
+    }
     s_raw[i] = raw;
     s_bn[i] = fmaf(raw, __ldg(in_scale + vc), __ldg(in_shift + vc));
   }
@@ -123,7 +137,7 @@ stem_gcn_kernel(const float* __restrict__ x, const float* __restrict__ in_scale,
 template <class T>
 static int launch_stem(const float* x, const float* sc, const float* sh, const float* agg, const float* w,
                        const float* bias, void* out, const float* res_w, void* res_out, int res_stride, int64_t N,
-                       int Tn, int V, int Cin, int K, int Cout, int relu, cudaStream_t s) {
+                       int Tn, int V, int Cin, int K, int Cout, int relu, const TikWindowing& win, int64_t win_n0, cudaStream_t s) {
   const size_t KC = (size_t)K * Cin;
   size_t smem = sizeof(float) * (2 * (size_t)kStemFrames * V * Cin + (size_t)kStemFrames * V * KC + KC * Cout +
                                  (size_t)V * Cout + (size_t)K * V * V + (res_w ? (size_t)V * Cin * Cout : 0));
@@ -139,17 +153,36 @@ static int launch_stem(const float* x, const float* sc, const float* sh, const f
   TIK_CHECK_ARG(blocks < (1ll << 31), "grid too large");
   stem_gcn_kernel<T><<<(unsigned)blocks, kStemThreads, smem, s>>>(x, sc, sh, agg, w, bias, reinterpret_cast<T*>(out), res_w,
                                                                    reinterpret_cast<T*>(res_out), res_stride, Tn, V, Cin, K,
-                                                                   Cout, relu);
+                                                                   Cout, relu, win, (long long)win_n0);
   TIK_LAUNCH_CHECK();
   return TIK_OK;
 }
 
 }  // namespace tik
 
+namespace tik {
+int stem_gcn_impl(int dtype, const float* x, const float* in_scale, const float* in_shift, const float* agg,
+                  const float* w, const float* bias, void* out, const float* res_w, void* res_out,
+                  int res_stride, int64_t N, int T, int V, int Cin, int K, int Cout, int relu,
+                  const TikWindowing* winp, int64_t win_n0, cudaStream_t s);
+}
+
 extern "C" int tik_stem_gcn(int dtype, const float* x, const float* in_scale, const float* in_shift, const float* agg,
                             const float* w, const float* bias, void* out, const float* res_w, void* res_out,
                             int res_stride, int64_t N, int T, int V, int Cin, int K, int Cout, int relu, void* stream) {
+  return tik::stem_gcn_impl(dtype, x, in_scale, in_shift, agg, w, bias, out, res_w, res_out, res_stride, N, T, V, Cin, K, Cout,
+                            relu, nullptr, 0, (cudaStream_t)stream);
+}
+
+int tik::stem_gcn_impl(int dtype, const float* x, const float* in_scale, const float* in_shift, const float* agg,
+                       const float* w, const float* bias, void* out, const float* res_w, void* res_out,
+                       int res_stride, int64_t N, int T, int V, int Cin, int K, int Cout, int relu,
+                       const TikWindowing* winp, int64_t win_n0, cudaStream_t s) {
   using namespace tik;
+  TikWindowing win;
+  if (winp) win = *winp; else { win.frames = 0; win.offset = 0; win.stride = 1; win.root_a = -1; win.root_b = -1; }
+  TIK_CHECK_ARG(win.frames == 0 || (win.stride >= 1 && win.root_a < V && win.root_b < V && (win.root_a < 0) == (win.root_b < 0)),
+                "stem: bad windowing");
   TIK_CHECK_ARG(x && in_scale && in_shift && agg && w && bias && out, "null pointer");
   TIK_CHECK_ARG(N >= 0 && T > 0 && V > 0 && V <= kStemMaxV && Cin > 0 && K > 0 && K <= 5 && K * Cin <= kStemMaxKC &&
                     Cout > 0 && Cout % 8 == 0,
@@ -157,11 +190,10 @@ extern "C" int tik_stem_gcn(int dtype, const float* x, const float* in_scale, co
   TIK_CHECK_ARG((res_w == nullptr) == (res_out == nullptr), "stem: res_w and res_out go together");
   TIK_CHECK_ARG(res_w == nullptr || res_stride >= 1, "stem: bad residual stride");
   if (N == 0) return TIK_OK;
-  cudaStream_t s = (cudaStream_t)stream;
   if (dtype == TIK_F32)
-    return launch_stem<float>(x, in_scale, in_shift, agg, w, bias, out, res_w, res_out, res_stride, N, T, V, Cin, K, Cout, relu, s);
+    return launch_stem<float>(x, in_scale, in_shift, agg, w, bias, out, res_w, res_out, res_stride, N, T, V, Cin, K, Cout, relu, win, win_n0, s);
   if (dtype == TIK_BF16)
-    return launch_stem<__nv_bfloat16>(x, in_scale, in_shift, agg, w, bias, out, res_w, res_out, res_stride, N, T, V, Cin, K, Cout, relu, s);
+    return launch_stem<__nv_bfloat16>(x, in_scale, in_shift, agg, w, bias, out, res_w, res_out, res_stride, N, T, V, Cin, K, Cout, relu, win, win_n0, s);
   set_error("bad dtype %d", dtype);
   return TIK_ERR_INVALID;
 }

@@ -46,5 +46,9 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 int rowgemm_f32(const TikRowGemm* d, cudaStream_t s);
 int rowgemm_bf16(const TikRowGemm* d, cudaStream_t s);
 int launch_batch_rodrigues(const float* aa, float* R9, int64_t M, cudaStream_t s);
+int stem_gcn_impl(int dtype, const float* x, const float* in_scale, const float* in_shift, const float* agg,
+                  const float* w, const float* bias, void* out, const float* res_w, void* res_out,
+                  int res_stride, int64_t N, int T, int V, int Cin, int K, int Cout, int relu,
+                  const TikWindowing* winp, int64_t win_n0, cudaStream_t s);
 
 }  // namespace tik

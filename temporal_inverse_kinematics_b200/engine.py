@@ -232,6 +232,16 @@ class Plan:
         entry[0].replay()
         return entry[1].clone()
 
+    def run_windows(self, seq, n_windows, offset, stride, root):
+        """Sliding windows of one resident sequence (F,V,C): window n, frame t = seq[clamp(n*stride + t + offset)],
+        root-centred on 0.5*(kp[root[0]] + kp[root[1]]) if root is given.  Nothing is materialised."""
+        p = self.packed
+        win = L.TikWindowing(seq.shape[0], offset, stride, root[0] if root else -1, root[1] if root else -1)
+        poses = torch.empty((n_windows, self.T_out, p.head_out), dtype=torch.float32, device=seq.device)
+        L.check(L.lib().tik_stgcn_plan_run_windows(self.handle, L.ptr(seq), C.byref(win), n_windows, L.ptr(poses), None,
+                                                   L.stream_ptr(seq.device)))
+        return poses
+
     def run(self, x, want_feat=False):
         p = self.packed
         N = x.shape[0]

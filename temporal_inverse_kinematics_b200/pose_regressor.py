@@ -64,6 +64,26 @@ class PoseRegressor(nn.Module, _ComputeDtypeMixin):
         return {"poses": poses}
 
 
+    def forward_windows(self, seq, win_frames, offset=0, stride=1, root=None, n_windows=None):
+        """Sliding-window inference over ONE sequence without materialising the windows.
+
+        seq (F, V, C) CUDA fp32.  Window n, frame t is seq[clamp(n*stride + t + offset, 0, F-1)], optionally
+        root-centred on 0.5*(kp[root[0]] + kp[root[1]]).  `offset=-(win//2)` with one window per frame reproduces
+        InferenceDataset / sample_window (reference data_amass.py:18-42,221-236); `offset=0` gives plain
+        [n, n+win) windows (BASELINE config 5).  Returns {'poses': (n_windows, T', 66)}."""
+        engine.require_cuda_eval(self, seq, "PoseRegressor.forward_windows")
+        if seq.dim() != 3 or seq.shape[1] != self.backbone.A.size(1) or seq.shape[2] != self.backbone.st_gcn_networks[0].in_channels:
+            raise ValueError(f"expected a (F, {self.backbone.A.size(1)}, C) sequence, got {tuple(seq.shape)}")
+        seq = seq.detach().float().contiguous()
+        F = seq.shape[0]
+        if n_windows is None:
+            n_windows = F if offset < 0 else max(0, (F - win_frames - offset) // stride + 1)
+        if n_windows == 0:
+            return {"poses": seq.new_zeros((0, self.backbone.out_frames(win_frames), self.pose_dim))}
+        plan = self.plan_for(n_windows, win_frames)
+        return {"poses": plan.run_windows(seq, n_windows, offset, stride, root)}
+
+
 class IKPoseTrainer(nn.Module, _ComputeDtypeMixin):
     """Inference-side stand-in for the reference LightningModule (pose_trainer.py:136-144): same attribute
     names (``hparams``, ``regressor``, ``device``), same forward, loads Lightning checkpoints."""

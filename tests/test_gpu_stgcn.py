@@ -154,3 +154,51 @@ def test_cuda_graph_replay_matches_eager():
     x2 = synth.make_clips(6, 32, seed=6).cuda()                          # new address -> new graph
     want = sp.regressor_forward(sd, x2.cpu())["poses"]
     assert float((m(x2)["poses"].cpu() - want).abs().max()) < TOL_BF16_ABS
+
+
+def test_run_inference_matches_reference_pipeline(golden):
+    """inference.run_inference on dance_contemporary.npz: GPU windowing + root-centring + model vs the reference's
+    host pipeline outputs (tests/golden/dance.npz)."""
+    from temporal_inverse_kinematics_b200 import inference, keypoints_util
+    from temporal_inverse_kinematics_b200.pose_regressor import IKPoseTrainer
+    g = golden("dance.npz")
+    names = [str(s) for s in g["joint_3d_names"]]
+    seq = keypoints_util.moveai_to_coco(g["joints_3d"], names)
+    assert np.array_equal(seq, g["coco_seq"])
+    tr = IKPoseTrainer().eval()
+    sd = synth.make_regressor_state(sp.build_adjacency("coco", "uniform", 2, 1), seed=0)
+    tr.regressor.load_state_dict(sd, strict=True)
+    tr = tr.cuda()
+    out = inference.run_inference(tr, seq)
+    assert out.shape == (231, 66)
+    assert np.abs(out - g["poses"][:, 0]).max() < TOL_F32
+
+
+@pytest.mark.parametrize("win,offset,stride", [(9, -4, 1), (16, 0, 1), (13, 0, 3), (64, -32, 5)])
+def test_forward_windows_equals_materialised_windows(win, offset, stride):
+    m, sd = _model()
+    F = 150
+    seq = synth.make_clips(1, F, seed=33)[0]                          # (F,17,3)
+    n_windows = F if offset < 0 else (F - win - offset) // stride + 1
+    idx = (torch.arange(n_windows)[:, None] * stride + torch.arange(win)[None, :] + offset).clamp(0, F - 1)
+    wins = seq[idx]                                                   # (n, win, 17, 3)
+    wins = wins - 0.5 * (wins[:, :, 11] + wins[:, :, 12])[:, :, None, :]
+    want = m(wins.cuda())["poses"]
+    got = m.forward_windows(seq.cuda(), win, offset=offset, stride=stride, root=(11, 12), n_windows=n_windows)["poses"]
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) < 1e-5
+
+
+def test_window_mean_matches_reference_loop():
+    from temporal_inverse_kinematics_b200.inference import window_mean
+    F, hw, D = 23, 2, 5
+    preds = torch.randn(F, 2 * hw + 1, D, device="cuda")
+    p = preds.cpu().numpy()
+    lists = [[] for _ in range(F)]
+    for i in range(F):                                               # the reference's accumulation, inference.py:56-67
+        for o in range(-hw, hw + 1):
+            if 0 <= i + o < F:
+                lists[i + o].append(p[i, o + hw])
+    want = np.array([np.mean(np.array(l), axis=0) for l in lists])
+    assert np.abs(window_mean(preds, hw).cpu().numpy() - want).max() < 1e-6
+    assert torch.equal(window_mean(preds, 0), preds[:, 0])

@@ -95,3 +95,14 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(dll, name), name
     assert _lib.lib().tik_version() >= 100
     assert ctypes.sizeof(_lib.TikSlab) == 24 and ctypes.sizeof(_lib.TikBlock) == 80
+
+
+def test_keypoint_preprocessing_matches_reference(golden):
+    """moveai -> COCO-17 remap + axis swap (reference inference.py:121-133) against the reference-generated fixture."""
+    from temporal_inverse_kinematics_b200 import keypoints_util as ku
+    g = golden("dance.npz")
+    names = [str(s) for s in g["joint_3d_names"]]
+    assert np.array_equal(ku.moveai_to_coco(g["joints_3d"], names), g["coco_seq"])
+    smplx_names = ["pelvis", "left_hip", "right_hip"] + ku.COCO17
+    assert ku.generate_smplx_to_coco_mappings(smplx_names) == list(range(3, 20))
+    assert len(ku.COCO_BONES) == 15
