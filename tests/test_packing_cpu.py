@@ -103,6 +103,6 @@ def test_keypoint_preprocessing_matches_reference(golden):
     g = golden("dance.npz")
     names = [str(s) for s in g["joint_3d_names"]]
     assert np.array_equal(ku.moveai_to_coco(g["joints_3d"], names), g["coco_seq"])
-    smplx_names = ["pelvis", "left_hip", "right_hip"] + ku.COCO17
+    smplx_names = ["pelvis", "spine1", "spine2"] + ku.COCO17
     assert ku.generate_smplx_to_coco_mappings(smplx_names) == list(range(3, 20))
     assert len(ku.COCO_BONES) == 15
