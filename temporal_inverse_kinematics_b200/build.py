@@ -38,6 +38,8 @@ def build(force=False, verbose=False):
              "--expt-relaxed-constexpr"]
     if verbose:
         flags += ["-Xptxas", "-v"]
+    if os.environ.get("TIK_PROBE") == "1":          # in-kernel clock64 probes for tools/umma_probe.py
+        flags += ["-DTIK_PROBE"]
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for s in SOURCES:

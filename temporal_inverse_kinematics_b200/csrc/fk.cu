@@ -242,6 +242,7 @@ static int launch_body22(const float* pose, const float* transl, float* joints, 
   TIK_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
     TIK_CUDA(cudaFuncSetAttribute(fk_body22_kernel<kRotIn, kLocalOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TIK_CUDA(cudaFuncSetAttribute(fk_body22_kernel<kRotIn, kLocalOut>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set[dev & 63] = true;
   }
   int64_t blocks = ceil_div(F, kB22Threads);

@@ -361,6 +361,7 @@ static int gf_launch_variant(const GcnFusedPrepared* g, unsigned grid, cudaStrea
   TIK_CUDA(cudaGetDevice(&dev));
   if (!attr_done[dev & 63]) {
     TIK_CUDA(cudaFuncSetAttribute(gcn_fused_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGfSmemBudget + 2048));
+    TIK_CUDA(cudaFuncSetAttribute(gcn_fused_kernel<CIN, COUT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_done[dev & 63] = true;
   }
   gcn_fused_kernel<CIN, COUT><<<grid, kGfThreads, g->smem_bytes, s>>>(g->p);

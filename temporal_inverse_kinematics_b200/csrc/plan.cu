@@ -78,7 +78,7 @@ static int check_net(const TikNet* net, int dtype) {
   TIK_CHECK_ARG(dtype == TIK_F32 || dtype == TIK_BF16, "bad dtype %d", dtype);
   TIK_CHECK_ARG(net->n_blocks >= 1 && net->n_blocks <= TIK_MAX_BLOCKS, "n_blocks=%d", net->n_blocks);
   TIK_CHECK_ARG(net->V >= 1 && net->V <= 32 && net->K >= 1 && net->K <= 5, "V=%d K=%d unsupported", net->V, net->K);
-  TIK_CHECK_ARG(net->c_in >= 1 && net->c_in * net->K <= 40, "stem needs K*c_in <= 40 (got c_in=%d K=%d)", net->c_in, net->K);
+  TIK_CHECK_ARG(net->c_in >= 1 && net->c_in <= 8 && net->c_in * net->K <= 16, "stem needs c_in <= 8 and K*c_in <= 16 (got c_in=%d K=%d)", net->c_in, net->K);
   TIK_CHECK_ARG(net->blocks[0].c_in == net->c_in, "block 0 c_in mismatch");
   const int cmul = dtype == TIK_BF16 ? 64 : 8;
   for (int i = 0; i < net->n_blocks; ++i) {

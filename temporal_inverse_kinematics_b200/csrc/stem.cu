@@ -9,12 +9,14 @@
 // Input is the reference's (N,T,V,Cin) fp32 layout; outputs are node-major (N,V,T,Cout) so that the temporal
 // convolution's TMA boxes are dense.  HBM-bound: Cin*4*V B in, 2 * V*Cout*sizeof(T) B out per frame.
 // One CTA handles kStemFrames frames of one clip; each thread produces 8 consecutive channels (one 16 B store).
+#include <algorithm>
+
 #include "tik_common.cuh"
 
 namespace tik {
 
 constexpr int kStemFrames = 32;
-constexpr int kStemThreads = 256;
+constexpr int kStemThreads = 288;   // >= 2 x 17 nodes x 8 channel groups (Cout = 64)
 constexpr int kStemMaxV = 32;
 constexpr int kStemMaxKC = 40;  // K * Cin
 
@@ -31,105 +33,117 @@ template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16*
   *reinterpret_cast<uint4*>(p) = t;
 }
 
-template <class OutT>
+// Thread t owns one (node w, 8-channel group g) pair for the whole CTA: its 8 x K*Cin weights, 8 biases and
+// 8 x Cin residual weights live in registers, and it walks the CTA's frames writing one 16-byte vector per frame
+// and tensor (consecutive frames of one node are consecutive 2*Cout-byte rows of the node-major output).
+constexpr int kStemMaxKCReg = 16;  // register-resident weights: K*Cin <= 16 (IK model: 1 x 3 -> KCR = 4; spatial K=5 -> 15)
+
+template <class OutT, int KCR, int CINR>
 __global__ void __launch_bounds__(kStemThreads)
 stem_gcn_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, const float* __restrict__ in_shift,
                 const float* __restrict__ agg, const float* __restrict__ w, const float* __restrict__ bias,
                 OutT* __restrict__ out, const float* __restrict__ res_w, OutT* __restrict__ res_out, int res_stride,
-                int T, int V, int Cin, int K, int Cout, int relu, const TikWindowing win, long long win_n0) {
+                int T, int V, int Cin, int K, int Cout, int relu, const TikWindowing win, long long win_n0, long long n_clips) {
   extern __shared__ __align__(16) float smem[];
   const int KC = K * Cin, VC = V * Cin;
   float* s_raw = smem;                                // [frames][V*Cin] raw input
-  float* s_a = s_raw + kStemFrames * VC;              // [frames][V][K*Cin] aggregated data_bn(x)
-  float* s_wT = s_a + kStemFrames * V * KC;           // [K*Cin][Cout]
-  float* s_b = s_wT + KC * Cout;                      // [V][Cout]
-  float* s_agg = s_b + V * Cout;                      // [K][V][V]
-  float* s_rw = s_agg + K * V * V;                    // [V][Cin][Cout] (only if res_w)
+  float* s_bn = s_raw + kStemFrames * VC;             // [frames][V*Cin] after data_bn
+  float* s_a = s_bn + kStemFrames * VC;               // [frames][V][K*Cin] aggregated data_bn(x)
+  float* s_agg = s_a + kStemFrames * V * KC;          // [K][V][V]
   const int tiles_t = (T + kStemFrames - 1) / kStemFrames;
-  const int64_t n = blockIdx.x / tiles_t;
-  const int t0 = (blockIdx.x % tiles_t) * kStemFrames;
-  const int nf = min(kStemFrames, T - t0);
-
-  for (int i = threadIdx.x; i < Cout * KC; i += kStemThreads) {
-    const int c = i / KC, kc = i - c * KC;
-    s_wT[kc * Cout + c] = __ldg(w + i);
-  }
-  for (int i = threadIdx.x; i < V * Cout; i += kStemThreads) s_b[i] = __ldg(bias + i);
-  for (int i = threadIdx.x; i < K * V * V; i += kStemThreads) s_agg[i] = __ldg(agg + i);
-  if (res_w != nullptr) {
-    for (int i = threadIdx.x; i < V * Cout * Cin; i += kStemThreads) {   // (V,Cout,Cin) -> [V][Cin][Cout]
-      const int ci = i % Cin, c = (i / Cin) % Cout, v = i / (Cin * Cout);
-      s_rw[(v * Cin + ci) * Cout + c] = __ldg(res_w + i);
-    }
-  }
-  float* s_bn = s_rw + (res_w != nullptr ? V * Cin * Cout : 0);   // [frames][V*Cin] after data_bn
-  const float* gx = x + (n * T + t0) * (int64_t)VC;   // (N,T,V,C): frames contiguous
-  for (int i = threadIdx.x; i < nf * VC; i += kStemThreads) {
-    const int vc = i % VC;
-    float raw;
-    if (win.frames > 0) {
-      // window mode: clip n is a window of one resident sequence (F,V,C); frame = clamp(n*stride + t + offset),
-      // i.e. sample_window's edge padding (data_amass.py:18-42), root-centred on 0.5*(kp[a]+kp[b]) (:232-235)
-      long long fi = (win_n0 + (long long)n) * win.stride + (t0 + i / VC) + win.offset;
-      fi = fi < 0 ? 0 : (fi >= win.frames ? win.frames - 1 : fi);
-      const float* fr = x + fi * VC;
-      raw = __ldg(fr + vc);
-      if (win.root_a >= 0) {
-        const int c = vc % Cin;
-        raw -= 0.5f * (__ldg(fr + win.root_a * Cin + c) + __ldg(fr + win.root_b * Cin + c));
-      }
-    } else {
-      raw = __ldg(gx + i);
-    }
-    s_raw[i] = raw;
-    s_bn[i] = fmaf(raw, __ldg(in_scale + vc), __ldg(in_shift + vc));
-  }
-  __syncthreads();
-  // aggregated input: a[f][w][k*Cin+ci] = sum_v agg[k][v][w] * data_bn(x)[f][v][ci]
-  for (int i = threadIdx.x; i < nf * V * KC; i += kStemThreads) {
-    const int kc = i % KC, wv = (i / KC) % V, f = i / (KC * V);
-    const int k = kc / Cin, ci = kc - k * Cin;
-    float acc = 0.f;
-    for (int v = 0; v < V; ++v) acc = fmaf(s_agg[(k * V + v) * V + wv], s_bn[f * VC + v * Cin + ci], acc);
-    s_a[i] = acc;
-  }
-  __syncthreads();
-  // outputs: item = (w, f, 8-channel group); consecutive threads -> consecutive channel groups of one (w,f)
   const int cg = Cout / 8;
-  const int total = V * nf * cg;
-  for (int i = threadIdx.x; i < total; i += kStemThreads) {
-    const int g = i % cg;
-    const int pair = i / cg;                        // (w, f) with f fastest -> adjacent threads write adjacent rows
-    const int wv = pair / nf, f = pair - wv * nf;
-    const int c0 = g * 8;
-    float acc[8];
+  const int pairs = V * cg;                           // (node, channel group) pairs
+  const int slots = kStemThreads / pairs > 0 ? kStemThreads / pairs : 1;
+  const int pid = threadIdx.x % pairs, slot = threadIdx.x / pairs;
+  const int wv = pid / cg, c0 = (pid - wv * cg) * 8;
+  const bool worker = slot < slots && threadIdx.x < slots * pairs;
+
+  // per-thread constants (registers)
+  float wreg[KCR][8], breg[8], rreg[CINR][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = s_b[wv * Cout + c0 + j];
-    const float* a = s_a + (f * V + wv) * KC;
-    for (int kc = 0; kc < KC; ++kc) {
-      const float av = a[kc];
-      const float4 w0 = *reinterpret_cast<const float4*>(s_wT + kc * Cout + c0);
-      const float4 w1 = *reinterpret_cast<const float4*>(s_wT + kc * Cout + c0 + 4);
-      acc[0] = fmaf(w0.x, av, acc[0]); acc[1] = fmaf(w0.y, av, acc[1]); acc[2] = fmaf(w0.z, av, acc[2]); acc[3] = fmaf(w0.w, av, acc[3]);
-      acc[4] = fmaf(w1.x, av, acc[4]); acc[5] = fmaf(w1.y, av, acc[5]); acc[6] = fmaf(w1.z, av, acc[6]); acc[7] = fmaf(w1.w, av, acc[7]);
+  for (int kc = 0; kc < KCR; ++kc)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      wreg[kc][j] = (worker && kc < KC) ? __ldg(w + (size_t)(c0 + j) * KC + kc) : 0.f;
+      if (kc < CINR) rreg[kc][j] = (worker && res_w != nullptr && kc < Cin) ? __ldg(res_w + ((size_t)wv * Cout + c0 + j) * Cin + kc) : 0.f;
     }
-    if (relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
-    }
-    store8<OutT>(out + ((n * V + wv) * (int64_t)T + t0 + f) * Cout + c0, acc);
-    if (res_w != nullptr && ((t0 + f) % res_stride) == 0) {
-      const int T_res = (T - 1) / res_stride + 1;
-      float r[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = 0.f;
-      for (int ci = 0; ci < Cin; ++ci) {
-        const float xv = s_raw[f * VC + wv * Cin + ci];
-        const float* rw = s_rw + (wv * Cin + ci) * Cout + c0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = fmaf(rw[j], xv, r[j]);
+  for (int j = 0; j < 8; ++j) breg[j] = worker ? __ldg(bias + wv * Cout + c0 + j) : 0.f;
+  for (int i = threadIdx.x; i < K * V * V; i += kStemThreads) s_agg[i] = __ldg(agg + i);
+  const int T_res = (T - 1) / res_stride + 1;
+
+  for (int64_t tile = blockIdx.x; tile < (int64_t)n_clips * tiles_t; tile += gridDim.x) {
+    const int64_t n = tile / tiles_t;
+    const int t0 = (int)(tile - n * tiles_t) * kStemFrames;
+    const int nf = min(kStemFrames, T - t0);
+    __syncthreads();                                  // previous tile's readers are done with the staging arrays
+    const float* gx = x + (n * T + t0) * (int64_t)VC; // (N,T,V,C): frames contiguous
+    for (int i = threadIdx.x; i < nf * VC; i += kStemThreads) {
+      const int vc = i % VC;
+      float raw;
+      if (win.frames > 0) {
+        // window mode: clip n is a window of one resident sequence (F,V,C); frame = clamp(n*stride + t + offset),
+        // i.e. sample_window's edge padding (data_amass.py:18-42), root-centred on 0.5*(kp[a]+kp[b]) (:232-235)
+        long long fi = (win_n0 + (long long)n) * win.stride + (t0 + i / VC) + win.offset;
+        fi = fi < 0 ? 0 : (fi >= win.frames ? win.frames - 1 : fi);
+        const float* fr = x + fi * VC;
+        raw = __ldg(fr + vc);
+        if (win.root_a >= 0) {
+          const int c = vc % Cin;
+          raw -= 0.5f * (__ldg(fr + win.root_a * Cin + c) + __ldg(fr + win.root_b * Cin + c));
+        }
+      } else {
+        raw = __ldg(gx + i);
       }
-      store8<OutT>(res_out + ((n * V + wv) * (int64_t)T_res + (t0 + f) / res_stride) * Cout + c0, r);
+      s_raw[i] = raw;
+      s_bn[i] = fmaf(raw, __ldg(in_scale + vc), __ldg(in_shift + vc));
+    }
+    __syncthreads();
+    // aggregated input: a[f][w][k*Cin+ci] = sum_v agg[k][v][w] * data_bn(x)[f][v][ci]
+    for (int i = threadIdx.x; i < nf * V * KC; i += kStemThreads) {
+      const int kc = i % KC, w2 = (i / KC) % V, f = i / (KC * V);
+      const int k = kc / Cin, ci = kc - k * Cin;
+      float acc = 0.f;
+      for (int v = 0; v < V; ++v) acc = fmaf(s_agg[(k * V + v) * V + w2], s_bn[f * VC + v * Cin + ci], acc);
+      s_a[i] = acc;
+    }
+    __syncthreads();
+    if (worker) {
+      OutT* orow = out + ((n * V + wv) * (int64_t)T + t0) * Cout + c0;
+      OutT* rrow = res_out != nullptr ? res_out + ((n * V + wv) * (int64_t)T_res) * Cout + c0 : nullptr;
+      for (int f = slot; f < nf; f += slots) {
+        const float* a = s_a + (f * V + wv) * KC;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = breg[j];
+#pragma unroll
+        for (int kc = 0; kc < KCR; ++kc) {
+          if (kc < KC) {
+            const float av = a[kc];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(wreg[kc][j], av, acc[j]);
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+        }
+        store8<OutT>(orow + (int64_t)f * Cout, acc);
+        if (rrow != nullptr && ((t0 + f) % res_stride) == 0) {
+          float r[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = 0.f;
+#pragma unroll
+          for (int ci = 0; ci < CINR; ++ci) {
+            if (ci < Cin) {
+              const float xv = s_raw[f * VC + wv * Cin + ci];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) r[j] = fmaf(rreg[ci][j], xv, r[j]);
+            }
+          }
+          store8<OutT>(rrow + (int64_t)((t0 + f) / res_stride) * Cout, r);
+        }
+      }
     }
   }
 }
@@ -139,21 +153,28 @@ static int launch_stem(const float* x, const float* sc, const float* sh, const f
                        const float* bias, void* out, const float* res_w, void* res_out, int res_stride, int64_t N,
                        int Tn, int V, int Cin, int K, int Cout, int relu, const TikWindowing& win, int64_t win_n0, cudaStream_t s) {
   const size_t KC = (size_t)K * Cin;
-  size_t smem = sizeof(float) * (2 * (size_t)kStemFrames * V * Cin + (size_t)kStemFrames * V * KC + KC * Cout +
-                                 (size_t)V * Cout + (size_t)K * V * V + (res_w ? (size_t)V * Cin * Cout : 0));
+  size_t smem = sizeof(float) * (2 * (size_t)kStemFrames * V * Cin + (size_t)kStemFrames * V * KC + (size_t)K * V * V);
+  TIK_CHECK_ARG(KC <= (size_t)kStemMaxKCReg, "stem: K*Cin=%zu > %d is not instantiated", KC, kStemMaxKCReg);
+  TIK_CHECK_ARG(V * (Cout / 8) <= kStemThreads, "stem: V*Cout/8 = %d exceeds the CTA size", V * (Cout / 8));
   TIK_CHECK_ARG(smem <= 200 * 1024, "stem shared memory %zu too large", smem);
   static bool attr_set[64] = {};
   int dev = 0;
   TIK_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {   // per device (and per template instantiation: the static is per T)
-    TIK_CUDA(cudaFuncSetAttribute(stem_gcn_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TIK_CUDA(cudaFuncSetAttribute(stem_gcn_kernel<T, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TIK_CUDA(cudaFuncSetAttribute(stem_gcn_kernel<T, 16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set[dev & 63] = true;
   }
-  int64_t blocks = N * ceil_div(Tn, kStemFrames);
-  TIK_CHECK_ARG(blocks < (1ll << 31), "grid too large");
-  stem_gcn_kernel<T><<<(unsigned)blocks, kStemThreads, smem, s>>>(x, sc, sh, agg, w, bias, reinterpret_cast<T*>(out), res_w,
-                                                                   reinterpret_cast<T*>(res_out), res_stride, Tn, V, Cin, K,
-                                                                   Cout, relu, win, (long long)win_n0);
+  int64_t tiles = N * ceil_div(Tn, kStemFrames);
+  const unsigned gx = (unsigned)std::min<int64_t>(tiles, 148 * 4);       // persistent CTAs: weights loaded once
+  if (KC <= 4 && Cin <= 4)
+    stem_gcn_kernel<T, 4, 4><<<gx, kStemThreads, smem, s>>>(x, sc, sh, agg, w, bias, reinterpret_cast<T*>(out), res_w,
+                                                          reinterpret_cast<T*>(res_out), res_stride, Tn, V, Cin, K, Cout, relu, win,
+                                                          (long long)win_n0, (long long)N);
+  else
+    stem_gcn_kernel<T, 16, 8><<<gx, kStemThreads, smem, s>>>(x, sc, sh, agg, w, bias, reinterpret_cast<T*>(out), res_w,
+                                                          reinterpret_cast<T*>(res_out), res_stride, Tn, V, Cin, K, Cout, relu, win,
+                                                          (long long)win_n0, (long long)N);
   TIK_LAUNCH_CHECK();
   return TIK_OK;
 }

@@ -249,6 +249,13 @@ static int launch_agg_v(const void* x, const float* agg, void* out, int64_t N, i
   int64_t total = N * Tn * (C / VN);
   int64_t blocks = ceil_div(total, kAggThreads);
   if (blocks > 148 * 32) blocks = 148 * 32;
+  static bool carve[64] = {};
+  int dev = 0;
+  TIK_CUDA(cudaGetDevice(&dev));
+  if (!carve[dev & 63]) {   // same carveout as the tensor-core kernels (no L1/shared reconfiguration between launches)
+    TIK_CUDA(cudaFuncSetAttribute(aggregate_kernel<T, V>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    carve[dev & 63] = true;
+  }
   aggregate_kernel<T, V><<<(unsigned)blocks, kAggThreads, 0, s>>>(reinterpret_cast<const T*>(x), agg,
                                                                    reinterpret_cast<T*>(out), N, Tn, C, K);
   TIK_LAUNCH_CHECK();

@@ -77,7 +77,14 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   return v;
 }
 
+// clock64 timeline probes (tools/umma_probe.py): compiled in only with -DTIK_PROBE (TIK_PROBE=1 python -m ...build)
+#ifdef TIK_PROBE
 #define TIK_T(i) do { if (p.dbg_times != nullptr && blockIdx.x == 0) p.dbg_times[i] = clock64(); } while (0)
+#define TIK_PROBE_ONLY(x) (x)
+#else
+#define TIK_T(i) do { } while (0)
+#define TIK_PROBE_ONLY(x) false
+#endif
 
 template <int BN, int ACT>
 __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __grid_constant__ UmmaParams p) {
@@ -146,7 +153,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
         const int ts = t0 * p.t_mul[s] + p.t_off[s];
         const int nc = p.chunks[s];
         for (int c = 0; c < nc; ++c, ++kw) {
-          const bool p3 = leader && kw == 0 && tile == (int)blockIdx.x + 3 * (int)gridDim.x;
+          const bool p3 = TIK_PROBE_ONLY(leader && kw == 0 && tile == (int)blockIdx.x + 3 * (int)gridDim.x);
           if (p3) TIK_T(25);
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (p3) TIK_T(26);
@@ -183,7 +190,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
     int acc = 0; uint32_t acc_phase = 0;
     const int total_chunks = p.total_chunks;
     for (int tile = blockIdx.x; tile < (int)num_tiles; tile += gridDim.x) {
-      const bool m3 = leader && tile == (int)blockIdx.x + 3 * (int)gridDim.x;
+      const bool m3 = TIK_PROBE_ONLY(leader && tile == (int)blockIdx.x + 3 * (int)gridDim.x);
       if (m3) TIK_T(16);
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);        // epilogue has drained this accumulator
       tc_fence_after();
@@ -205,6 +212,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
 #pragma unroll
             for (int k = 0; k < kChunkK / 16; ++k)
               umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+            if (TIK_PROBE_ONLY((p.dbg_flags & 96) != 0)) {   // issue-cost experiment: 12 extra MMAs, same accumulator (32) or alternating (64)
+              const uint32_t other = (p.dbg_flags & 64) ? tmem_base + (uint32_t)((acc ^ 1) * BN) : tmem_d;
+#pragma unroll
+              for (int k = 0; k < 12; ++k)
+                umma_bf16((k & 1) ? other : tmem_d, da + (uint64_t)(2 * (k & 3)), db + (uint64_t)(2 * (k & 3)), idesc, 1u);
+            }
           }
           if (m3 && kc < 2) TIK_T(19 + 3 * kc);
           umma_commit(&empty_bar[stage]);                  // frees this ring slot once the MMAs have read it
@@ -280,7 +293,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
       else out_off = row * p.c_out_valid + n0 + cb;
       uint8_t* stage_row = s_stage + (size_t)sbuf * (BN / 64) * kABytes + (size_t)r * 128;
 
-      const bool t3 = (tile == (int)blockIdx.x + 3 * (int)gridDim.x) && threadIdx.x == 64;   // 4th tile of CTA 0: steady state
+      const bool t3 = TIK_PROBE_ONLY((tile == (int)blockIdx.x + 3 * (int)gridDim.x) && threadIdx.x == 64);   // 4th tile of CTA 0
       if (t3) TIK_T(12);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -432,6 +445,7 @@ static int launch_variant(const UmmaParams& p, int smem_bytes, unsigned grid, cu
   TIK_CUDA(cudaGetDevice(&dev));
   if (attr_done[dev & 63] < smem_bytes) {   // the attribute is per device
     TIK_CUDA(cudaFuncSetAttribute(rowgemm_umma_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048));
+    TIK_CUDA(cudaFuncSetAttribute(rowgemm_umma_kernel<BN, ACT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_done[dev & 63] = kSmemBudget + 2048;
   }
   rowgemm_umma_kernel<BN, ACT><<<grid, kUmmaThreads, smem_bytes, s>>>(p);

@@ -54,7 +54,7 @@ def case(name, n, t_in, t_out, cin_slabs, c_out, stride, residual):
         us = bench(lambda: ops.rowgemm(slabs, w, b, nv, V, t_out, act="relu", residual=res))
         out.append(f"flags={flags}: {us:7.1f}us")
     lib.tik_debug_set_umma_shift(0, 0)
-    for fl in (0, 16):
+    for fl in (0, 32, 64):
         tb = torch.zeros(32, dtype=torch.int64, device="cuda")
         lib.tik_debug_set_umma_times(_lib.ptr(tb))
         lib.tik_debug_set_umma_shift(0, fl << 8)
