@@ -135,40 +135,59 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc_bf16(128, CIN) | (1u << 16);   // B operand MN-major
-      constexpr uint32_t idesc2 = make_idesc_bf16(128, COUT);
-      mbar_wait(w_full, 0);
-      int b = 0; uint32_t phase = 0, tphase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t xb = smem_u32(s_x + (size_t)b * KC1 * kGfTile);
-        mbar_wait(&x_full[b], phase);
-        tc_fence_after();
-        // ---- MMA 1: D1 = Abd . X   (K = 128 tile rows, 16 per instruction)
+    // Warp-uniform loop, lane 0 issues.  Software-pipelined: the aggregation MMA of tile i+1 is issued right after
+    // the channel MMA of tile i, so it runs on the tensor pipe while the epilogue warps do tile i's final pass.
+    constexpr uint32_t idesc1 = make_idesc_bf16(128, CIN) | (1u << 16);   // B operand MN-major
+    constexpr uint32_t idesc2 = make_idesc_bf16(128, COUT);
+    const bool leader = lane == 0;
+    mbar_wait(w_full, 0);
+    const uint32_t abd_u32 = smem_u32(s_abd), w_u32 = smem_u32(s_w), x_u32 = smem_u32(s_x);
+    auto issue_mma1 = [&](uint32_t xb) {
+      if (leader) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const uint64_t da = make_smem_desc_kmajor_sw128(smem_u32(s_abd) + (uint32_t)(k >> 2) * kGfTile + (uint32_t)(k & 3) * 32u);
+          const uint64_t da = make_smem_desc_kmajor_sw128(abd_u32 + (uint32_t)(k >> 2) * kGfTile + (uint32_t)(k & 3) * 32u);
           const uint64_t db = make_smem_desc_mnmajor_sw128(xb + (uint32_t)k * 2048u, (uint32_t)kGfTile);
           umma_bf16(tmem_d1, da, db, idesc1, k != 0 ? 1u : 0u);
         }
         umma_commit(d1_full);
-        // ---- MMA 2: D2 = Xagg . Wg^T once the epilogue warps have rewritten the tile as bf16 Xagg
-        mbar_wait(xagg_full, tphase);
-        mbar_wait(d2_empty, tphase ^ 1);                     // previous tile's D2 has been read
-        tc_fence_after();
+      }
+      __syncwarp();
+    };
+    int b = 0; uint32_t phase = 0, tphase = 0;
+    int tile = blockIdx.x;
+    if (tile < n_tiles) {
+      mbar_wait(&x_full[0], 0);
+      tc_fence_after();
+      issue_mma1(x_u32);
+    }
+    for (; tile < n_tiles; tile += gridDim.x) {
+      const uint32_t xb = x_u32 + (uint32_t)b * (uint32_t)(KC1 * kGfTile);
+      // ---- MMA 2: D2 = Xagg . Wg^T once the epilogue warps have rewritten the tile as bf16 Xagg
+      mbar_wait(xagg_full, tphase);
+      mbar_wait(d2_empty, tphase ^ 1);                     // previous tile's D2 has been read
+      tc_fence_after();
+      if (leader) {
 #pragma unroll
         for (int kc = 0; kc < KC1; ++kc) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = make_smem_desc_kmajor_sw128(xb + (uint32_t)kc * kGfTile + (uint32_t)k * 32u);
-            const uint64_t db = make_smem_desc_kmajor_sw128(smem_u32(s_w) + (uint32_t)kc * (COUT * 128) + (uint32_t)k * 32u);
+            const uint64_t db = make_smem_desc_kmajor_sw128(w_u32 + (uint32_t)kc * (COUT * 128) + (uint32_t)k * 32u);
             umma_bf16(tmem_d2, da, db, idesc2, (kc | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(d2_full);
         umma_commit(&x_empty[b]);                            // the tile buffer may be refilled once MMA 2 has read it
-        tphase ^= 1;
-        if (++b == p.xbufs) { b = 0; phase ^= 1; }
+      }
+      __syncwarp();
+      tphase ^= 1;
+      if (++b == p.xbufs) { b = 0; phase ^= 1; }
+      // ---- MMA 1 of the NEXT tile: D1 is free (tile i's mid pass finished before xagg_full), its X tile is in the ring
+      if (tile + (int)gridDim.x < n_tiles) {
+        mbar_wait(&x_full[b], phase);
+        tc_fence_after();
+        issue_mma1(x_u32 + (uint32_t)b * (uint32_t)(KC1 * kGfTile));
       }
     }
   } else {

@@ -39,7 +39,7 @@ template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16*
 constexpr int kStemMaxKCReg = 16;  // register-resident weights: K*Cin <= 16 (IK model: 1 x 3 -> KCR = 4; spatial K=5 -> 15)
 
 template <class OutT, int KCR, int CINR>
-__global__ void __launch_bounds__(kStemThreads)
+__global__ void __launch_bounds__(kStemThreads, (KCR <= 4 ? 3 : 1))
 stem_gcn_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, const float* __restrict__ in_shift,
                 const float* __restrict__ agg, const float* __restrict__ w, const float* __restrict__ bias,
                 OutT* __restrict__ out, const float* __restrict__ res_w, OutT* __restrict__ res_out, int res_stride,
@@ -166,7 +166,7 @@ static int launch_stem(const float* x, const float* sc, const float* sh, const f
     attr_set[dev & 63] = true;
   }
   int64_t tiles = N * ceil_div(Tn, kStemFrames);
-  const unsigned gx = (unsigned)std::min<int64_t>(tiles, 148 * 4);       // persistent CTAs: weights loaded once
+  const unsigned gx = (unsigned)std::min<int64_t>(tiles, 148 * 3);       // persistent CTAs: weights loaded once
   if (KC <= 4 && Cin <= 4)
     stem_gcn_kernel<T, 4, 4><<<gx, kStemThreads, smem, s>>>(x, sc, sh, agg, w, bias, reinterpret_cast<T*>(out), res_w,
                                                           reinterpret_cast<T*>(res_out), res_stride, Tn, V, Cin, K, Cout, relu, win,
