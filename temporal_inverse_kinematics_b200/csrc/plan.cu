@@ -408,6 +408,13 @@ int tik_stgcn_plan_profile(TikPlan* P, const float* x, int64_t N, float* poses, 
     const int kind = st.kind == Step::FUSED_GCN ? (int)Step::GEMM : (int)st.kind;   // fused gcn counts with the tensor-core family
     ms_by_kind[kind] += ms;
     launches_by_kind[kind] += 1;
+    if (getenv("TIK_PLAN_TRACE")) {
+      static const char* names[] = {"stem", "aggregate", "gemm", "fused_gcn"};
+      int ktot = 0;
+      for (int q = 0; q < st.g.n_slabs && st.kind == Step::GEMM; ++q) ktot += st.g.slabs[q].c;
+      fprintf(stderr, "tik trace: step %2zu %-9s clips=%lld K=%d c_out=%d t_out=%d  %.1f us\n", i, names[st.kind], (long long)n, ktot,
+              st.kind == Step::GEMM ? st.g.c_out : st.c, st.kind == Step::GEMM ? st.g.t_out : st.t, ms * 1e3);
+    }
     if (st.kind == Step::FUSED_GCN) *flops_gemm += st.fused_flops_per_clip * (double)n;
     if (st.kind == Step::GEMM) {
       double ktot = -st.k_identity;

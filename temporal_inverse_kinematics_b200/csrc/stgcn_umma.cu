@@ -24,6 +24,7 @@
 // Serves: BN-folded 1x1 channel GEMM of ConvTemporalGraphical (gconv_origin.py:59) after the adjacency
 // aggregation, the temporal convolution + residual + BN + ReLU of StGcnBlock (st_gcn_aaai18.py:177-214)
 // and both Linear layers of the head (pose_trainer.py:89-92).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -58,6 +59,7 @@ struct UmmaParams {
   int32_t n_tiles_n;               // c_out / BN
   int64_t tiles_m;                 // ceil(nv/vv) * tiles_t
   int32_t stages, w_resident;
+  int32_t group;                   // K chunks per ring stage: one full/empty barrier hand-off per `group` chunks
   int32_t off_ring, off_bias, off_bar;   // byte offsets in the 1024-aligned dynamic shared memory
   int32_t bias_rows;
   int64_t nv;
@@ -107,7 +109,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stages = p.stages;
-  const int stage_bytes = kABytes + (p.w_resident ? 0 : kBBytes);
+  const int chunk_bytes = kABytes + (p.w_resident ? 0 : kBBytes);
+  const int stage_bytes = p.group * chunk_bytes;
   const int64_t num_tiles = p.tiles_m * p.n_tiles_n;
 
   if (warp == 0 && lane == 0) {
@@ -141,6 +144,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
     }
     const uint32_t tx_bytes = (uint32_t)(p.a_box_bytes + (p.w_resident ? 0 : kBBytes));
     const bool skip_a = (p.dbg_flags & 8) != 0;
+    const int group = p.group, total_chunks = p.total_chunks;
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < (int)num_tiles; tile += gridDim.x) {
       const int tm = tile / p.n_tiles_n;
@@ -148,29 +152,33 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
       const int tile_nv = tm / p.tiles_t;
       const int t0 = (tm - tile_nv * p.tiles_t) * p.tt;
       const int nv0 = tile_nv * p.vv;
-      int kw = 0;
+      int kw = 0, j = 0;                                   // j = position of this chunk inside its stage
       for (int s = 0; s < p.n_slabs; ++s) {
         const int ts = t0 * p.t_mul[s] + p.t_off[s];
         const int nc = p.chunks[s];
         for (int c = 0; c < nc; ++c, ++kw) {
           const bool p3 = TIK_PROBE_ONLY(leader && kw == 0 && tile == (int)blockIdx.x + 3 * (int)gridDim.x);
           if (p3) TIK_T(25);
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (p3) TIK_T(26);
-          uint8_t* sa = ring + (size_t)stage * stage_bytes;
-          if (leader) {
-            if (skip_a) {
-              if (p.w_resident) { mbar_arrive(&full_bar[stage]); }
-              else { mbar_expect_tx(&full_bar[stage], (uint32_t)kBBytes); tma_load_2d(sa + kABytes, &p.map_w, &full_bar[stage], kw * kChunkK, n0); }
-            } else {
-              mbar_expect_tx(&full_bar[stage], tx_bytes);
-              tma_load_3d(sa, &p.map_a[s], &full_bar[stage], c * kChunkK, ts, nv0);
-              if (!p.w_resident) tma_load_2d(sa + kABytes, &p.map_w, &full_bar[stage], kw * kChunkK, n0);
+          if (j == 0) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            const int in_stage = min(group, total_chunks - kw);
+            if (leader) {
+              if (skip_a && p.w_resident) mbar_arrive(&full_bar[stage]);
+              else mbar_expect_tx(&full_bar[stage], (skip_a ? (uint32_t)kBBytes : tx_bytes) * (uint32_t)in_stage);
             }
+          }
+          if (p3) TIK_T(26);
+          uint8_t* sa = ring + (size_t)stage * stage_bytes + (size_t)j * chunk_bytes;
+          if (leader) {
+            if (!skip_a) tma_load_3d(sa, &p.map_a[s], &full_bar[stage], c * kChunkK, ts, nv0);
+            if (!p.w_resident) tma_load_2d(sa + kABytes, &p.map_w, &full_bar[stage], kw * kChunkK, n0);
           }
           if (p3) TIK_T(27);
           __syncwarp();
-          if (++stage == stages) { stage = 0; phase ^= 1; }
+          if (++j == group || kw + 1 == total_chunks) {
+            j = 0;
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
         }
       }
       if (tile == blockIdx.x && leader) TIK_T(2);
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
     const uint32_t shift_bytes = (uint32_t)p.dbg_shift_rows * 128u;
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    const int total_chunks = p.total_chunks;
+    const int total_chunks = p.total_chunks, group = p.group;
     for (int tile = blockIdx.x; tile < (int)num_tiles; tile += gridDim.x) {
       const bool m3 = TIK_PROBE_ONLY(leader && tile == (int)blockIdx.x + 3 * (int)gridDim.x);
       if (m3) TIK_T(16);
@@ -196,22 +204,23 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
       tc_fence_after();
       if (m3) TIK_T(17);
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-      for (int kc = 0; kc < total_chunks; ++kc) {
+      for (int kc = 0; kc < total_chunks; kc += group) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (m3 && kc < 2) TIK_T(18 + 3 * kc);
+        if (m3 && kc < 2 * group) TIK_T(18 + 3 * (kc / group));
         if (tile == blockIdx.x && kc == 0 && leader) TIK_T(3);
-        const uint32_t sa = ring_u32 + (uint32_t)stage * (uint32_t)stage_bytes;
-        const uint32_t sb = p.w_resident ? wres_u32 + (uint32_t)kc * (uint32_t)kBBytes : sa + kABytes;
-        // descriptor = constant high part | (address >> 4); +2 per 16-element (32 B) K step inside the swizzled row
-        uint64_t da = desc_hi | (uint64_t)(((sa + shift_bytes) >> 4) & 0x3FFF);
-        if (p.dbg_base_offset_mode) da |= (uint64_t)(((sa + shift_bytes) >> 7) & 7u) << 49;
-        const uint64_t db = desc_hi | (uint64_t)((sb >> 4) & 0x3FFF);
-        if (leader) {
-          if (!skip_mma) {
+        const int in_stage = min(group, total_chunks - kc);
+        for (int j = 0; j < in_stage; ++j) {
+          const uint32_t sa = ring_u32 + (uint32_t)stage * (uint32_t)stage_bytes + (uint32_t)j * (uint32_t)chunk_bytes;
+          const uint32_t sb = p.w_resident ? wres_u32 + (uint32_t)(kc + j) * (uint32_t)kBBytes : sa + kABytes;
+          // descriptor = constant high part | (address >> 4); +2 per 16-element (32 B) K step inside the swizzled row
+          uint64_t da = desc_hi | (uint64_t)(((sa + shift_bytes) >> 4) & 0x3FFF);
+          if (p.dbg_base_offset_mode) da |= (uint64_t)(((sa + shift_bytes) >> 7) & 7u) << 49;
+          const uint64_t db = desc_hi | (uint64_t)((sb >> 4) & 0x3FFF);
+          if (leader && !skip_mma) {
 #pragma unroll
             for (int k = 0; k < kChunkK / 16; ++k)
-              umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+              umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | j | k) != 0 ? 1u : 0u);
             if (TIK_PROBE_ONLY((p.dbg_flags & 96) != 0)) {   // issue-cost experiment: 12 extra MMAs, same accumulator (32) or alternating (64)
               const uint32_t other = (p.dbg_flags & 64) ? tmem_base + (uint32_t)((acc ^ 1) * BN) : tmem_d;
 #pragma unroll
@@ -219,9 +228,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
                 umma_bf16((k & 1) ? other : tmem_d, da + (uint64_t)(2 * (k & 3)), db + (uint64_t)(2 * (k & 3)), idesc, 1u);
             }
           }
-          if (m3 && kc < 2) TIK_T(19 + 3 * kc);
+        }
+        if (leader) {
+          if (m3 && kc < 2 * group) TIK_T(19 + 3 * (kc / group));
           umma_commit(&empty_bar[stage]);                  // frees this ring slot once the MMAs have read it
-          if (m3 && kc < 2) TIK_T(20 + 3 * kc);
+          if (m3 && kc < 2 * group) TIK_T(20 + 3 * (kc / group));
         }
         __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -510,25 +521,44 @@ int umma_prepare(const TikRowGemm* d, int64_t nv_capacity, UmmaPrepared** out) {
   p.tma_store = (d->out_layout == TIK_OUT_NODE_MAJOR && d->out_dev != nullptr) ? 1 : 0;
   // smem policy: a deep A ring matters most (>= 4 stages), then resident weights, then a second staging tile
   const int one_stage_tile = p.tma_store ? (u->bn / 64) * kABytes : 0;
-  int w_res = 0, stages = 0, sbufs = 1;
-  auto ring_stages = [&](int wres, int sb) {
+  // Ring stages hold `group` K chunks each: the producer -> MMA -> producer barrier round trip (~650 cycles on the
+  // MMA thread) is paid once per stage, so small-N layers need several chunks per stage to stay HBM-bound.
+  int w_res = 0, stages = 0, sbufs = 1, group = 1;
+  auto ring_chunks = [&](int wres, int sb) {
     const int fixed_ = bias_bytes + bar_bytes + sb * one_stage_tile;
-    const int st = wres ? (kSmemBudget - fixed_ - w_bytes) / kABytes : (kSmemBudget - fixed_) / (kABytes + b_bytes);
-    return st > kMaxStages ? kMaxStages : st;
+    return wres ? (kSmemBudget - fixed_ - w_bytes) / kABytes : (kSmemBudget - fixed_) / (kABytes + b_bytes);
   };
+  // Pick (weights resident?, staging tiles, chunks per stage) by a cost model fitted to whole-batch B200 timings
+  // (tools/umma_probe.py grp): barrier hand-offs per tile cost ~400 cycles each, and the activation stream needs
+  // ~8 chunks (128 KB) in flight per SM to cover HBM latency.
+  const char* env_g = getenv("TIK_UMMA_GROUP");     // tuning hooks (tools/umma_probe.py)
+  const char* env_o = getenv("TIK_UMMA_OPT");
   const int options[4][2] = {{1, 2}, {1, 1}, {0, 2}, {0, 1}};
+  int best_score = INT32_MAX;
   for (int o = 0; o < 4; ++o) {
     const int wres = options[o][0], sb = options[o][1];
     if (wres && p.n_tiles_n != 1) continue;
-    const int st = ring_stages(wres, sb);
-    if (st >= (wres ? 4 : 3) || o == 3) { w_res = wres; sbufs = sb; stages = st; break; }
+    if (env_o && o != atoi(env_o)) continue;
+    const int fit = ring_chunks(wres, sb);
+    for (int g = 4; g >= 1; g >>= 1) {
+      if (env_g && g != atoi(env_g)) continue;
+      if (g > 1 && g > p.total_chunks) continue;
+      int st = fit / g;
+      if (st < 2) continue;
+      if (st > kMaxStages) st = kMaxStages;
+      const int inflight = std::min(st * g, 8);
+      const int handoffs = (p.total_chunks + g - 1) / g;
+      const int score = handoffs * 400 + 24000 / inflight + (wres ? 0 : 200) + (sb == 2 ? 0 : 100);
+      if (score < best_score) { best_score = score; w_res = wres; sbufs = sb; group = g; stages = st; }
+    }
   }
+  p.group = group;
   p.stage_bufs = sbufs;
   const int stage_out_bytes = sbufs * one_stage_tile;
   if (stages < 2) { delete u; set_error("bf16 path: bias table too large for shared memory"); return TIK_ERR_UNSUPPORTED; }
   p.w_resident = w_res; p.stages = stages;
   p.off_ring = w_res ? w_bytes : 0;
-  p.off_stage = p.off_ring + stages * (kABytes + (w_res ? 0 : b_bytes));
+  p.off_stage = p.off_ring + stages * group * (kABytes + (w_res ? 0 : b_bytes));
   p.off_bias = p.off_stage + stage_out_bytes;
   p.off_bar = p.off_bias + bias_bytes;
   if (p.tma_store) {

@@ -100,7 +100,52 @@ def big():
         print(f"big {name}: " + " | ".join(res), flush=True)
 
 
+def grp():
+    """Sweep the ring-stage grouping (TIK_UMMA_GROUP) and shared-memory option (TIK_UMMA_OPT) on whole-batch layer shapes."""
+    V, n = 17, 4096
+    g = torch.Generator(device="cuda").manual_seed(0)
+    shapes = [("b1 tcn 64->64 T64 K=256", 64, 64, 64, 64, 1, 64),
+              ("b2 tcn 128->128 s2 K=448", 64, 32, 128, 64, 2, 128),
+              ("b3 tcn 128->128 T32 K=512", 32, 32, 128, 128, 1, 128),
+              ("b6 tcn 256->256 s2 K=896", 16, 8, 256, 128, 2, 256)]
+    only = sys.argv[2:] and int(sys.argv[2])
+    for si, (name, t_in, t_out, ch, cres, stride, c_out) in enumerate(shapes):
+        if sys.argv[2:] and si != only:
+            continue
+        nv = n * V
+        h = torch.randn(nv, t_in, ch, device="cuda", generator=g).bfloat16()
+        r = torch.randn(nv, t_in, cres, device="cuda", generator=g).bfloat16()
+        slabs = [(h, stride, -1), (h, stride, 0), (h, stride, 1), (r, stride, 0)]
+        w = (torch.randn(c_out, 3 * ch + cres, device="cuda", generator=g) * 0.05).bfloat16()
+        b = torch.zeros(1, c_out, device="cuda")
+        gb = (h.numel() * 2 + r.numel() * 2 + nv * t_out * c_out * 2) / 1e9
+        ref = None
+        for opt in ("", "0", "1", "2", "3"):
+            for grp_ in ("1", "2", "4"):
+                os.environ["TIK_UMMA_GROUP"] = grp_
+                if opt:
+                    os.environ["TIK_UMMA_OPT"] = opt
+                else:
+                    os.environ.pop("TIK_UMMA_OPT", None)
+                try:
+                    out = ops.rowgemm(slabs, w, b, nv, V, t_out, act="relu")
+                    us = bench(lambda: ops.rowgemm(slabs, w, b, nv, V, t_out, act="relu"), reps=5)
+                except RuntimeError as e:
+                    print(f"{name} opt={opt or 'auto'} G={grp_}: {str(e)[:80]}", flush=True)
+                    continue
+                if ref is None:
+                    ref = out
+                same = bool((out == ref).all())
+                print(f"{name} opt={opt or 'auto'} G={grp_}: {us:7.1f} us  {gb / us * 1e3:5.2f} TB/s  same={same}", flush=True)
+        del h, r, w
+    os.environ.pop("TIK_UMMA_GROUP", None)
+    os.environ.pop("TIK_UMMA_OPT", None)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "grp":
+        grp()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "big":
         big()
         sys.exit(0)
