@@ -30,30 +30,6 @@ constexpr int kGfTile = 16384;                     // one 128-row x 64-channel s
 constexpr int kGfSmemBudget = 225 * 1024;
 constexpr int kGfMaxBufs = 8;                      // input tiles in flight: the kernel is HBM-latency bound otherwise
 
-// MN-major operand, 128-byte swizzle: 64 contiguous elements per row, 8-row groups 1024 B apart (SBO),
-// next 64-element block of the MN dimension `lbo` bytes away (LBO).
-__device__ __forceinline__ uint64_t make_smem_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-
 struct GcnFusedParams {
   CUtensorMap map_x, map_out, map_abd, map_w;
   int32_t n_clips, T, V, ttg, tiles_t;   // ttg = frames per tile (min(T, 7))
@@ -282,7 +258,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int gf_encode(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box) {
+int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* q = nullptr;
@@ -331,25 +307,25 @@ int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float
     uint64_t dims[4] = {(uint64_t)cin, (uint64_t)T, (uint64_t)V, (uint64_t)n_clips};
     uint64_t strides[3] = {(uint64_t)cin * 2, (uint64_t)cin * 2 * T, (uint64_t)cin * 2 * T * V};
     uint32_t box[4] = {64, (uint32_t)p.ttg, (uint32_t)V, 1};
-    rc = gf_encode(&p.map_x, x, 4, dims, strides, box);
+    rc = encode_bf16_map(&p.map_x, x, 4, dims, strides, box);
   }
   if (rc == TIK_OK) {
     uint64_t dims[4] = {(uint64_t)cout, (uint64_t)T, (uint64_t)V, (uint64_t)n_clips};
     uint64_t strides[3] = {(uint64_t)cout * 2, (uint64_t)cout * 2 * T, (uint64_t)cout * 2 * T * V};
     uint32_t box[4] = {64, (uint32_t)p.ttg, (uint32_t)V, 1};
-    rc = gf_encode(&p.map_out, out, 4, dims, strides, box);
+    rc = encode_bf16_map(&p.map_out, out, 4, dims, strides, box);
   }
   if (rc == TIK_OK) {
     uint64_t dims[2] = {128, 128};
     uint64_t strides[1] = {256};
     uint32_t box[2] = {64, 128};
-    rc = gf_encode(&p.map_abd, abd, 2, dims, strides, box);
+    rc = encode_bf16_map(&p.map_abd, abd, 2, dims, strides, box);
   }
   if (rc == TIK_OK) {
     uint64_t dims[2] = {(uint64_t)cin, (uint64_t)cout};
     uint64_t strides[1] = {(uint64_t)cin * 2};
     uint32_t box[2] = {64, (uint32_t)cout};
-    rc = gf_encode(&p.map_w, w, 2, dims, strides, box);
+    rc = encode_bf16_map(&p.map_w, w, 2, dims, strides, box);
   }
   if (rc != TIK_OK) { delete g; return rc; }
   const int kc1 = cin / 64, kc2 = cout / 64;

@@ -30,8 +30,9 @@ static int out_frames(int t, int stride) { return (t - 1) / stride + 1; }
 static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 struct Step {
-  enum Kind { STEM = 0, AGG = 1, GEMM = 2, FUSED_GCN = 3 } kind;
+  enum Kind { STEM = 0, AGG = 1, GEMM = 2, FUSED_GCN = 3, STEM_BLOCK = 4 } kind;
   GcnFusedPrepared* fused = nullptr;
+  StemBlockPrepared* stem_block = nullptr;
   double fused_flops_per_clip = 0;
   TikRowGemm g;               // GEMM
   UmmaPrepared* prep = nullptr;
@@ -63,6 +64,7 @@ struct TikPlan {
       {
         if (s.prep) tik::umma_free(s.prep);
         if (s.fused) tik::gcn_fused_free(s.fused);
+        if (s.stem_block) tik::stem_block_free(s.stem_block);
       }
   }
 };
@@ -70,7 +72,7 @@ struct TikPlan {
 namespace tik {
 
 struct WsLayout {
-  int64_t off_x0, off_x1, off_agg, off_h, off_r0, off_feat, off_z, off_abd, total_bytes;
+  int64_t off_x0, off_x1, off_agg, off_h, off_r0, off_feat, off_z, off_abd, off_w16, total_bytes;
 };
 
 static int check_net(const TikNet* net, int dtype) {
@@ -131,6 +133,7 @@ static void ws_layout(const TikNet* net, int dtype, int64_t n, int64_t n_max, in
   L->off_feat = off; off = align_up(off + feat * n_max * es, 1024);
   L->off_z = off; off = align_up(off + z * n_max * es, 1024);
   L->off_abd = off; off = align_up(off + (int64_t)net->n_blocks * 128 * 128 * 2, 1024);
+  L->off_w16 = off; off = align_up(off + stem_block_workspace_bytes(), 1024);
   L->total_bytes = off;
 }
 
@@ -149,6 +152,7 @@ static int run_step(TikPlan* P, Step& st, const float* xc, int64_t n, int64_t cl
     return tik_aggregate(P->dtype, st.src, st.blk->agg_dev, st.dst, P->n_chunk, st.t, V, st.c, net.K, s);
   }
   if (st.kind == Step::FUSED_GCN) return gcn_fused_launch(st.fused, n, s);
+  if (st.kind == Step::STEM_BLOCK) return stem_block_launch(st.stem_block, xc, n, win, win_n0, s);
   TikRowGemm g = st.g;
   if (g.v == 1) {             // head: rows = n * T'
     g.t_out = (int32_t)(n * P->T_out);
@@ -274,6 +278,17 @@ int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int64_t
     const int pad = (b.kt - 1) / 2;
     const int t_o = out_frames(t, b.stride);
     const bool last = i == net->n_blocks - 1;
+    if (i == 0 && net->n_blocks > 1 && stem_block_supported(net, dtype) && !getenv("TIK_NO_STEM_BLOCK")) {
+      // the whole first block in one kernel: neither H0 nor the residual branch touches HBM
+      Step s; s.kind = Step::STEM_BLOCK; s.blk = &b; s.t = t;
+      int rcs = stem_block_prepare(&P->net, ws + L.off_w16, xbuf[0], n_chunk, t, &s.stem_block);
+      if (rcs != TIK_OK) { delete P; return rcs; }
+      s.fused_flops_per_clip = 2.0 * V * t * (double)b.c_out * (K * b.c_in + b.kt * b.c_out + (b.res_kind == TIK_RES_STEM ? b.c_in : 0));
+      P->chunk_steps.push_back(s);
+      cur = 0;
+      t = t_o;
+      continue;
+    }
     if (i == 0) {
       Step s; s.kind = Step::STEM; s.dst = hbuf; s.t = t; s.blk = &b;
       s.dst2 = b.res_kind == TIK_RES_STEM ? r0buf : nullptr;
@@ -405,17 +420,17 @@ int tik_stgcn_plan_profile(TikPlan* P, const float* x, int64_t N, float* poses, 
     TIK_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
     Step& st = *trace[i].first;
     const int64_t n = trace[i].second;
-    const int kind = st.kind == Step::FUSED_GCN ? (int)Step::GEMM : (int)st.kind;   // fused gcn counts with the tensor-core family
+    const int kind = (st.kind == Step::FUSED_GCN || st.kind == Step::STEM_BLOCK) ? (int)Step::GEMM : (int)st.kind;   // tensor-core family
     ms_by_kind[kind] += ms;
     launches_by_kind[kind] += 1;
     if (getenv("TIK_PLAN_TRACE")) {
-      static const char* names[] = {"stem", "aggregate", "gemm", "fused_gcn"};
+      static const char* names[] = {"stem", "aggregate", "gemm", "fused_gcn", "stem_block"};
       int ktot = 0;
       for (int q = 0; q < st.g.n_slabs && st.kind == Step::GEMM; ++q) ktot += st.g.slabs[q].c;
       fprintf(stderr, "tik trace: step %2zu %-9s clips=%lld K=%d c_out=%d t_out=%d  %.1f us\n", i, names[st.kind], (long long)n, ktot,
               st.kind == Step::GEMM ? st.g.c_out : st.c, st.kind == Step::GEMM ? st.g.t_out : st.t, ms * 1e3);
     }
-    if (st.kind == Step::FUSED_GCN) *flops_gemm += st.fused_flops_per_clip * (double)n;
+    if (st.kind == Step::FUSED_GCN || st.kind == Step::STEM_BLOCK) *flops_gemm += st.fused_flops_per_clip * (double)n;
     if (st.kind == Step::GEMM) {
       double ktot = -st.k_identity;
       for (int q = 0; q < st.g.n_slabs; ++q) ktot += st.g.slabs[q].c;

@@ -1,5 +1,6 @@
 // Prepared (tensor maps encoded once) launches of the tcgen05 implicit GEMM.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -18,4 +19,13 @@ int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float
                       int cin, int cout, int relu, GcnFusedPrepared** outp);
 int gcn_fused_launch(GcnFusedPrepared* g, int64_t n_clips, cudaStream_t s);
 void gcn_fused_free(GcnFusedPrepared* g);
+// 128B-swizzled bf16 tiled tensor map (rank <= 5, unit element strides), defined in gcn_fused.cu
+int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box);
+struct StemBlockPrepared;
+// Whole first ST-GCN block (data_bn + graph conv + temporal conv + residual) in one kernel; stem_block.cu
+bool stem_block_supported(const TikNet* net, int dtype);
+int64_t stem_block_workspace_bytes();
+int stem_block_prepare(const TikNet* net, void* w16_dev, void* out, int64_t n_clips, int T, StemBlockPrepared** outp);
+int stem_block_launch(StemBlockPrepared* g, const float* x, int64_t n_clips, const TikWindowing* win, int64_t win_n0, cudaStream_t s);
+void stem_block_free(StemBlockPrepared* g);
 }  // namespace tik

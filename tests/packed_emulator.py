@@ -35,6 +35,20 @@ def rowgemm(slabs, w, bias, v, t_out, act, residual=None, quant=None):
     return y if quant is None else y.to(quant)
 
 
+def _hilo(a, q):
+    """fp32 -> bf16 hi + bf16 lo (what the stem-block kernel feeds the tensor core), back in fp32."""
+    hi = a.to(q).float()
+    return hi + (a - hi).to(q).float()
+
+
+def stem_block_applies(packed):
+    """Mirror of stem_block_supported (csrc/stem_block.cu): the first block runs as one tensor-core kernel."""
+    net = packed.net
+    b = net.blocks[0]
+    return (packed.tdtype == torch.bfloat16 and net.n_blocks > 1 and net.K == 1 and net.c_in == 3 and b.c_out == 64
+            and b.kt == 3 and b.stride == 1 and net.V <= 18 and b.res_kind in (0, 2))
+
+
 def forward(packed, x):
     """x (N,T,V,C) fp32 CPU -> poses (N,T',head_out).  Activations are rounded to packed.tdtype between kernels."""
     t = packed.named
@@ -47,9 +61,13 @@ def forward(packed, x):
     for i in range(net.n_blocks):
         b = net.blocks[i]
         A = t[f"b{i}.agg"]
+        fused0 = i == 0 and stem_block_applies(packed)
         if i == 0:
             xa = torch.einsum("kvw,ntvc->ntwkc", A, x0).reshape(N, T, V, K * Cin)          # (n,t,w,k*Cin+ci)
-            h = torch.relu(torch.einsum("ntwj,cj->ntwc", xa, t["b0.w_gcn"]) + t["b0.b_gcn"].view(1, 1, V, -1))
+            wg = t["b0.w_gcn"]
+            if fused0:                                                                       # bf16 weights, hi/lo inputs
+                xa, wg = _hilo(xa, q), wg.to(q).float()
+            h = torch.relu(torch.einsum("ntwj,cj->ntwc", xa, wg) + t["b0.b_gcn"].view(1, 1, V, -1))
             h = h.permute(0, 2, 1, 3).reshape(N * V, T, b.c_out).to(q)
         else:
             xn = cur.view(N, V, T, b.c_in).float()
@@ -65,7 +83,21 @@ def forward(packed, x):
             residual = cur
         elif b.res_kind == 2:
             xs = x[:, torch.arange(t_out) * b.stride]                                        # raw input frames
-            residual = torch.einsum("vci,ntvi->nvtc", t["b0.w_res_stem"], xs).reshape(N * V, t_out, b.c_out).to(q)
+            if fused0:
+                # the kernel multiplies (s0 * x) hi/lo by the unscaled bf16 residual weights and keeps R0 in fp32 (TMEM)
+                s0 = t["in_scale"].view(V, Cin)
+                vb = s0.abs().argmax(dim=0)                                                  # per channel: node with the largest scale
+                sc = s0[vb, torch.arange(Cin)]
+                wr = t["b0.w_res_stem"][vb, :, torch.arange(Cin)].t().double() / sc.double()  # (Cout, Cin)
+                wr = torch.where(sc[None, :] != 0, wr, torch.zeros_like(wr)).float().to(q).float()
+                residual = torch.einsum("ci,ntvi->nvtc", wr, _hilo(xs * s0.view(1, 1, V, Cin), q)).reshape(N * V, t_out, b.c_out)
+            else:
+                residual = torch.einsum("vci,ntvi->nvtc", t["b0.w_res_stem"], xs).reshape(N * V, t_out, b.c_out).to(q)
+        if fused0:                                                                           # taps only; R0 added in fp32
+            w_taps = t["b0.w_tcn"][:, : b.kt * b.c_out]
+            cur = rowgemm(slabs, w_taps, t["b0.b_tcn"], V, t_out, "relu", residual, quant=q)
+            T = t_out
+            continue
         if b.res_as_slab:                                                                    # identity block in w_tcn
             slabs.append((residual, 1, 0))
             residual = None
