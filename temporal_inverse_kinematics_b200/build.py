@@ -21,8 +21,20 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
+STAMP = os.path.join(HERE, "build", "flavour.txt")
+
+
+def _flavour():
+    return "probe" if os.environ.get("TIK_PROBE") == "1" else "release"
+
+
 def _stale():
     if not os.path.exists(LIB):
+        return True
+    try:
+        if open(STAMP).read().strip() != _flavour():     # a probe build must never be mistaken for the product library
+            return True
+    except OSError:
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
@@ -56,6 +68,8 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     subprocess.check_call([_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB, *objs, "-cudart", "static"])
+    with open(STAMP, "w") as f:
+        f.write(_flavour() + "\n")
     return LIB
 
 

@@ -12,17 +12,16 @@
 // Rows are node-major inside the tile, h = v*14 + l (238 rows = two 128-row MMA tiles), so a temporal tap is a
 // shift of the A operand by one 128-byte shared-memory row and a tap at a tile edge never crosses a node boundary
 // into a valid output row.
-//   builders (4 warps, SIMT): data_bn, adjacency aggregation and the residual's scaled input, written as ONE
+//   builders (8 warps, SIMT): data_bn, adjacency aggregation and the residual's scaled input, written as ONE
 //            16-wide K slice per row: [agg_hi | agg_lo | xs_hi | xs_lo | 0] (bf16 hi/lo split: the inputs keep
 //            ~16 bits of mantissa), double buffered;
-//   MMA A:   D[:, 0:64] = H0 pre-activation, D[:, 64:128] = R0  -- one K=16 tcgen05.mma per 128 rows against the
-//            stacked weights [Wg' ; Wr'];
-//   mid pass (16 warps): D[:, 0:64] + b1 -> ReLU -> zero outside the clip (the temporal conv pads H0, not x) -> bf16
+//   MMA A:   Hpre = slice . Wg'^T (H0 pre-activation) and RD = slice . Wr'^T (R0): one K=16 tcgen05.mma each per 128 rows;
+//   mid pass (16 warps): Hpre + b1 -> ReLU -> zero outside the clip (the temporal conv pads H0, not x) -> bf16
 //            -> shared memory in the 128B-swizzled K-major layout;
-//   MMA 3:   D[:, 64:128] += sum_dt H0[h + dt - 1] . Wt'[dt]^T -- accumulates ON TOP of R0 in tensor memory, so the
+//   MMA 3:   RD += sum_dt H0[h + dt - 1] . Wt'[dt]^T -- accumulates ON TOP of R0 in tensor memory, so the
 //            residual costs nothing;
-//   final pass: D[:, 64:128] + b2 -> ReLU -> bf16 -> staging (aliases the H0 tile) -> 4-D TMA store.
-// Two tiles are in flight (TMEM 2 x 256 columns): the epilogue warps run tile i+1's mid pass and tile i's final
+//   final pass: RD + b2 -> ReLU -> bf16 -> staging (aliases the H0 tile) -> 4-D TMA store.
+// Two tiles are in flight (TMEM: 2 x 128 columns of Hpre, 2 x 128 of RD): the epilogue warps run tile i+1's mid pass and tile i's final
 // pass while the tensor pipe executes tile i's temporal taps.
 #include <string.h>
 
@@ -51,7 +50,8 @@ constexpr int kSbOffH = kSbOffA0 + 4 * kSbTile;     // 2 buffers
 constexpr int kSbOffBias1 = kSbOffH + 2 * kSbHBytes;
 constexpr int kSbOffBias2 = kSbOffBias1 + kSbMaxV * kSbCout * 4;
 constexpr int kSbOffAs = kSbOffBias2 + kSbMaxV * kSbCout * 4;           // As[u][v][c] = A^[u,v] * s0[u,c]   (V*V*Cin fp32)
-constexpr int kSbOffCst = kSbOffAs + kSbMaxV * kSbMaxV * 4 * 4;         // cst[v][c] = sum_u A^[u,v] o0[u,c]; sum[v][c] = sum_u As; scale[v][c]
+constexpr int kSbOffNbr = kSbOffAs + kSbMaxV * kSbMaxV * 4 * 4;           // per node: count + source-node offsets of the non-zero A^[u,v]
+constexpr int kSbOffCst = kSbOffNbr + kSbMaxV * (kSbMaxV + 1) * 4;         // cst[v][c] = sum_u A^[u,v] o0[u,c]; sum[v][c] = sum_u As; scale[v][c]
 constexpr int kSbRawBufs = 3;                                           // raw keypoint tiles in flight (cp.async)
 constexpr int kSbOffRaw = kSbOffCst + 3 * kSbMaxV * 4 * 4;              // kSbRawBufs x 14 x V*Cin fp32
 constexpr int kSbOffBar = (kSbOffRaw + kSbRawBufs * kSbL * kSbMaxV * 4 * 4 + 15) / 16 * 16;
@@ -65,7 +65,15 @@ struct StemBlockParams {
   const float* bias2; int32_t bias2_per_node;
   int32_t n_clips, T, V, lo, tiles_t;       // lo = output frames per tile, tiles_t = ceil(T / lo)
   TikWindowing win; long long win_n0;
+  unsigned long long* dbg;                  // TIK_PROBE builds: clock64 timeline of CTA 0, tile iteration 4
 };
+
+#ifdef TIK_PROBE
+extern unsigned long long* g_dbg_times;   // stgcn_umma.cu (tik_debug_set_umma_times)
+#define SB_T(i) do { if (p.dbg != nullptr && blockIdx.x == 0) p.dbg[32 + (i)] = clock64(); } while (0)
+#else
+#define SB_T(i) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t bf16_bits(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
 
@@ -81,6 +89,7 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
   float* s_bias1 = reinterpret_cast<float*>(smem + kSbOffBias1);
   float* s_bias2 = reinterpret_cast<float*>(smem + kSbOffBias2);
   float* s_as = reinterpret_cast<float*>(smem + kSbOffAs);
+  int* s_nbr = reinterpret_cast<int*>(smem + kSbOffNbr);   // [v][0] = count, [v][1 + k] = u_k * CIN
   float* s_cst = reinterpret_cast<float*>(smem + kSbOffCst);
   float* s_sum = s_cst + kSbMaxV * 4;
   float* s_scale = s_sum + kSbMaxV * 4;
@@ -117,10 +126,20 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
     s_bias1[i] = __ldg(p.bias1 + i);
     s_bias2[i] = __ldg(p.bias2 + (p.bias2_per_node ? i : (i % kSbCout)));
   }
-  // data_bn folded into the aggregation:  sum_u A^[u,v] (s0[u,c] x[u,c] + o0[u,c]) = sum_u As[u,v,c] x[u,c] + cst[v,c]
-  for (int i = threadIdx.x; i < V * V * CIN; i += kSbThreads) {
-    const int c = i % CIN, uv = i / CIN, u = uv / V;
-    s_as[i] = __ldg(p.agg + uv) * __ldg(p.in_scale + u * CIN + c);
+  // data_bn folded into the aggregation:  sum_u A^[u,v] (s0[u,c] x[u,c] + o0[u,c]) = sum_u As[v,u,c] x[u,c] + cst[v,c]
+  // and only the non-zero adjacency entries are visited (the skeleton graph is sparse): compacted per target node v
+  if (threadIdx.x < V) {
+    const int v = threadIdx.x;
+    int cnt = 0;
+    for (int u = 0; u < V; ++u) {
+      const float a = __ldg(p.agg + u * V + v);
+      if (a != 0.f) {
+        s_nbr[v * (kSbMaxV + 1) + 1 + cnt] = u * CIN;
+        for (int c = 0; c < CIN; ++c) s_as[(v * kSbMaxV + cnt) * CIN + c] = a * __ldg(p.in_scale + u * CIN + c);
+        ++cnt;
+      }
+    }
+    s_nbr[v * (kSbMaxV + 1)] = cnt;
   }
   for (int i = threadIdx.x; i < VC; i += kSbThreads) {
     const int v = i / CIN, c = i - v * CIN;
@@ -136,6 +155,7 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) SB_T(0);
 
   if (warp == 0) {
     // ===================== weights (once) + TMA store issuer =====================
@@ -148,42 +168,62 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
         const int n = tile / p.tiles_t, tt = tile - n * p.tiles_t;
         const int b = it & 1;
         mbar_wait(&stage_full[b], (uint32_t)((it >> 1) & 1));
+        if (it == 4) SB_T(20);
         tma_store_4d(&p.map_out, s_h + (size_t)b * kSbHBytes + 1024, 0, tt * p.lo, 0, n);
         tma_store_commit();
         tma_store_wait_read0();
         mbar_arrive(&h_empty[b]);
+        if (it == 4) SB_T(21);
+        if (it == 5) SB_T(22);
       }
       tma_store_wait0();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform loop, lane 0 issues) =====================
-    constexpr uint32_t idesc_a = make_idesc_bf16(128, 128);
-    constexpr uint32_t idesc_3 = make_idesc_bf16(128, kSbCout);
+    constexpr uint32_t idesc = make_idesc_bf16(128, kSbCout);
     const bool leader = lane == 0;
     mbar_wait(w_full, 0);
     const uint32_t w16_u32 = smem_u32(s_w16), wt_u32 = smem_u32(s_wt), a0_u32 = smem_u32(s_a0), h_u32 = smem_u32(s_h);
-    auto issue_a = [&](int it) {
+    // TMEM: Hpre[b][j] at columns b*128 + j*64 (read by the mid pass), RD[b][j] at 256 + b*128 + j*64 (R0, then the
+    // temporal taps accumulate on top; read by the final pass).  Separate lifetimes: the next tile's H0 GEMM never
+    // waits for the previous final pass.
+    auto issue_ah = [&](int it) {
       const int b = it & 1;
-      const uint32_t ph = (uint32_t)((it >> 1) & 1);
-      mbar_wait(&a0_full[b], ph);
-      mbar_wait(&tmem_empty[b], ph ^ 1);
+      if (it == 4 && leader) SB_T(6);
+      mbar_wait(&a0_full[b], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
+      if (it == 4 && leader) SB_T(7);
       if (leader) {
 #pragma unroll
         for (int j = 0; j < 2; ++j)
-          umma_bf16(tmem_base + (uint32_t)(b * 256 + j * 128), make_smem_desc_kmajor_sw128(a0_u32 + (uint32_t)(b * 2 + j) * kSbTile),
-                    make_smem_desc_kmajor_sw128(w16_u32), idesc_a, 0u);
+          umma_bf16(tmem_base + (uint32_t)(b * 128 + j * 64), make_smem_desc_kmajor_sw128(a0_u32 + (uint32_t)(b * 2 + j) * kSbTile),
+                    make_smem_desc_kmajor_sw128(w16_u32), idesc, 0u);
         umma_commit(&da_full[b]);
+      }
+      __syncwarp();
+    };
+    auto issue_ar = [&](int it) {
+      const int b = it & 1;
+      mbar_wait(&tmem_empty[b], (uint32_t)(((it >> 1) & 1) ^ 1));
+      tc_fence_after();
+      if (it == 4 && leader) SB_T(8);
+      if (leader) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          umma_bf16(tmem_base + (uint32_t)(256 + b * 128 + j * 64), make_smem_desc_kmajor_sw128(a0_u32 + (uint32_t)(b * 2 + j) * kSbTile),
+                    make_smem_desc_kmajor_sw128(w16_u32 + 64u * 128u), idesc, 0u);
         umma_commit(&a0_empty[b]);
       }
       __syncwarp();
     };
-    if (my_tiles > 0) issue_a(0);
+    if (my_tiles > 0) { issue_ah(0); issue_ar(0); }
     for (int it = 0; it < my_tiles; ++it) {
       const int b = it & 1;
-      if (it + 1 < my_tiles) issue_a(it + 1);
+      if (it + 1 < my_tiles) issue_ah(it + 1);
+      if (it == 4 && leader) SB_T(9);
       mbar_wait(&h_full[b], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
+      if (it == 4 && leader) SB_T(10);
       if (leader) {
         const uint32_t hb = h_u32 + (uint32_t)b * kSbHBytes + 1024u;
 #pragma unroll
@@ -193,13 +233,15 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
             const uint32_t arow = hb + (uint32_t)(128 * j + dt - 1) * 128u;     // may start 128 B below the tile: guard rows
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + (uint32_t)(b * 256 + j * 128 + 64), make_smem_desc_kmajor_sw128(arow + (uint32_t)k * 32u),
-                        make_smem_desc_kmajor_sw128(wt_u32 + (uint32_t)dt * 8192u + (uint32_t)k * 32u), idesc_3, 1u);
+              umma_bf16(tmem_base + (uint32_t)(256 + b * 128 + j * 64), make_smem_desc_kmajor_sw128(arow + (uint32_t)k * 32u),
+                        make_smem_desc_kmajor_sw128(wt_u32 + (uint32_t)dt * 8192u + (uint32_t)k * 32u), idesc, 1u);
           }
         }
         umma_commit(&d3_full[b]);
+        if (it == 4) SB_T(11);
       }
       __syncwarp();
+      if (it + 1 < my_tiles) issue_ar(it + 1);
     }
   } else if (warp < 2 + kSbEpiWarps) {
     // ===================== epilogue warps: mid pass of tile i, then final pass of tile i-1 =====================
@@ -212,11 +254,13 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       const int tt = tile % p.tiles_t;
       (void)tt;
+      if (it == 4 && threadIdx.x == 64) SB_T(17);
       mbar_wait(&d3_full[b], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
+      if (it == 4 && threadIdx.x == 64) SB_T(18);
       uint32_t a[2][16];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) tmem_ld16(tmem_base + lane_off + (uint32_t)(b * 256 + j * 128 + 64 + cq * 16), a[j]);
+      for (int j = 0; j < 2; ++j) tmem_ld16(tmem_base + lane_off + (uint32_t)(256 + b * 128 + j * 64 + cq * 16), a[j]);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -245,6 +289,7 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&stage_full[b]);
+      if (it == 4 && threadIdx.x == 64) SB_T(19);
     };
     for (int it = 0; it < my_tiles; ++it) {
       const int b = it & 1;
@@ -253,13 +298,17 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
       const int tt = tile % p.tiles_t;
       const int t_first = tt * p.lo - 1;                  // frame of tile row l = 0
       // ---- mid pass
+      if (it == 4 && threadIdx.x == 64) SB_T(12);
       mbar_wait(&da_full[b], ph);
       tc_fence_after();
+      if (it == 4 && threadIdx.x == 64) SB_T(13);
       uint32_t a[2][16];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) tmem_ld16(tmem_base + lane_off + (uint32_t)(b * 256 + j * 128 + cq * 16), a[j]);
+      for (int j = 0; j < 2; ++j) tmem_ld16(tmem_base + lane_off + (uint32_t)(b * 128 + j * 64 + cq * 16), a[j]);
       tmem_ld_wait();
+      if (it == 4 && threadIdx.x == 64) SB_T(14);
       mbar_wait(&h_empty[b], ph ^ 1);                     // the store that read this buffer as a staging tile is done
+      if (it == 4 && threadIdx.x == 64) SB_T(15);
       uint8_t* hb = s_h + (size_t)b * kSbHBytes + 1024;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -281,10 +330,13 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
           *reinterpret_cast<uint4*>(hb + (size_t)h * 128 + (((cq * 2 + q) ^ (h & 7)) << 4)) = u;
         }
       }
+      if (it == 4 && threadIdx.x == 64) SB_T(23);
       tc_fence_before();
       fence_proxy_async_smem();
+      if (it == 4 && threadIdx.x == 64) SB_T(24);
       __syncwarp();
       if (lane == 0) mbar_arrive(&h_full[b]);
+      if (it == 4 && threadIdx.x == 64) SB_T(16);
       // ---- final pass of the previous tile (its temporal taps ran on the tensor pipe during this mid pass)
       if (it > 0) final_pass(it - 1);
     }
@@ -324,11 +376,16 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
     prefetch(1);
     for (int it = 0; it < my_tiles; ++it) {
       const int b = it & 1;
+      if (it == 4 && tid == 0) SB_T(1);
       prefetch(it + 2);
+      if (it == 4 && tid == 0) SB_T(28);
       asm volatile("cp.async.wait_group 2;" ::: "memory");
+      if (it == 4 && tid == 0) SB_T(29);
       named_bar_sync(3, NB);                                // every thread's copies of tile `it` have landed
       const float* raw = s_rawbuf + (it % kSbRawBufs) * (kSbL * kSbMaxV * 4);
+      if (it == 4 && tid == 0) SB_T(2);
       mbar_wait(&a0_empty[b], (uint32_t)(((it >> 1) & 1) ^ 1));
+      if (it == 4 && tid == 0) SB_T(3);
       const int h = tid;
       if (h < V * kSbL) {
         const int v = h / kSbL, l = h - v * kSbL;
@@ -341,10 +398,14 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
           agg[c] = s_cst[v * CIN + c] - root[c] * s_sum[v * CIN + c];
           xs[c] = (fr[v * CIN + c] - root[c]) * s_scale[v * CIN + c];
         }
-        for (int u = 0; u < V; ++u) {
+        const int* nbr = s_nbr + v * (kSbMaxV + 1);
+        const int cnt = nbr[0];
+        for (int k = 0; k < cnt; ++k) {
+          const float* xu = fr + nbr[1 + k];
 #pragma unroll
-          for (int c = 0; c < CIN; ++c) agg[c] = fmaf(s_as[(u * V + v) * CIN + c], fr[u * CIN + c], agg[c]);
+          for (int c = 0; c < CIN; ++c) agg[c] = fmaf(s_as[(v * kSbMaxV + k) * CIN + c], xu[c], agg[c]);
         }
+        if (it == 4 && tid == 0) SB_T(25);
         // slots: [agg_hi(CIN) | agg_lo(CIN) | xs_hi(CIN) | xs_lo(CIN) | 0...]
         uint32_t e[16];
 #pragma unroll
@@ -364,10 +425,14 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
         *reinterpret_cast<uint4*>(row + ((0 ^ (h & 7)) << 4)) = p0;
         *reinterpret_cast<uint4*>(row + ((1 ^ (h & 7)) << 4)) = p1;
       }
+      if (it == 4 && tid == 0) SB_T(26);
       fence_proxy_async_smem();
+      if (it == 4 && tid == 0) SB_T(27);
       __syncwarp();
       if (lane == 0) mbar_arrive(&a0_full[b]);
+      if (it == 4 && tid == 0) SB_T(4);
       named_bar_sync(3, NB);                                // the raw buffer is refilled by the next prefetch
+      if (it == 4 && tid == 0) SB_T(5);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
@@ -472,6 +537,9 @@ int stem_block_launch(StemBlockPrepared* g, const float* x, int64_t n_clips, con
   p.x = x; p.n_clips = (int32_t)n_clips;
   if (win) p.win = *win; else { p.win.frames = 0; p.win.offset = 0; p.win.stride = 1; p.win.root_a = -1; p.win.root_b = -1; }
   p.win_n0 = (long long)win_n0;
+#ifdef TIK_PROBE
+  p.dbg = g_dbg_times;
+#endif
   static bool attr_done[64] = {};
   int dev = 0;
   TIK_CUDA(cudaGetDevice(&dev));

@@ -577,7 +577,7 @@ int umma_prepare(const TikRowGemm* d, int64_t nv_capacity, UmmaPrepared** out) {
 }
 
 static int g_dbg_shift_rows = 0, g_dbg_base_offset_mode = 0, g_dbg_flags = 0;
-static unsigned long long* g_dbg_times = nullptr;
+unsigned long long* g_dbg_times = nullptr;   // also read by stem_block.cu in TIK_PROBE builds
 
 int umma_launch(UmmaPrepared* u, const TikRowGemm* d, cudaStream_t s) {
   UmmaParams& p = u->p;

@@ -149,6 +149,10 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "big":
         big()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "tlbig":
+        case("b1 tcn  3x64    T64 +slab, 4096 clips", 4096, 64, 64, [64, 64, 64, 64], 64, 1, False)
+        case("b3 tcn  3x128+128 T32, 4096 clips", 4096, 32, 32, [128, 128, 128, 128], 128, 1, False)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "tl":
         case("b1 tcn  3x64    T64 +slab", 128, 64, 64, [64, 64, 64, 64], 64, 1, False)
         case("b3 tcn  3x128+128 T32", 128, 32, 32, [128, 128, 128, 128], 128, 1, False)
