@@ -10,12 +10,13 @@
 //   MMA 1 (aggregation as a dense block-structured GEMM):   D1[128 x Cin] = Abd[128 x 128] . Xtile[128 x Cin]
 //          Abd[(w,t),(v,t')] = A^[v,w] * delta(t,t'), bf16, K-major, resident in shared memory;
 //          the X tile is used in place as the MN-major B operand (rows = K, channels contiguous).
-//   mid pass: 16 warps move D1 TMEM -> registers -> bf16 -> the SAME shared-memory tile, now a K-major A operand.
+//   mid pass: 8 warps move D1 TMEM -> registers -> bf16 -> the SAME shared-memory tile, now a K-major A operand.
 //   MMA 2 (channel mix):                                      D2[128 x Cout] = Xagg[128 x Cin] . Wg'[Cout x Cin]^T
 //   final pass: D2 + bias[node] -> ReLU -> bf16 -> swizzled staging -> 4-D TMA store (box clipped at the clip end).
 // The dense Abd multiply costs 128/Cout of the channel GEMM in tensor time, far less than a round trip of the
-// aggregated tensor through HBM.  Warp roles as in stgcn_umma.cu: warp 0 TMA producer, warp 1 MMA issuer,
-// 16 epilogue warps (TMEM lane group x column quarter).
+// aggregated tensor through HBM.  Warp roles: warp 0 TMA producer, warp 1 MMA issuer, 8 mid-pass warps and 8
+// final-pass warps (TMEM lane group x column half each), so tile i+1's mid pass overlaps tile i's final pass; D1 is
+// double buffered in tensor memory, D2 too when 2*(Cin+Cout) <= 512 columns.
 #include <string.h>
 
 #include <algorithm>
@@ -25,7 +26,8 @@
 
 namespace tik {
 
-constexpr int kGfThreads = 64 + 32 * 16;
+constexpr int kGfGroupWarps = 8;                  // warps per epilogue group (mid pass / final pass)
+constexpr int kGfThreads = 64 + 32 * 2 * kGfGroupWarps;
 constexpr int kGfTile = 16384;                     // one 128-row x 64-channel swizzled slab
 constexpr int kGfSmemBudget = 225 * 1024;
 constexpr int kGfMaxBufs = 8;                      // input tiles in flight: the kernel is HBM-latency bound otherwise
@@ -33,7 +35,8 @@ constexpr int kGfMaxBufs = 8;                      // input tiles in flight: the
 struct GcnFusedParams {
   CUtensorMap map_x, map_out, map_abd, map_w;
   int32_t n_clips, T, V, ttg, tiles_t;   // ttg = frames per tile (min(T, 7))
-  int32_t xbufs;                          // 1 or 2 input tiles in flight
+  int32_t xbufs;                          // input tiles in flight
+  int32_t sbufs;                          // staging tiles (2: the store of tile i-1 may still be reading while tile i is staged)
   int32_t off_w, off_x, off_stage, off_bias, off_bar;
   const float* bias;                      // (V, COUT)
   int32_t relu;
@@ -43,7 +46,9 @@ template <int CIN, int COUT>
 __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_constant__ GcnFusedParams p) {
   constexpr int KC1 = CIN / 64;                       // 64-channel slabs of the input
   constexpr int KC2 = COUT / 64;
-  constexpr int TMEM_COLS = (CIN + COUT) <= 128 ? 128 : ((CIN + COUT) <= 256 ? 256 : 512);
+  constexpr int ND2 = (2 * CIN + 2 * COUT) <= 512 ? 2 : 1;   // D1 is always double buffered, D2 when it fits
+  constexpr int TMEM_NEED = 2 * CIN + ND2 * COUT;
+  constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* s_abd = smem;                              // 2 slabs (K = 0..63, 64..127) of 128 rows
@@ -54,14 +59,15 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
   uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [kGfMaxBufs]
   uint64_t* x_empty = x_full + kGfMaxBufs;            // [kGfMaxBufs]
   uint64_t* w_full = x_empty + kGfMaxBufs;
-  uint64_t* d1_full = w_full + 1;
-  uint64_t* xagg_full = d1_full + 1;
-  uint64_t* d2_full = xagg_full + 1;
-  uint64_t* d2_empty = d2_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 1);
+  uint64_t* d1_full = w_full + 1;                     // [2] aggregation MMA done -> mid group
+  uint64_t* xagg_full = d1_full + 2;                  // [2] mid group rewrote the tile as bf16 Xagg -> channel MMA
+  uint64_t* d2_full = xagg_full + 2;                  // [2] channel MMA done -> final group
+  uint64_t* d2_empty = d2_full + 2;                   // [2] final group has read D2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.n_clips * p.tiles_t;
+  const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int rows_valid = p.ttg * p.V;                 // rows the TMA box fills (<= 128)
   const uint32_t x_bytes = (uint32_t)(KC1 * rows_valid * 128);
 
@@ -70,7 +76,10 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kGfMaxBufs; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-    mbar_init(w_full, 1); mbar_init(d1_full, 1); mbar_init(xagg_full, 16); mbar_init(d2_full, 1); mbar_init(d2_empty, 16);
+    mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&d1_full[i], 1); mbar_init(&xagg_full[i], kGfGroupWarps); mbar_init(&d2_full[i], 1); mbar_init(&d2_empty[i], kGfGroupWarps);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -89,7 +98,7 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + CIN;
+  const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + 2 * CIN;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -111,37 +120,48 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // Warp-uniform loop, lane 0 issues.  Software-pipelined: the aggregation MMA of tile i+1 is issued right after
-    // the channel MMA of tile i, so it runs on the tensor pipe while the epilogue warps do tile i's final pass.
+    // Warp-uniform loop, lane 0 issues.  The aggregation MMA of tile i+1 goes out before the channel MMA of tile i
+    // (D1 is double buffered), so the mid group can start on tile i+1 while the final group drains tile i.
     constexpr uint32_t idesc1 = make_idesc_bf16(128, CIN) | (1u << 16);   // B operand MN-major
     constexpr uint32_t idesc2 = make_idesc_bf16(128, COUT);
     const bool leader = lane == 0;
     mbar_wait(w_full, 0);
     const uint32_t abd_u32 = smem_u32(s_abd), w_u32 = smem_u32(s_w), x_u32 = smem_u32(s_x);
-    auto issue_mma1 = [&](uint32_t xb) {
+    auto issue_mma1 = [&](uint32_t xb, int s) {
       if (leader) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint64_t da = make_smem_desc_kmajor_sw128(abd_u32 + (uint32_t)(k >> 2) * kGfTile + (uint32_t)(k & 3) * 32u);
           const uint64_t db = make_smem_desc_mnmajor_sw128(xb + (uint32_t)k * 2048u, (uint32_t)kGfTile);
-          umma_bf16(tmem_d1, da, db, idesc1, k != 0 ? 1u : 0u);
+          umma_bf16(tmem_d1 + (uint32_t)(s * CIN), da, db, idesc1, k != 0 ? 1u : 0u);
         }
-        umma_commit(d1_full);
+        umma_commit(&d1_full[s]);
       }
       __syncwarp();
     };
-    int b = 0; uint32_t phase = 0, tphase = 0;
-    int tile = blockIdx.x;
-    if (tile < n_tiles) {
+    int b = 0; uint32_t phase = 0;
+    if (my_tiles > 0) {
       mbar_wait(&x_full[0], 0);
       tc_fence_after();
-      issue_mma1(x_u32);
+      issue_mma1(x_u32, 0);
     }
-    for (; tile < n_tiles; tile += gridDim.x) {
+    for (int it = 0; it < my_tiles; ++it) {
       const uint32_t xb = x_u32 + (uint32_t)b * (uint32_t)(KC1 * kGfTile);
-      // ---- MMA 2: D2 = Xagg . Wg^T once the epilogue warps have rewritten the tile as bf16 Xagg
-      mbar_wait(xagg_full, tphase);
-      mbar_wait(d2_empty, tphase ^ 1);                     // previous tile's D2 has been read
+      const int s = it & 1;
+      const int s2 = ND2 == 2 ? s : 0;
+      int nb = b + 1; uint32_t nphase = phase;
+      if (nb == p.xbufs) { nb = 0; nphase ^= 1; }
+      // ---- MMA 1 of the NEXT tile: D1[(it+1)&1] was drained by the mid pass of tile it-1 (its xagg_full was waited on).
+      // With a single X buffer the next tile cannot land before this tile's channel MMA has released it.
+      const bool early = p.xbufs >= 2;
+      if (early && it + 1 < my_tiles) {
+        mbar_wait(&x_full[nb], nphase);
+        tc_fence_after();
+        issue_mma1(x_u32 + (uint32_t)nb * (uint32_t)(KC1 * kGfTile), s ^ 1);
+      }
+      // ---- MMA 2: D2 = Xagg . Wg^T once the mid group has rewritten the tile as bf16 Xagg
+      mbar_wait(&xagg_full[s], (uint32_t)((it >> 1) & 1));
+      mbar_wait(&d2_empty[s2], (uint32_t)(((ND2 == 2 ? (it >> 1) : it) & 1) ^ 1));   // that accumulator has been read
       tc_fence_after();
       if (leader) {
 #pragma unroll
@@ -150,77 +170,93 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = make_smem_desc_kmajor_sw128(xb + (uint32_t)kc * kGfTile + (uint32_t)k * 32u);
             const uint64_t db = make_smem_desc_kmajor_sw128(w_u32 + (uint32_t)kc * (COUT * 128) + (uint32_t)k * 32u);
-            umma_bf16(tmem_d2, da, db, idesc2, (kc | k) != 0 ? 1u : 0u);
+            umma_bf16(tmem_d2 + (uint32_t)(s2 * COUT), da, db, idesc2, (kc | k) != 0 ? 1u : 0u);
           }
         }
-        umma_commit(d2_full);
+        umma_commit(&d2_full[s2]);
         umma_commit(&x_empty[b]);                            // the tile buffer may be refilled once MMA 2 has read it
       }
       __syncwarp();
-      tphase ^= 1;
-      if (++b == p.xbufs) { b = 0; phase ^= 1; }
-      // ---- MMA 1 of the NEXT tile: D1 is free (tile i's mid pass finished before xagg_full), its X tile is in the ring
-      if (tile + (int)gridDim.x < n_tiles) {
-        mbar_wait(&x_full[b], phase);
+      if (!early && it + 1 < my_tiles) {
+        mbar_wait(&x_full[nb], nphase);
         tc_fence_after();
-        issue_mma1(x_u32 + (uint32_t)b * (uint32_t)(KC1 * kGfTile));
+        issue_mma1(x_u32 + (uint32_t)nb * (uint32_t)(KC1 * kGfTile), s ^ 1);
       }
+      b = nb; phase = nphase;
     }
-  } else {
-    // ===================== epilogue warps: mid pass (D1 -> bf16 Xagg) and final pass (D2 -> H) =====================
-    constexpr int CW1 = CIN / 4, CW2 = COUT / 4;
+  } else if (warp < 2 + kGfGroupWarps) {
+    // ===================== mid group (8 warps): D1 -> bf16 Xagg, in place over the X tile =====================
+    constexpr int CW1 = CIN / 2;                             // columns per thread: TMEM lane group x column half
     const int lane_grp = warp & 3;
-    const int cq = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;
     const int r = lane_grp * 32 + lane;
-    const int node = r / p.ttg;                              // tile row r = node * ttg + t_local
-    const float* bias = s_bias + (node < p.V ? node : 0) * COUT + cq * CW2;
     const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
-    int b = 0; uint32_t tphase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int n = tile / p.tiles_t, tt = tile - n * p.tiles_t;
-      const int t0 = min(tt * p.ttg, p.T - p.ttg);
+    int b = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it & 1;
       uint8_t* xrow = s_x + (size_t)b * KC1 * kGfTile + (size_t)r * 128;
-      // ---- mid pass
-      mbar_wait(d1_full, tphase);
+      mbar_wait(&d1_full[s], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      {
-        uint32_t a[CW1];
+      uint32_t a[CW1];
 #pragma unroll
-        for (int i = 0; i < CW1 / 16; ++i) tmem_ld16(tmem_d1 + lane_off + (uint32_t)(cq * CW1 + 16 * i), a + 16 * i);
-        tmem_ld_wait();
+      for (int i = 0; i < CW1 / 16; ++i) tmem_ld16(tmem_d1 + lane_off + (uint32_t)(s * CIN + half * CW1 + 16 * i), a + 16 * i);
+      tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < CW1 / 8; ++q) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(a[8 * q + 0]), __uint_as_float(a[8 * q + 1]));
-          u.y = pack_bf16x2(__uint_as_float(a[8 * q + 2]), __uint_as_float(a[8 * q + 3]));
-          u.z = pack_bf16x2(__uint_as_float(a[8 * q + 4]), __uint_as_float(a[8 * q + 5]));
-          u.w = pack_bf16x2(__uint_as_float(a[8 * q + 6]), __uint_as_float(a[8 * q + 7]));
-          const int col = cq * CW1 + 8 * q;
-          const int j = (col & 63) >> 3;
-          *reinterpret_cast<uint4*>(xrow + (size_t)(col >> 6) * kGfTile + ((j ^ (r & 7)) << 4)) = u;
-        }
+      for (int q = 0; q < CW1 / 8; ++q) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(a[8 * q + 0]), __uint_as_float(a[8 * q + 1]));
+        u.y = pack_bf16x2(__uint_as_float(a[8 * q + 2]), __uint_as_float(a[8 * q + 3]));
+        u.z = pack_bf16x2(__uint_as_float(a[8 * q + 4]), __uint_as_float(a[8 * q + 5]));
+        u.w = pack_bf16x2(__uint_as_float(a[8 * q + 6]), __uint_as_float(a[8 * q + 7]));
+        const int col = half * CW1 + 8 * q;
+        const int j = (col & 63) >> 3;
+        *reinterpret_cast<uint4*>(xrow + (size_t)(col >> 6) * kGfTile + ((j ^ (r & 7)) << 4)) = u;
       }
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(xagg_full);
-      // ---- final pass
-      if (threadIdx.x == 64) tma_store_wait_read0();          // previous tile's store has finished reading the staging tile
-      mbar_wait(d2_full, tphase);
+      if (lane == 0) mbar_arrive(&xagg_full[s]);
+      if (++b == p.xbufs) b = 0;
+    }
+  } else {
+    // ===================== final group (8 warps): D2 + bias -> ReLU -> bf16 -> staging -> TMA store =====================
+    constexpr int CW2 = COUT / 2;                            // columns per thread
+    constexpr int SUB = CW2 > 64 ? 64 : CW2;                 // columns per register pass
+    const int lane_grp = warp & 3;
+    const int half = (warp - 2 - kGfGroupWarps) >> 2;
+    const int r = lane_grp * 32 + lane;
+    const int node = r / p.ttg;                              // tile row r = node * ttg + t_local
+    const float* bias = s_bias + (node < p.V ? node : 0) * COUT + half * CW2;
+    const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
+    const bool issuer = threadIdx.x == 32 * (2 + kGfGroupWarps);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int n = tile / p.tiles_t, tt = tile - n * p.tiles_t;
+      const int t0 = min(tt * p.ttg, p.T - p.ttg);
+      const int s2 = ND2 == 2 ? (it & 1) : 0;
+      uint8_t* stage = s_stage + (size_t)((p.sbufs == 2) ? (it & 1) : 0) * (KC2 * kGfTile);
+      if (issuer) {                                          // the store that last read this staging tile has finished reading it
+        if (p.sbufs == 2) tma_store_wait_read1(); else tma_store_wait_read0();
+      }
+      mbar_wait(&d2_full[s2], (uint32_t)((ND2 == 2 ? (it >> 1) : it) & 1));
       tc_fence_after();
-      {
-        uint32_t a[CW2];
 #pragma unroll
-        for (int i = 0; i < CW2 / 16; ++i) tmem_ld16(tmem_d2 + lane_off + (uint32_t)(cq * CW2 + 16 * i), a + 16 * i);
+      for (int sub = 0; sub < CW2 / SUB; ++sub) {
+        uint32_t a[SUB];
+#pragma unroll
+        for (int i = 0; i < SUB / 16; ++i)
+          tmem_ld16(tmem_d2 + lane_off + (uint32_t)(s2 * COUT + half * CW2 + sub * SUB + 16 * i), a + 16 * i);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(d2_empty);
-        named_bar_sync(1, 512);                               // staging tile free (store issuer passed wait_read)
+        if (sub == CW2 / SUB - 1) {                          // accumulator fully in registers: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&d2_empty[s2]);
+        }
+        if (sub == 0) named_bar_sync(1, 32 * kGfGroupWarps); // staging tile free (issuer passed wait_read)
 #pragma unroll
-        for (int q = 0; q < CW2 / 8; ++q) {
-          const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * q);
-          const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * q + 4);
+        for (int q = 0; q < SUB / 8; ++q) {
+          const float4 b0 = *reinterpret_cast<const float4*>(bias + sub * SUB + 8 * q);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias + sub * SUB + 8 * q + 4);
           const float v0 = __uint_as_float(a[8 * q + 0]) + b0.x, v1 = __uint_as_float(a[8 * q + 1]) + b0.y;
           const float v2 = __uint_as_float(a[8 * q + 2]) + b0.z, v3 = __uint_as_float(a[8 * q + 3]) + b0.w;
           const float v4 = __uint_as_float(a[8 * q + 4]) + b1.x, v5 = __uint_as_float(a[8 * q + 5]) + b1.y;
@@ -228,21 +264,19 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
           uint4 u;
           if (p.relu) { u.x = pack_bf16x2_relu(v0, v1); u.y = pack_bf16x2_relu(v2, v3); u.z = pack_bf16x2_relu(v4, v5); u.w = pack_bf16x2_relu(v6, v7); }
           else { u.x = pack_bf16x2(v0, v1); u.y = pack_bf16x2(v2, v3); u.z = pack_bf16x2(v4, v5); u.w = pack_bf16x2(v6, v7); }
-          const int col = cq * CW2 + 8 * q;
+          const int col = half * CW2 + sub * SUB + 8 * q;
           const int j = (col & 63) >> 3;
-          *reinterpret_cast<uint4*>(s_stage + (size_t)(col >> 6) * kGfTile + (size_t)r * 128 + ((j ^ (r & 7)) << 4)) = u;
+          *reinterpret_cast<uint4*>(stage + (size_t)(col >> 6) * kGfTile + (size_t)r * 128 + ((j ^ (r & 7)) << 4)) = u;
         }
       }
       fence_proxy_async_smem();
-      named_bar_sync(2, 512);
-      if (threadIdx.x == 64) {
-        for (int c = 0; c < KC2; ++c) tma_store_4d(&p.map_out, s_stage + (size_t)c * kGfTile, c * 64, t0, 0, n);
+      named_bar_sync(2, 32 * kGfGroupWarps);
+      if (issuer) {
+        for (int c = 0; c < KC2; ++c) tma_store_4d(&p.map_out, stage + (size_t)c * kGfTile, c * 64, t0, 0, n);
         tma_store_commit();
       }
-      tphase ^= 1;
-      if (++b == p.xbufs) b = 0;
     }
-    if (threadIdx.x == 64) tma_store_wait0();
+    if (issuer) tma_store_wait0();
   }
   __syncwarp();
   tc_fence_before();
@@ -331,7 +365,13 @@ int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float
   const int kc1 = cin / 64, kc2 = cout / 64;
   const int w_bytes = kc1 * cout * 128;
   const int bias_bytes = (V * cout * 4 + 1023) / 1024 * 1024;
-  const int fixed = 2 * kGfTile + w_bytes + kc2 * kGfTile + bias_bytes + 256;
+  // two staging tiles when at least three input tiles still fit beside them (measured: input depth matters more)
+  p.sbufs = 2;
+  int fixed = 2 * kGfTile + w_bytes + p.sbufs * kc2 * kGfTile + bias_bytes + 256;
+  if ((kGfSmemBudget - fixed) / (kc1 * kGfTile) < 3) {
+    p.sbufs = 1;
+    fixed = 2 * kGfTile + w_bytes + kc2 * kGfTile + bias_bytes + 256;
+  }
   p.xbufs = (kGfSmemBudget - fixed) / (kc1 * kGfTile);
   if (p.xbufs > kGfMaxBufs) p.xbufs = kGfMaxBufs;
   if (p.xbufs < 1) {
@@ -342,7 +382,7 @@ int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float
   p.off_w = 2 * kGfTile;
   p.off_x = p.off_w + (w_bytes + 1023) / 1024 * 1024;
   p.off_stage = p.off_x + p.xbufs * kc1 * kGfTile;
-  p.off_bias = p.off_stage + kc2 * kGfTile;
+  p.off_bias = p.off_stage + p.sbufs * kc2 * kGfTile;
   p.off_bar = p.off_bias + bias_bytes;
   g->smem_bytes = p.off_bar + 256 + 1024;
   *outp = g;
