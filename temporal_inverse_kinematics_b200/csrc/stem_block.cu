@@ -16,13 +16,13 @@
 //            16-wide K slice per row: [agg_hi | agg_lo | xs_hi | xs_lo | 0] (bf16 hi/lo split: the inputs keep
 //            ~16 bits of mantissa), double buffered;
 //   MMA A:   Hpre = slice . Wg'^T (H0 pre-activation) and RD = slice . Wr'^T (R0): one K=16 tcgen05.mma each per 128 rows;
-//   mid pass (16 warps): Hpre + b1 -> ReLU -> zero outside the clip (the temporal conv pads H0, not x) -> bf16
+//   mid pass (8 warps): Hpre + b1 -> ReLU -> zero outside the clip (the temporal conv pads H0, not x) -> bf16
 //            -> shared memory in the 128B-swizzled K-major layout;
 //   MMA 3:   RD += sum_dt H0[h + dt - 1] . Wt'[dt]^T -- accumulates ON TOP of R0 in tensor memory, so the
 //            residual costs nothing;
-//   final pass: RD + b2 -> ReLU -> bf16 -> staging (aliases the H0 tile) -> 4-D TMA store.
+//   final pass (8 other warps): RD + b2 -> ReLU -> bf16 -> staging (aliases the H0 tile) -> 4-D TMA store.
 // Two tiles are in flight (TMEM: 2 x 128 columns of Hpre, 2 x 128 of RD): the epilogue warps run tile i+1's mid pass and tile i's final
-// pass while the tensor pipe executes tile i's temporal taps.
+// pass concurrently, while the tensor pipe executes tile i's temporal taps.
 #include <string.h>
 
 #include <algorithm>
@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a0_full[i], kSbBuildWarps); mbar_init(&a0_empty[i], 1); mbar_init(&da_full[i], 1);
-      mbar_init(&h_full[i], kSbEpiWarps); mbar_init(&d3_full[i], 1); mbar_init(&tmem_empty[i], kSbEpiWarps);
-      mbar_init(&stage_full[i], kSbEpiWarps); mbar_init(&h_empty[i], 1);
+      mbar_init(&h_full[i], kSbEpiWarps / 2); mbar_init(&d3_full[i], 1); mbar_init(&tmem_empty[i], kSbEpiWarps / 2);
+      mbar_init(&stage_full[i], kSbEpiWarps / 2); mbar_init(&h_empty[i], 1);
     }
     fence_barrier_init();
   }
@@ -243,91 +243,47 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
       __syncwarp();
       if (it + 1 < my_tiles) issue_ar(it + 1);
     }
-  } else if (warp < 2 + kSbEpiWarps) {
-    // ===================== epilogue warps: mid pass of tile i, then final pass of tile i-1 =====================
+  } else if (warp < 2 + kSbEpiWarps / 2) {
+    // ===================== mid group (8 warps): Hpre + b1 -> ReLU -> bf16 H0 tile in shared memory =====================
     const int lane_grp = warp & 3;
-    const int cq = (warp - 2) >> 2;                       // 16-column quarter of the 64 channels
+    const int half = (warp - 2) >> 2;                     // 32-column half of the 64 channels
     const int i_row = lane_grp * 32 + lane;
     const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
-    auto final_pass = [&](int it) {
-      const int b = it & 1;
-      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-      const int tt = tile % p.tiles_t;
-      (void)tt;
-      if (it == 4 && threadIdx.x == 64) SB_T(17);
-      mbar_wait(&d3_full[b], (uint32_t)((it >> 1) & 1));
-      tc_fence_after();
-      if (it == 4 && threadIdx.x == 64) SB_T(18);
-      uint32_t a[2][16];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) tmem_ld16(tmem_base + lane_off + (uint32_t)(256 + b * 128 + j * 64 + cq * 16), a[j]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[b]);
-      uint8_t* stage = s_h + (size_t)b * kSbHBytes + 1024;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int h = 128 * j + i_row;
-        const int v = h / kSbL, l = h - v * kSbL;
-        if (v < V && l >= 1 && l <= p.lo) {
-          const int srow = v * p.lo + l - 1;
-          const float* bias = s_bias2 + v * kSbCout + cq * 16;
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * q);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * q + 4);
-            uint4 u;
-            u.x = pack_bf16x2_relu(__uint_as_float(a[j][8 * q + 0]) + b0.x, __uint_as_float(a[j][8 * q + 1]) + b0.y);
-            u.y = pack_bf16x2_relu(__uint_as_float(a[j][8 * q + 2]) + b0.z, __uint_as_float(a[j][8 * q + 3]) + b0.w);
-            u.z = pack_bf16x2_relu(__uint_as_float(a[j][8 * q + 4]) + b1.x, __uint_as_float(a[j][8 * q + 5]) + b1.y);
-            u.w = pack_bf16x2_relu(__uint_as_float(a[j][8 * q + 6]) + b1.z, __uint_as_float(a[j][8 * q + 7]) + b1.w);
-            *reinterpret_cast<uint4*>(stage + (size_t)srow * 128 + (((cq * 2 + q) ^ (srow & 7)) << 4)) = u;
-          }
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&stage_full[b]);
-      if (it == 4 && threadIdx.x == 64) SB_T(19);
-    };
     for (int it = 0; it < my_tiles; ++it) {
       const int b = it & 1;
       const uint32_t ph = (uint32_t)((it >> 1) & 1);
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       const int tt = tile % p.tiles_t;
       const int t_first = tt * p.lo - 1;                  // frame of tile row l = 0
-      // ---- mid pass
       if (it == 4 && threadIdx.x == 64) SB_T(12);
       mbar_wait(&da_full[b], ph);
       tc_fence_after();
       if (it == 4 && threadIdx.x == 64) SB_T(13);
-      uint32_t a[2][16];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) tmem_ld16(tmem_base + lane_off + (uint32_t)(b * 128 + j * 64 + cq * 16), a[j]);
-      tmem_ld_wait();
-      if (it == 4 && threadIdx.x == 64) SB_T(14);
       mbar_wait(&h_empty[b], ph ^ 1);                     // the store that read this buffer as a staging tile is done
       if (it == 4 && threadIdx.x == 64) SB_T(15);
       uint8_t* hb = s_h + (size_t)b * kSbHBytes + 1024;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < 2; ++j) {                       // one 128-row MMA tile at a time: 32 live accumulator registers
+        uint32_t a[32];
+        tmem_ld16(tmem_base + lane_off + (uint32_t)(b * 128 + j * 64 + half * 32), a);
+        tmem_ld16(tmem_base + lane_off + (uint32_t)(b * 128 + j * 64 + half * 32 + 16), a + 16);
+        tmem_ld_wait();
         const int h = 128 * j + i_row;
         const int v = h / kSbL, l = h - v * kSbL;
         const int t = t_first + l;
         const bool ok = v < V && t >= 0 && t < p.T;
-        const float* bias = s_bias1 + (v < V ? v : 0) * kSbCout + cq * 16;
+        const float* bias = s_bias1 + (v < V ? v : 0) * kSbCout + half * 32;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
+        for (int q = 0; q < 4; ++q) {
           const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * q);
           const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * q + 4);
           uint4 u;
-          u.x = pack_bf16x2_relu(__uint_as_float(a[j][8 * q + 0]) + b0.x, __uint_as_float(a[j][8 * q + 1]) + b0.y);
-          u.y = pack_bf16x2_relu(__uint_as_float(a[j][8 * q + 2]) + b0.z, __uint_as_float(a[j][8 * q + 3]) + b0.w);
-          u.z = pack_bf16x2_relu(__uint_as_float(a[j][8 * q + 4]) + b1.x, __uint_as_float(a[j][8 * q + 5]) + b1.y);
-          u.w = pack_bf16x2_relu(__uint_as_float(a[j][8 * q + 6]) + b1.z, __uint_as_float(a[j][8 * q + 7]) + b1.w);
+          u.x = pack_bf16x2_relu(__uint_as_float(a[8 * q + 0]) + b0.x, __uint_as_float(a[8 * q + 1]) + b0.y);
+          u.y = pack_bf16x2_relu(__uint_as_float(a[8 * q + 2]) + b0.z, __uint_as_float(a[8 * q + 3]) + b0.w);
+          u.z = pack_bf16x2_relu(__uint_as_float(a[8 * q + 4]) + b1.x, __uint_as_float(a[8 * q + 5]) + b1.y);
+          u.w = pack_bf16x2_relu(__uint_as_float(a[8 * q + 6]) + b1.z, __uint_as_float(a[8 * q + 7]) + b1.w);
           if (!ok) u = make_uint4(0, 0, 0, 0);            // temporal zero padding applies to H0
-          *reinterpret_cast<uint4*>(hb + (size_t)h * 128 + (((cq * 2 + q) ^ (h & 7)) << 4)) = u;
+          *reinterpret_cast<uint4*>(hb + (size_t)h * 128 + (((half * 4 + q) ^ (h & 7)) << 4)) = u;
         }
       }
       if (it == 4 && threadIdx.x == 64) SB_T(23);
@@ -337,10 +293,56 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(&h_full[b]);
       if (it == 4 && threadIdx.x == 64) SB_T(16);
-      // ---- final pass of the previous tile (its temporal taps ran on the tensor pipe during this mid pass)
-      if (it > 0) final_pass(it - 1);
     }
-    if (my_tiles > 0) final_pass(my_tiles - 1);
+  } else if (warp < 2 + kSbEpiWarps) {
+    // ===================== final group (8 warps): RD + b2 -> ReLU -> bf16 -> staging tile (aliases H0) =====================
+    const int lane_grp = warp & 3;
+    const int half = (warp - 2 - kSbEpiWarps / 2) >> 2;
+    const int i_row = lane_grp * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
+    const bool probe_thread = threadIdx.x == 32 * (2 + kSbEpiWarps / 2);
+    (void)probe_thread;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int b = it & 1;
+      if (it == 4 && probe_thread) SB_T(17);
+      mbar_wait(&d3_full[b], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      if (it == 4 && probe_thread) SB_T(18);
+      uint8_t* stage = s_h + (size_t)b * kSbHBytes + 1024;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint32_t a[32];
+        tmem_ld16(tmem_base + lane_off + (uint32_t)(256 + b * 128 + j * 64 + half * 32), a);
+        tmem_ld16(tmem_base + lane_off + (uint32_t)(256 + b * 128 + j * 64 + half * 32 + 16), a + 16);
+        tmem_ld_wait();
+        if (j == 1) {                                      // both accumulator tiles are in registers / already staged
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[b]);
+        }
+        const int h = 128 * j + i_row;
+        const int v = h / kSbL, l = h - v * kSbL;
+        if (v < V && l >= 1 && l <= p.lo) {
+          const int srow = v * p.lo + l - 1;
+          const float* bias = s_bias2 + v * kSbCout + half * 32;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * q);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * q + 4);
+            uint4 u;
+            u.x = pack_bf16x2_relu(__uint_as_float(a[8 * q + 0]) + b0.x, __uint_as_float(a[8 * q + 1]) + b0.y);
+            u.y = pack_bf16x2_relu(__uint_as_float(a[8 * q + 2]) + b0.z, __uint_as_float(a[8 * q + 3]) + b0.w);
+            u.z = pack_bf16x2_relu(__uint_as_float(a[8 * q + 4]) + b1.x, __uint_as_float(a[8 * q + 5]) + b1.y);
+            u.w = pack_bf16x2_relu(__uint_as_float(a[8 * q + 6]) + b1.z, __uint_as_float(a[8 * q + 7]) + b1.w);
+            *reinterpret_cast<uint4*>(stage + (size_t)srow * 128 + (((half * 4 + q) ^ (srow & 7)) << 4)) = u;
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&stage_full[b]);
+      if (it == 4 && probe_thread) SB_T(19);
+    }
   } else {
     // ===================== builders: raw keypoints -> one K=16 operand slice per tile row =====================
     // Raw frames arrive through 4-byte cp.async copies two tiles ahead (the 204-byte frames are not 16-byte aligned,

@@ -68,6 +68,9 @@ struct UmmaParams {
   int32_t act; float slope;
   int32_t res_kind; const void* res; const float* res_w; int32_t res_cin, res_t_mul, res_t_in;
   void* out; int32_t out_layout;
+  int32_t ts;                      // weights stationary in tensor memory (rowgemm_ts_kernel)
+  const __nv_bfloat16* w_gmem;     // ts: (c_out, ktot) row-major weights
+  int32_t ktot;
   unsigned long long* dbg_times;   // probe hook: clock64 timeline of CTA 0 (tools/umma_probe.py)
   int32_t dbg_flags;               // probe hook: 1 skip epilogue body, 2 skip residual, 4 skip MMAs, 8 skip A loads
   int32_t dbg_shift_rows, dbg_base_offset_mode;   // experiment hook: A operand read at a row offset (tik_debug_set_umma_shift)
@@ -393,6 +396,207 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
   if (threadIdx.x == 64) TIK_T(10);
 }
 
+// ------------------------------------------------------------------------------------------------ weight-stationary variant
+// Same implicit GEMM computed TRANSPOSED with the weights as the tensor-memory-resident A operand:
+//
+//   D^T[c_out (TMEM lanes), tile rows (TMEM columns)] = W[c_out x K] (TMEM) . A_tile[rows x K]^T (shared memory)
+//
+// The SS form above reads a 128 x 16 weight slice from shared memory for every MMA (and streams the weights through
+// the ring again for every tile when they do not fit beside it); at N <= 128 that operand traffic, not the tensor
+// pipe, is what saturates the 128 B/clk shared-memory port.  Here the weights are written to tensor memory once per
+// CTA (c_out <= 128 lanes x K/2 columns, bf16 pairs) and only the activation tile is read from shared memory.
+// The accumulator comes out channel-major (lane = output channel, column = tile row), so the epilogue adds a
+// per-lane bias and transposes through the swizzled staging tile with 2-byte stores (one 64-byte run per warp
+// instruction).  Eligible: c_out == 128 (at 64 the padded lanes cost more than the saved weight reads), K <= 512,
+// per-channel bias, node-major TMA-stored output.
+template <int ACT>
+__global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_ts_kernel(const __grid_constant__ UmmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = smem + p.off_ring;
+  uint8_t* s_stage = smem + p.off_stage;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;             // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                     // [2]
+  uint64_t* w_full = tmem_empty + 2;                        // unused here
+  uint64_t* stage_full = w_full + 1;                        // [2]
+  uint64_t* stage_empty = stage_full + 2;                   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stages = p.stages, group = p.group, total_chunks = p.total_chunks;
+  const int stage_bytes = group * kABytes;
+  const int n_tiles = (int)p.tiles_m;
+  const int regions = p.c_out / 64;                         // 64-channel staging regions
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.n_slabs; ++s) tma_prefetch_desc(&p.map_a[s]);
+    tma_prefetch_desc(&p.map_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&stage_full[i], kEpiWarps); mbar_init(&stage_empty[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_w = tmem_base;                        // K/2 columns of bf16 pairs, lane = output channel
+  const uint32_t tmem_acc = tmem_base + 256;                // 2 x 128 fp32 columns
+  // ---- weights -> tensor memory (once per CTA): warps 2-5 cover the 128 lanes
+  if (warp >= 2 && warp < 6) {
+    const int co = (warp & 3) * 32 + lane;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint4* wrow = reinterpret_cast<const uint4*>(p.w_gmem + (size_t)(co < p.c_out ? co : 0) * p.ktot);
+    for (int k8 = 0; k8 < p.ktot / 16; ++k8) {              // 16 bf16 = 8 packed columns per store
+      uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+      if (co < p.c_out) { v0 = __ldg(wrow + 2 * k8); v1 = __ldg(wrow + 2 * k8 + 1); }
+      const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      tmem_st8(tmem_w + lane_off + (uint32_t)(8 * k8), r);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 0) {
+    // ===================== TMA producer: activation chunks only =====================
+    const bool leader = lane == 0;
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int tile_nv = tile / p.tiles_t;
+      const int t0 = (tile - tile_nv * p.tiles_t) * p.tt;
+      const int nv0 = tile_nv * p.vv;
+      int kw = 0, j = 0;
+      for (int s = 0; s < p.n_slabs; ++s) {
+        const int ts = t0 * p.t_mul[s] + p.t_off[s];
+        const int nc = p.chunks[s];
+        for (int c = 0; c < nc; ++c, ++kw) {
+          if (j == 0) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (leader) mbar_expect_tx(&full_bar[stage], (uint32_t)p.a_box_bytes * (uint32_t)min(group, total_chunks - kw));
+          }
+          if (leader) tma_load_3d(ring + (size_t)stage * stage_bytes + (size_t)j * kABytes, &p.map_a[s], &full_bar[stage], c * kChunkK, ts, nv0);
+          __syncwarp();
+          if (++j == group || kw + 1 == total_chunks) {
+            j = 0;
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(128, kTileM);   // M = 128 channel lanes (zero rows beyond c_out), N = tile rows
+    const bool leader = lane == 0;
+    const uint32_t ring_u32 = smem_u32(ring);
+    const uint64_t desc_hi = make_smem_desc_kmajor_sw128(0);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_acc + (uint32_t)(acc * kTileM);
+      for (int kc = 0; kc < total_chunks; kc += group) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const int in_stage = min(group, total_chunks - kc);
+        for (int j = 0; j < in_stage; ++j) {
+          const uint32_t sa = ring_u32 + (uint32_t)stage * (uint32_t)stage_bytes + (uint32_t)j * (uint32_t)kABytes;
+          const uint64_t db = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
+          if (leader) {
+#pragma unroll
+            for (int k = 0; k < kChunkK / 16; ++k)
+              umma_bf16_ts(tmem_d, tmem_w + (uint32_t)((kc + j) * 32 + k * 8), db + (uint64_t)(2 * k), idesc, (kc | j | k) != 0 ? 1u : 0u);
+          }
+        }
+        if (leader) umma_commit(&empty_bar[stage]);
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+      if (leader) umma_commit(&tmem_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp == 2 + kEpiWarps) {
+    // ===================== TMA-store warp =====================
+    if (lane == 0) {
+      int sbuf = 0; uint32_t sphase = 0;
+      int prev = -1;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int tile_nv = tile / p.tiles_t, tile_t = tile - tile_nv * p.tiles_t;
+        mbar_wait(&stage_full[sbuf], sphase);
+        for (int c = 0; c < regions; ++c)
+          tma_store_3d(&p.map_out, s_stage + ((size_t)sbuf * regions + c) * kABytes, c * 64, tile_t * p.tt, tile_nv * p.vv);
+        tma_store_commit();
+        if (p.stage_bufs == 2) {
+          tma_store_wait_read1();
+          if (prev >= 0) mbar_arrive(&stage_empty[prev]);
+          prev = sbuf;
+          if (++sbuf == 2) { sbuf = 0; sphase ^= 1; }
+        } else {
+          tma_store_wait_read0();
+          mbar_arrive(&stage_empty[0]);
+          sphase ^= 1;
+        }
+      }
+      tma_store_wait0();
+    }
+  } else {
+    // ===================== epilogue: 16 warps = TMEM lane group (channels) x 32-row quarter =====================
+    const int lane_grp = warp & 3;
+    const int rq = (warp - 2) >> 2;                         // tile rows [32*rq, +32)
+    const int co = lane_grp * 32 + lane;                    // output channel == TMEM lane
+    const bool co_ok = co < p.c_out;
+    const float bias = co_ok ? __ldg(p.bias + co) : 0.f;
+    const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
+    // this channel's 2-byte slot inside a staging row: region (co/64), 16-byte piece (co%64)/8 (XOR row&7), element co%8
+    const uint32_t col_base = (uint32_t)(co >> 6) * kABytes + (uint32_t)(co & 7) * 2u;
+    const uint32_t piece = (uint32_t)(co & 63) >> 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    int sbuf = 0; uint32_t sphase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      uint32_t a[32];
+      tmem_ld32(tmem_acc + lane_off + (uint32_t)(acc * kTileM + rq * 32), a);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      mbar_wait(&stage_empty[sbuf], sphase ^ 1);
+      if (co_ok) {
+        uint8_t* st = s_stage + (size_t)sbuf * regions * kABytes + col_base;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int r = rq * 32 + i;
+          float v = __uint_as_float(a[i]) + bias;
+          if (ACT == TIK_ACT_RELU) v = fmaxf(v, 0.f);
+          if (ACT == TIK_ACT_LEAKY) v = v > 0.f ? v : v * p.slope;
+          *reinterpret_cast<__nv_bfloat16*>(st + (size_t)r * 128 + ((piece ^ (uint32_t)(r & 7)) << 4)) = __float2bfloat16_rn(v);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&stage_full[sbuf]);
+      if (p.stage_bufs == 2) { if (++sbuf == 2) { sbuf = 0; sphase ^= 1; } } else { sphase ^= 1; }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -552,12 +756,29 @@ int umma_prepare(const TikRowGemm* d, int64_t nv_capacity, UmmaPrepared** out) {
       if (score < best_score) { best_score = score; w_res = wres; sbufs = sb; group = g; stages = st; }
     }
   }
+  // Weight-stationary kernel (weights in tensor memory, see rowgemm_ts_kernel): the whole ring is activations.
+  p.ts = (p.tma_store && d->c_out == 128 && ktot <= 512 && !d->bias_per_node && d->res_kind == TIK_RES_NONE && !getenv("TIK_NO_TS")) ? 1 : 0;
+  if (p.ts) {
+    best_score = INT32_MAX;
+    for (int sb = 2; sb >= 1; --sb) {
+      const int fit = (kSmemBudget - bar_bytes - bias_bytes - sb * one_stage_tile) / kABytes;
+      for (int g = 4; g >= 1; g >>= 1) {
+        if (env_g && g != atoi(env_g)) continue;
+        if (g > 1 && g > p.total_chunks) continue;
+        int st = fit / g;
+        if (st < 2) continue;
+        if (st > kMaxStages) st = kMaxStages;
+        const int score = ((p.total_chunks + g - 1) / g) * 400 + 24000 / std::min(st * g, 8) + (sb == 2 ? 0 : 100);
+        if (score < best_score) { best_score = score; w_res = 1; sbufs = sb; group = g; stages = st; }
+      }
+    }
+  }
   p.group = group;
   p.stage_bufs = sbufs;
   const int stage_out_bytes = sbufs * one_stage_tile;
   if (stages < 2) { delete u; set_error("bf16 path: bias table too large for shared memory"); return TIK_ERR_UNSUPPORTED; }
   p.w_resident = w_res; p.stages = stages;
-  p.off_ring = w_res ? w_bytes : 0;
+  p.off_ring = (w_res && !p.ts) ? w_bytes : 0;
   p.off_stage = p.off_ring + stages * group * (kABytes + (w_res ? 0 : b_bytes));
   p.off_bias = p.off_stage + stage_out_bytes;
   p.off_bar = p.off_bias + bias_bytes;
@@ -570,6 +791,7 @@ int umma_prepare(const TikRowGemm* d, int64_t nv_capacity, UmmaPrepared** out) {
     if (rc != TIK_OK) { delete u; return rc; }
   }
   p.bias_rows = bias_rows;
+  p.w_gmem = reinterpret_cast<const __nv_bfloat16*>(d->w_dev); p.ktot = ktot;
   u->smem_bytes = p.off_bar + bar_bytes + 1024;
   u->nv_capacity = nv_capacity;
   *out = u;
@@ -601,6 +823,23 @@ int umma_launch(UmmaPrepared* u, const TikRowGemm* d, cudaStream_t s) {
     if (d->act == TIK_ACT_LEAKY) return launch_variant<BN_, TIK_ACT_LEAKY>(p, u->smem_bytes, grid, s);  \
     return launch_variant<BN_, TIK_ACT_NONE>(p, u->smem_bytes, grid, s);                              \
   } while (0)
+  if (p.ts) {
+    static int ts_attr[64] = {};
+    int dev = 0;
+    TIK_CUDA(cudaGetDevice(&dev));
+    if (!ts_attr[dev & 63]) {
+      TIK_CUDA(cudaFuncSetAttribute(rowgemm_ts_kernel<TIK_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048));
+      TIK_CUDA(cudaFuncSetAttribute(rowgemm_ts_kernel<TIK_ACT_LEAKY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048));
+      TIK_CUDA(cudaFuncSetAttribute(rowgemm_ts_kernel<TIK_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048));
+      ts_attr[dev & 63] = 1;
+    }
+    TIK_CHECK_ARG(d->res_kind == TIK_RES_NONE && !d->bias_per_node, "weight-stationary kernel: residual / per-node bias changed after prepare");
+    if (d->act == TIK_ACT_RELU) rowgemm_ts_kernel<TIK_ACT_RELU><<<grid, kUmmaThreads, u->smem_bytes, s>>>(p);
+    else if (d->act == TIK_ACT_LEAKY) rowgemm_ts_kernel<TIK_ACT_LEAKY><<<grid, kUmmaThreads, u->smem_bytes, s>>>(p);
+    else rowgemm_ts_kernel<TIK_ACT_NONE><<<grid, kUmmaThreads, u->smem_bytes, s>>>(p);
+    TIK_LAUNCH_CHECK();
+    return TIK_OK;
+  }
   if (u->bn == 64) TIK_LAUNCH_BN(64);
   if (u->bn == 128) TIK_LAUNCH_BN(128);
   TIK_LAUNCH_BN(256);
