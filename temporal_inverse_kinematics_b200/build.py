@@ -25,6 +25,8 @@ STAMP = os.path.join(HERE, "build", "flavour.txt")
 
 
 def _flavour():
+    if os.environ.get("TIK_TEST_WAIT") == "1":
+        return "probe-testwait" if os.environ.get("TIK_PROBE") == "1" else "testwait"
     return "probe" if os.environ.get("TIK_PROBE") == "1" else "release"
 
 
@@ -52,6 +54,8 @@ def build(force=False, verbose=False):
         flags += ["-Xptxas", "-v"]
     if os.environ.get("TIK_PROBE") == "1":          # in-kernel clock64 probes for tools/umma_probe.py
         flags += ["-DTIK_PROBE"]
+    if os.environ.get("TIK_TEST_WAIT") == "1":      # experiment: spin on mbarrier.test_wait instead of try_wait
+        flags += ["-DTIK_TEST_WAIT"]
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for s in SOURCES:

@@ -479,9 +479,13 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_ts_kernel(const __gri
         for (int c = 0; c < nc; ++c, ++kw) {
           if (j == 0) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (leader) mbar_expect_tx(&full_bar[stage], (uint32_t)p.a_box_bytes * (uint32_t)min(group, total_chunks - kw));
+            if (leader) {
+              if (TIK_PROBE_ONLY((p.dbg_flags & 8) != 0)) mbar_arrive(&full_bar[stage]);
+              else mbar_expect_tx(&full_bar[stage], (uint32_t)p.a_box_bytes * (uint32_t)min(group, total_chunks - kw));
+            }
           }
-          if (leader) tma_load_3d(ring + (size_t)stage * stage_bytes + (size_t)j * kABytes, &p.map_a[s], &full_bar[stage], c * kChunkK, ts, nv0);
+          if (leader && !TIK_PROBE_ONLY((p.dbg_flags & 8) != 0))
+            tma_load_3d(ring + (size_t)stage * stage_bytes + (size_t)j * kABytes, &p.map_a[s], &full_bar[stage], c * kChunkK, ts, nv0);
           __syncwarp();
           if (++j == group || kw + 1 == total_chunks) {
             j = 0;
@@ -492,32 +496,51 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_ts_kernel(const __gri
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // The state of the NEXT barrier this thread will need (next ring stage, or the next tile's accumulator) is
+    // polled with a non-blocking test_wait before the current stage's MMAs are issued, so the poll's round trip
+    // overlaps the issue; in steady state the blocking wait is never entered.
     constexpr uint32_t idesc = make_idesc_bf16(128, kTileM);   // M = 128 channel lanes (zero rows beyond c_out), N = tile rows
     const bool leader = lane == 0;
     const uint32_t ring_u32 = smem_u32(ring);
     const uint64_t desc_hi = make_smem_desc_kmajor_sw128(0);
+    const int stages_per_tile = (total_chunks + group - 1) / group;
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
+    bool full_ready = false, acc_ready = false;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      if (!acc_ready) mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
+      const bool last_tile = tile + (int)gridDim.x >= n_tiles;
       const uint32_t tmem_d = tmem_acc + (uint32_t)(acc * kTileM);
-      for (int kc = 0; kc < total_chunks; kc += group) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
+      int sidx = 0;
+      for (int kc = 0; kc < total_chunks; kc += group, ++sidx) {
+        if (!full_ready) mbar_wait(&full_bar[stage], phase);
+        if (!TIK_PROBE_ONLY((p.dbg_flags & 32) != 0)) tc_fence_after();
+        int nstage = stage + 1; uint32_t nphase = phase;
+        if (nstage == stages) { nstage = 0; nphase ^= 1; }
+        const bool last_stage = sidx + 1 == stages_per_tile;
+        // early polls for what comes next
+        const bool poll_full = !(last_stage && last_tile);
+        bool nfull = false, nacc = false;
+        if (poll_full) nfull = mbar_test_wait(&full_bar[nstage], nphase);
+        if (last_stage && !last_tile) nacc = mbar_test_wait(&tmem_empty[acc ^ 1], (acc == 1 ? acc_phase ^ 1 : acc_phase) ^ 1);
         const int in_stage = min(group, total_chunks - kc);
         for (int j = 0; j < in_stage; ++j) {
           const uint32_t sa = ring_u32 + (uint32_t)stage * (uint32_t)stage_bytes + (uint32_t)j * (uint32_t)kABytes;
           const uint64_t db = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
-          if (leader) {
+          if (leader && !TIK_PROBE_ONLY((p.dbg_flags & 4) != 0)) {
 #pragma unroll
             for (int k = 0; k < kChunkK / 16; ++k)
               umma_bf16_ts(tmem_d, tmem_w + (uint32_t)((kc + j) * 32 + k * 8), db + (uint64_t)(2 * k), idesc, (kc | j | k) != 0 ? 1u : 0u);
           }
         }
-        if (leader) umma_commit(&empty_bar[stage]);
+        if (leader) {
+          if (TIK_PROBE_ONLY((p.dbg_flags & 64) != 0)) mbar_arrive(&empty_bar[stage]);   // experiment: cost of tcgen05.commit
+          else umma_commit(&empty_bar[stage]);
+        }
         __syncwarp();
-        if (++stage == stages) { stage = 0; phase ^= 1; }
+        stage = nstage; phase = nphase;
+        full_ready = nfull; acc_ready = nacc;
       }
       if (leader) umma_commit(&tmem_full[acc]);
       __syncwarp();
@@ -531,7 +554,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_ts_kernel(const __gri
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int tile_nv = tile / p.tiles_t, tile_t = tile - tile_nv * p.tiles_t;
         mbar_wait(&stage_full[sbuf], sphase);
-        for (int c = 0; c < regions; ++c)
+        for (int c = 0; c < (TIK_PROBE_ONLY((p.dbg_flags & 16) != 0) ? 0 : regions); ++c)
           tma_store_3d(&p.map_out, s_stage + ((size_t)sbuf * regions + c) * kABytes, c * 64, tile_t * p.tt, tile_nv * p.vv);
         tma_store_commit();
         if (p.stage_bufs == 2) {
@@ -570,7 +593,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_ts_kernel(const __gri
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       mbar_wait(&stage_empty[sbuf], sphase ^ 1);
-      if (co_ok) {
+      if (co_ok && !TIK_PROBE_ONLY((p.dbg_flags & 1) != 0)) {
         uint8_t* st = s_stage + (size_t)sbuf * regions * kABytes + col_base;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {

@@ -142,7 +142,34 @@ def grp():
     os.environ.pop("TIK_UMMA_OPT", None)
 
 
+def tsflags():
+    """Weight-stationary temporal conv at whole-batch size with parts switched off (probe build)."""
+    V, n = 17, 4096
+    g = torch.Generator(device="cuda").manual_seed(0)
+    nv = n * V
+    h = torch.randn(nv, 32, 128, device="cuda", generator=g).bfloat16()
+    x = torch.randn(nv, 32, 128, device="cuda", generator=g).bfloat16()
+    slabs = [(h, 1, -1), (h, 1, 0), (h, 1, 1), (x, 1, 0)]
+    w = (torch.randn(128, 512, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.zeros(1, 128, device="cuda")
+    lib = _lib.lib()
+    for grp_ in ("", "1", "2"):
+        if grp_:
+            os.environ["TIK_UMMA_GROUP"] = grp_
+        res = []
+        for flags in (0, 1 | 4 | 8 | 16, 1 | 4 | 8 | 16 | 64):
+            lib.tik_debug_set_umma_shift(0, flags << 8)
+            us = bench(lambda: ops.rowgemm(slabs, w, b, nv, V, 32, act="relu"), reps=5)
+            res.append(f"f{flags}: {us:6.1f}")
+        lib.tik_debug_set_umma_shift(0, 0)
+        print(f"ts b3 tcn G={grp_ or 'auto'}: " + " | ".join(res), flush=True)
+    os.environ.pop("TIK_UMMA_GROUP", None)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "tsflags":
+        tsflags()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "grp":
         grp()
         sys.exit(0)
