@@ -452,11 +452,15 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_ts_kernel(const __gri
     const int co = (warp & 3) * 32 + lane;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const uint4* wrow = reinterpret_cast<const uint4*>(p.w_gmem + (size_t)(co < p.c_out ? co : 0) * p.ktot);
-    for (int k8 = 0; k8 < p.ktot / 16; ++k8) {              // 16 bf16 = 8 packed columns per store
-      uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-      if (co < p.c_out) { v0 = __ldg(wrow + 2 * k8); v1 = __ldg(wrow + 2 * k8 + 1); }
-      const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-      tmem_st8(tmem_w + lane_off + (uint32_t)(8 * k8), r);
+    for (int k8 = 0; k8 < p.ktot / 16; k8 += 4) {           // 16 bf16 = 8 packed columns per store; 4 stores per batch of loads
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = co < p.c_out ? __ldg(wrow + 2 * k8 + u) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t r[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w, v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
+        tmem_st8(tmem_w + lane_off + (uint32_t)(8 * (k8 + u)), r);
+      }
     }
     tmem_st_wait();
   }

@@ -202,3 +202,41 @@ def test_window_mean_matches_reference_loop():
     want = np.array([np.mean(np.array(l), axis=0) for l in lists])
     assert np.abs(window_mean(preds, hw).cpu().numpy() - want).max() < 1e-6
     assert torch.equal(window_mean(preds, 0), preds[:, 0])
+
+
+@pytest.mark.parametrize("win,offset,stride", [(9, -4, 1), (64, -32, 5), (30, 0, 2)])
+def test_bf16_forward_windows_equals_materialised_windows(win, offset, stride):
+    """Window mode of the fused first-block kernel (frames gathered from the resident sequence with edge clamping and
+    root-centring inside the kernel) vs the same kernel fed materialised windows.  The two differ only in where the
+    root is subtracted (before vs inside the folded data_bn + aggregation), i.e. by fp32 rounding ahead of the bf16
+    hi/lo split."""
+    m, sd = _model(dtype="bf16")
+    F = 150
+    seq = synth.make_clips(1, F, seed=34)[0]
+    n_windows = F if offset < 0 else (F - win - offset) // stride + 1
+    idx = (torch.arange(n_windows)[:, None] * stride + torch.arange(win)[None, :] + offset).clamp(0, F - 1)
+    wins = seq[idx]
+    wins = wins - 0.5 * (wins[:, :, 11] + wins[:, :, 12])[:, :, None, :]
+    want = m(wins.cuda())["poses"]
+    got = m.forward_windows(seq.cuda(), win, offset=offset, stride=stride, root=(11, 12), n_windows=n_windows)["poses"]
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) < 0.03
+    ref = sp.regressor_forward(sd, wins)["poses"]
+    assert float((got.cpu() - ref).abs().max()) < TOL_BF16_ABS
+
+
+@pytest.mark.parametrize("switch", ["TIK_NO_STEM_BLOCK", "TIK_NO_TS", "TIK_NO_FUSED_GCN"])
+def test_bf16_kernel_variants_agree(monkeypatch, switch):
+    """Every specialised tensor-core kernel has a more general one behind it (first block: stem + temporal conv;
+    weight-stationary temporal conv: SS-mode kernel; fused graph conv: aggregate + channel GEMM).  Both routes must
+    meet the stated bf16 tolerance against the oracle and stay close to each other."""
+    x = synth.make_clips(6, 40, seed=21)
+    m, sd = _model(dtype="bf16")
+    fast = m(x.cuda())["poses"].cpu()
+    monkeypatch.setenv(switch, "1")
+    m2, _ = _model(dtype="bf16")                                      # plans are built at first use: new model, new plan
+    slow = m2(x.cuda())["poses"].cpu()
+    want = sp.regressor_forward(sd, x)["poses"]
+    assert float((fast - want).abs().max()) < TOL_BF16_ABS
+    assert float((slow - want).abs().max()) < TOL_BF16_ABS
+    assert float((fast - slow).abs().max()) < 0.06
