@@ -48,8 +48,9 @@ constexpr int kSbOffWt = kSbOffW16 + kSbTile;       // 3 taps x (64 rows x 64 K)
 constexpr int kSbOffA0 = kSbOffWt + 3 * 8192;       // 2 buffers x 2 MMA tiles
 constexpr int kSbOffH = kSbOffA0 + 4 * kSbTile;     // 2 buffers
 constexpr int kSbOffBias1 = kSbOffH + 2 * kSbHBytes;
-constexpr int kSbOffBias2 = kSbOffBias1 + kSbMaxV * kSbCout * 4;
-constexpr int kSbOffAs = kSbOffBias2 + kSbMaxV * kSbCout * 4;           // As[u][v][c] = A^[u,v] * s0[u,c]   (V*V*Cin fp32)
+constexpr int kSbBiasLd = kSbCout + 4;               // padded pitch: rows of different nodes start in different banks
+constexpr int kSbOffBias2 = kSbOffBias1 + kSbMaxV * kSbBiasLd * 4;
+constexpr int kSbOffAs = kSbOffBias2 + kSbMaxV * kSbBiasLd * 4;           // As[u][v][c] = A^[u,v] * s0[u,c]   (V*V*Cin fp32)
 constexpr int kSbOffNbr = kSbOffAs + kSbMaxV * kSbMaxV * 4 * 4;           // per node: count + source-node offsets of the non-zero A^[u,v]
 constexpr int kSbOffCst = kSbOffNbr + kSbMaxV * (kSbMaxV + 1) * 4;         // cst[v][c] = sum_u A^[u,v] o0[u,c]; sum[v][c] = sum_u As; scale[v][c]
 constexpr int kSbRawBufs = 3;                                           // raw keypoint tiles in flight (cp.async)
@@ -123,8 +124,9 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
   for (int i = threadIdx.x; i < V * kSbCout; i += kSbThreads) {
-    s_bias1[i] = __ldg(p.bias1 + i);
-    s_bias2[i] = __ldg(p.bias2 + (p.bias2_per_node ? i : (i % kSbCout)));
+    const int bi = (i / kSbCout) * kSbBiasLd + (i % kSbCout);
+    s_bias1[bi] = __ldg(p.bias1 + i);
+    s_bias2[bi] = __ldg(p.bias2 + (p.bias2_per_node ? i : (i % kSbCout)));
   }
   // data_bn folded into the aggregation:  sum_u A^[u,v] (s0[u,c] x[u,c] + o0[u,c]) = sum_u As[v,u,c] x[u,c] + cst[v,c]
   // and only the non-zero adjacency entries are visited (the skeleton graph is sparse): compacted per target node v
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
         const int v = h / kSbL, l = h - v * kSbL;
         const int t = t_first + l;
         const bool ok = v < V && t >= 0 && t < p.T;
-        const float* bias = s_bias1 + (v < V ? v : 0) * kSbCout + half * 32;
+        const float* bias = s_bias1 + (v < V ? v : 0) * kSbBiasLd + half * 32;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * q);
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
         const int v = h / kSbL, l = h - v * kSbL;
         if (v < V && l >= 1 && l <= p.lo) {
           const int srow = v * p.lo + l - 1;
-          const float* bias = s_bias2 + v * kSbCout + half * 32;
+          const float* bias = s_bias2 + v * kSbBiasLd + half * 32;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * q);

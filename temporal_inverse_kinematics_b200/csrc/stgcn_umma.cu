@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
-  for (int i = threadIdx.x; i < p.bias_rows * p.c_out; i += kUmmaThreads) s_bias[i] = __ldg(p.bias + i);
+  // per-node tables are stored with a 4-float pad per row (rows c_out*4 bytes apart would share their first bank)
+  for (int i = threadIdx.x; i < p.bias_rows * p.c_out; i += kUmmaThreads) s_bias[(i / p.c_out) * (p.c_out + 4) + (i % p.c_out)] = __ldg(p.bias + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
       const int n = nv / p.v, node = nv - n * p.v;
       const int64_t row = (int64_t)nv * p.t_out + t;
       const int cb = cq * CW;                    // first column (within the tile) this thread handles
-      const float* bias = s_bias + (p.bias_per_node ? node * p.c_out : 0) + n0 + cb;
+      const float* bias = s_bias + (p.bias_per_node ? node * (p.c_out + 4) : 0) + n0 + cb;
       const __nv_bfloat16* res_row = (valid && use_res) ? reinterpret_cast<const __nv_bfloat16*>(p.res) + row * p.c_out + n0 + cb : nullptr;
       int64_t out_off;
       if (p.out_layout == TIK_OUT_NODE_MAJOR) out_off = row * p.c_out + n0 + cb;
@@ -746,7 +747,7 @@ int umma_prepare(const TikRowGemm* d, int64_t nv_capacity, UmmaPrepared** out) {
   // shared-memory plan: [resident W][ring][bias][barriers]
   const int b_bytes = u->bn * kChunkK * 2;
   const int bias_rows = d->bias_per_node ? d->v : 1;
-  const int bias_bytes = (int)align_up_i(bias_rows * d->c_out * 4, 16);
+  const int bias_bytes = (int)align_up_i(bias_rows * (d->c_out + 4) * 4, 16);
   const int bar_bytes = 256;
   const int w_bytes = p.total_chunks * b_bytes;
   p.tma_store = (d->out_layout == TIK_OUT_NODE_MAJOR && d->out_dev != nullptr) ? 1 : 0;
