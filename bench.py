@@ -28,6 +28,25 @@ UNIT = "frames/s"
 CPU_SAMPLE_CLIPS = 256
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner there when NCCL_DEBUG is
+    set) must not interleave with it: keep a private handle on the real stdout and point fd 1 at stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -135,7 +154,7 @@ def run_reference(args):
             "config": {"workload": f"configs[2]: B={B_PER_GPU} clips/GPU, T={T_FRAMES}, ST-GCN fwd + 22-joint FK", "sample": sample},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def run_ours(args):
@@ -287,7 +306,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{CPU_SAMPLE_CLIPS} of the {B} clips (T={T}), 3 iterations, oracle port of the "
                                               f"reference PyTorch modules + numpy FK; {sec:.2f} s/iteration"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -304,6 +323,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying a CUDA graph")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
