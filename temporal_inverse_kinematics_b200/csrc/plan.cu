@@ -30,9 +30,10 @@ static int out_frames(int t, int stride) { return (t - 1) / stride + 1; }
 static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 struct Step {
-  enum Kind { STEM = 0, AGG = 1, GEMM = 2, FUSED_GCN = 3, STEM_BLOCK = 4 } kind;
+  enum Kind { STEM = 0, AGG = 1, GEMM = 2, FUSED_GCN = 3, STEM_BLOCK = 4, TCN_HALO = 5 } kind;
   GcnFusedPrepared* fused = nullptr;
   StemBlockPrepared* stem_block = nullptr;
+  TcnHaloPrepared* halo = nullptr;
   double fused_flops_per_clip = 0;
   TikRowGemm g;               // GEMM
   UmmaPrepared* prep = nullptr;
@@ -65,6 +66,7 @@ struct TikPlan {
         if (s.prep) tik::umma_free(s.prep);
         if (s.fused) tik::gcn_fused_free(s.fused);
         if (s.stem_block) tik::stem_block_free(s.stem_block);
+        if (s.halo) tik::tcn_halo_free(s.halo);
       }
   }
 };
@@ -153,6 +155,7 @@ static int run_step(TikPlan* P, Step& st, const float* xc, int64_t n, int64_t cl
   }
   if (st.kind == Step::FUSED_GCN) return gcn_fused_launch(st.fused, n, s);
   if (st.kind == Step::STEM_BLOCK) return stem_block_launch(st.stem_block, xc, n, win, win_n0, s);
+  if (st.kind == Step::TCN_HALO) return tcn_halo_launch(st.halo, n * V, s);
   TikRowGemm g = st.g;
   if (g.v == 1) {             // head: rows = n * T'
     g.t_out = (int32_t)(n * P->T_out);
@@ -323,6 +326,20 @@ int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int64_t
       g.g.out_dev = hbuf; g.g.out_layout = TIK_OUT_NODE_MAJOR;
       P->chunk_steps.push_back(g);
     }
+    if (dtype == TIK_BF16 && !last && b.res_kind == TIK_RES_IDENTITY &&
+        tcn_halo_supported(b.c_in, b.c_out, b.kt, b.stride, t, b.res_as_slab != 0) && getenv("TIK_TCN_HALO")) {
+      // EXPERIMENT (opt-in, TIK_TCN_HALO=1): one halo tile serves all three taps (tcn_halo.cu).  Correct, but its
+      // transposed 2-byte-store epilogue makes it slower than the per-tap kernels today (profiles/r1_notes.md)
+      const int nxt_h = (i == 0) ? 0 : cur ^ 1;
+      Step hs; hs.kind = Step::TCN_HALO; hs.blk = &b; hs.t = t;
+      int rch = tcn_halo_prepare(hbuf, xbuf[cur], b.w_tcn_dev, b.b_tcn_dev, xbuf[nxt_h], nv, t, b.c_out, &hs.halo);
+      if (rch != TIK_OK) { delete P; return rch; }
+      hs.fused_flops_per_clip = 2.0 * V * t * (double)b.c_out * (b.kt * b.c_out);
+      P->chunk_steps.push_back(hs);
+      cur = nxt_h;
+      t = t_o;
+      continue;
+    }
     Step c; c.kind = Step::GEMM; memset(&c.g, 0, sizeof(c.g));
     int ns = 0;
     for (int dt = 0; dt < b.kt; ++dt) c.g.slabs[ns++] = {hbuf, b.c_out, t, b.stride, dt - pad};
@@ -420,17 +437,17 @@ int tik_stgcn_plan_profile(TikPlan* P, const float* x, int64_t N, float* poses, 
     TIK_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
     Step& st = *trace[i].first;
     const int64_t n = trace[i].second;
-    const int kind = (st.kind == Step::FUSED_GCN || st.kind == Step::STEM_BLOCK) ? (int)Step::GEMM : (int)st.kind;   // tensor-core family
+    const int kind = (st.kind == Step::FUSED_GCN || st.kind == Step::STEM_BLOCK || st.kind == Step::TCN_HALO) ? (int)Step::GEMM : (int)st.kind;   // tensor-core family
     ms_by_kind[kind] += ms;
     launches_by_kind[kind] += 1;
     if (getenv("TIK_PLAN_TRACE")) {
-      static const char* names[] = {"stem", "aggregate", "gemm", "fused_gcn", "stem_block"};
+      static const char* names[] = {"stem", "aggregate", "gemm", "fused_gcn", "stem_block", "tcn_halo"};
       int ktot = 0;
       for (int q = 0; q < st.g.n_slabs && st.kind == Step::GEMM; ++q) ktot += st.g.slabs[q].c;
       fprintf(stderr, "tik trace: step %2zu %-9s clips=%lld K=%d c_out=%d t_out=%d  %.1f us\n", i, names[st.kind], (long long)n, ktot,
               st.kind == Step::GEMM ? st.g.c_out : st.c, st.kind == Step::GEMM ? st.g.t_out : st.t, ms * 1e3);
     }
-    if (st.kind == Step::FUSED_GCN || st.kind == Step::STEM_BLOCK) *flops_gemm += st.fused_flops_per_clip * (double)n;
+    if (st.kind == Step::FUSED_GCN || st.kind == Step::STEM_BLOCK || st.kind == Step::TCN_HALO) *flops_gemm += st.fused_flops_per_clip * (double)n;
     if (st.kind == Step::GEMM) {
       double ktot = -st.k_identity;
       for (int q = 0; q < st.g.n_slabs; ++q) ktot += st.g.slabs[q].c;

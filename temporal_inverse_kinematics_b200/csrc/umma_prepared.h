@@ -28,4 +28,11 @@ int64_t stem_block_workspace_bytes();
 int stem_block_prepare(const TikNet* net, void* w16_dev, void* out, int64_t n_clips, int T, StemBlockPrepared** outp);
 int stem_block_launch(StemBlockPrepared* g, const float* x, int64_t n_clips, const TikWindowing* win, int64_t win_n0, cudaStream_t s);
 void stem_block_free(StemBlockPrepared* g);
+struct TcnHaloPrepared;
+// Stride-1 temporal conv + identity residual, weight-stationary, each activation row loaded once; tcn_halo.cu
+bool tcn_halo_supported(int c, int c_out, int kt, int stride, int T, bool identity_slab);
+int tcn_halo_prepare(const void* h, const void* x, const void* w, const float* bias, void* out, int64_t nv_cap, int T, int c,
+                     TcnHaloPrepared** outp);
+int tcn_halo_launch(TcnHaloPrepared* g, int64_t nv, cudaStream_t s);
+void tcn_halo_free(TcnHaloPrepared* g);
 }  // namespace tik

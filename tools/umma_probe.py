@@ -166,7 +166,30 @@ def tsflags():
     os.environ.pop("TIK_UMMA_GROUP", None)
 
 
+def fill():
+    """Is the temporal conv bound by DRAM or by the L2 -> shared-memory fill?  Same K and fill bytes, different
+    numbers of distinct tensors behind the four K slabs."""
+    V, n = 17, 4096
+    g = torch.Generator(device="cuda").manual_seed(0)
+    nv = n * V
+    for (T, C) in ((32, 128), (64, 64)):
+        ts_ = [torch.randn(nv, T, C, device="cuda", generator=g).bfloat16() for _ in range(4)]
+        w = (torch.randn(C, 4 * C, device="cuda", generator=g) * 0.05).bfloat16()
+        b = torch.zeros(1, C, device="cuda")
+        cases = {"3 taps + residual (2 tensors)": [(ts_[0], 1, -1), (ts_[0], 1, 0), (ts_[0], 1, 1), (ts_[1], 1, 0)],
+                 "1 tensor x4 (same tap)": [(ts_[0], 1, 0)] * 4,
+                 "4 distinct tensors": [(ts_[i], 1, 0) for i in range(4)]}
+        for name, slabs in cases.items():
+            us = bench(lambda: ops.rowgemm(slabs, w, b, nv, V, T, act="relu"), reps=8)
+            distinct = len({id(s[0]) for s in slabs})
+            gb = (distinct * nv * T * C * 2 + nv * T * C * 2) / 1e9
+            print(f"T={T} C={C} {name}: {us:6.1f} us  DRAM {gb:.2f} GB -> {gb / us * 1e3:.2f} TB/s; fill {4 * nv * T * C * 2 / 1e9 / us * 1e3:.2f} TB/s", flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "fill":
+        fill()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "tsflags":
         tsflags()
         sys.exit(0)
