@@ -576,37 +576,59 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_ts_kernel(const __gri
       tma_store_wait0();
     }
   } else {
-    // ===================== epilogue: 16 warps = TMEM lane group (channels) x 32-row quarter =====================
+    // ===================== epilogue: 16 warps = TMEM lane group (32 channels) x 32-row quarter =====================
+    // The accumulator is channel-major.  tcgen05.ld.16x256b hands each thread mma-style fragments (two adjacent tile
+    // rows of one channel per register pair); packed to bf16x2 they are exactly the fragments stmatrix.trans wants,
+    // which writes them transposed: 16-byte pieces of 8 consecutive channels per tile row, at the piece's 128B-swizzle
+    // position (every lane supplies the address of one piece).
     const int lane_grp = warp & 3;
     const int rq = (warp - 2) >> 2;                         // tile rows [32*rq, +32)
-    const int co = lane_grp * 32 + lane;                    // output channel == TMEM lane
-    const bool co_ok = co < p.c_out;
-    const float bias = co_ok ? __ldg(p.bias + co) : 0.f;
-    const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
-    // this channel's 2-byte slot inside a staging row: region (co/64), 16-byte piece (co%64)/8 (XOR row&7), element co%8
-    const uint32_t col_base = (uint32_t)(co >> 6) * kABytes + (uint32_t)(co & 7) * 2u;
-    const uint32_t piece = (uint32_t)(co & 63) >> 3;
+    const bool grp_ok = lane_grp * 32 < p.c_out;
+    float bias[2][2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int co = lane_grp * 32 + 16 * h + 8 * u + (lane >> 2);
+        bias[h][u] = co < p.c_out ? __ldg(p.bias + co) : 0.f;
+      }
+    // stmatrix address role of this lane: matrix i = lane/8 -> rows +8*(i/2), channel piece +(i%2); row k = lane%8
+    const int a_row = ((lane >> 4) & 1) * 8 + (lane & 7);
+    const int a_piece = (lane >> 3) & 1;
     int acc = 0; uint32_t acc_phase = 0;
     int sbuf = 0; uint32_t sphase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      uint32_t a[32];
-      tmem_ld32(tmem_acc + lane_off + (uint32_t)(acc * kTileM + rq * 32), a);
+      uint32_t a[2][16];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        tmem_ld_16x256b_x4(tmem_acc + ((uint32_t)(lane_grp * 32 + 16 * h) << 16) + (uint32_t)(acc * kTileM + rq * 32), a[h]);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       mbar_wait(&stage_empty[sbuf], sphase ^ 1);
-      if (co_ok && !TIK_PROBE_ONLY((p.dbg_flags & 1) != 0)) {
-        uint8_t* st = s_stage + (size_t)sbuf * regions * kABytes + col_base;
+      if (grp_ok && !TIK_PROBE_ONLY((p.dbg_flags & 1) != 0)) {
+        const uint32_t st_u32 = smem_u32(s_stage + (size_t)sbuf * regions * kABytes);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int r = rq * 32 + i;
-          float v = __uint_as_float(a[i]) + bias;
-          if (ACT == TIK_ACT_RELU) v = fmaxf(v, 0.f);
-          if (ACT == TIK_ACT_LEAKY) v = v > 0.f ? v : v * p.slope;
-          *reinterpret_cast<__nv_bfloat16*>(st + (size_t)r * 128 + ((piece ^ (uint32_t)(r & 7)) << 4)) = __float2bfloat16_rn(v);
+        for (int h = 0; h < 2; ++h) {
+          const int co0 = lane_grp * 32 + 16 * h;
+          const uint32_t piece = (uint32_t)(((co0 & 63) >> 3) + a_piece);
+          const uint32_t region = st_u32 + (uint32_t)(co0 >> 6) * kABytes;
+#pragma unroll
+          for (int pr = 0; pr < 2; ++pr) {                  // two 8-row blocks per stmatrix.x4
+            uint32_t m[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {                   // q = 2*(row block) + (channel half)
+              float v0 = __uint_as_float(a[h][8 * pr + 2 * q]) + bias[h][q & 1];
+              float v1 = __uint_as_float(a[h][8 * pr + 2 * q + 1]) + bias[h][q & 1];
+              if (ACT == TIK_ACT_LEAKY) { v0 = v0 > 0.f ? v0 : v0 * p.slope; v1 = v1 > 0.f ? v1 : v1 * p.slope; }
+              m[q] = (ACT == TIK_ACT_RELU) ? pack_bf16x2_relu(v0, v1) : pack_bf16x2(v0, v1);
+            }
+            const int r = rq * 32 + pr * 16 + a_row;
+            stmatrix_x4_trans(region + (uint32_t)r * 128u + ((piece ^ (uint32_t)(r & 7)) << 4), m[0], m[1], m[2], m[3]);
+          }
         }
       }
       fence_proxy_async_smem();
