@@ -327,9 +327,8 @@ int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int64_t
       P->chunk_steps.push_back(g);
     }
     if (dtype == TIK_BF16 && !last && b.res_kind == TIK_RES_IDENTITY &&
-        tcn_halo_supported(b.c_in, b.c_out, b.kt, b.stride, t, b.res_as_slab != 0) && getenv("TIK_TCN_HALO")) {
-      // EXPERIMENT (opt-in, TIK_TCN_HALO=1): one halo tile serves all three taps (tcn_halo.cu).  Correct, but its
-      // transposed 2-byte-store epilogue makes it slower than the per-tap kernels today (profiles/r1_notes.md)
+        tcn_halo_supported(b.c_in, b.c_out, b.kt, b.stride, t, b.res_as_slab != 0) && !getenv("TIK_NO_TCN_HALO")) {
+      // stride-1 block with an identity residual: one halo tile serves all three taps (tcn_halo.cu)
       const int nxt_h = (i == 0) ? 0 : cur ^ 1;
       Step hs; hs.kind = Step::TCN_HALO; hs.blk = &b; hs.t = t;
       int rch = tcn_halo_prepare(hbuf, xbuf[cur], b.w_tcn_dev, b.b_tcn_dev, xbuf[nxt_h], nv, t, b.c_out, &hs.halo);

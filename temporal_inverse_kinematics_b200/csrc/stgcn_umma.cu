@@ -807,7 +807,7 @@ int umma_prepare(const TikRowGemm* d, int64_t nv_capacity, UmmaPrepared** out) {
     }
   }
   // Weight-stationary kernel (weights in tensor memory, see rowgemm_ts_kernel): the whole ring is activations.
-  p.ts = (p.tma_store && d->c_out == 128 && ktot <= 512 && !d->bias_per_node && d->res_kind == TIK_RES_NONE && !getenv("TIK_NO_TS")) ? 1 : 0;
+  p.ts = (p.tma_store && (d->c_out == 128 || d->c_out == 64) && ktot <= 512 && !d->bias_per_node && d->res_kind == TIK_RES_NONE && !getenv("TIK_NO_TS")) ? 1 : 0;
   if (p.ts) {
     best_score = INT32_MAX;
     for (int sb = 2; sb >= 1; --sb) {

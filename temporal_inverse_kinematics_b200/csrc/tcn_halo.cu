@@ -13,10 +13,10 @@
 // memory, N = the tile's rows rounded up to 16; output column n = j*(T+2) + t is valid for t < T.
 // One ring stage = one tile (all of its 64-channel chunks): one barrier hand-off per tile.
 //
-// STATUS: experiment, opt-in with TIK_TCN_HALO=1.  Parity-green, and it halves the L2 -> shared-memory fill, but the
-// channel-major accumulator needs a transposed epilogue; with 2-byte shared-memory stores that epilogue is
-// instruction-bound (b1: 801 vs 410 us, b3: 459 vs 360 us for the per-tap kernels).  Next step: tcgen05.ld.16x256b +
-// stmatrix.trans so the transpose happens in 16-byte pieces.
+// Measured (B=4096): b1 (64 ch, T=64) 410 us (SS, per-tap boxes) -> 324 (TS, per-tap boxes) -> 297 us here; b3/b4
+// (128 ch, T=32) 397 -> 338 -> 288 us = 5.8 TB/s of DRAM traffic, 89 % of the copy peak.  The channel-major accumulator
+// is transposed by the epilogue with tcgen05.ld.16x256b fragments + stmatrix.trans; a first version with 2-byte
+// shared-memory stores was instruction-bound and 2x slower than the kernels it replaces.
 #include <string.h>
 
 #include <algorithm>
@@ -180,45 +180,74 @@ __global__ void __launch_bounds__(kThThreads, 1) tcn_halo_kernel(const __grid_co
       tma_store_wait0();
     }
   } else {
-    // ===================== epilogue: 16 warps = TMEM lane group (channels) x interleaved 16-column chunks =====================
+    // ===================== epilogue: 16 warps = TMEM lane group (32 channels) x interleaved 16-column chunks =====================
+    // Channel-major accumulator -> row-major bf16 staging through tcgen05.ld.16x256b fragments and stmatrix.trans
+    // (see rowgemm_ts_kernel).  Every lane supplies the address of one 16-byte piece; pieces of halo columns go to a
+    // scratch sink.
+    constexpr int kMaxChunks = 3;                           // N <= 192 columns -> at most 3 chunks of 16 per warp
     const int lane_grp = warp & 3;
     const int rq = (warp - 2) >> 2;
-    const int co = lane_grp * 32 + lane;                    // output channel == TMEM lane
-    const bool co_ok = co < p.c_out;
-    const float bias = co_ok ? __ldg(p.bias + co) : 0.f;
-    const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
-    const uint32_t col_base = (uint32_t)(co >> 6) * (uint32_t)p.region_bytes + (uint32_t)(co & 7) * 2u;
-    const uint32_t piece = (uint32_t)(co & 63) >> 3;
+    const bool grp_ok = lane_grp * 32 < p.c_out;
+    float bias[2][2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int co = lane_grp * 32 + 16 * h + 8 * u + (lane >> 2);
+        bias[h][u] = co < p.c_out ? __ldg(p.bias + co) : 0.f;
+      }
+    const int a_col = ((lane >> 4) & 1) * 8 + (lane & 7);   // column inside a 16-column chunk whose piece this lane addresses
+    const int a_piece = (lane >> 3) & 1;
+    const uint32_t sink = smem_u32(smem + p.off_bar + 256) + (uint32_t)lane * 16u;
     const int n_chunks16 = p.N / 16;
     int acc = 0; uint32_t acc_phase = 0;
     int sbuf = 0; uint32_t sphase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      mbar_wait(&stage_empty[sbuf], sphase ^ 1);
-      uint8_t* st = s_stage + (size_t)sbuf * regions * p.region_bytes + col_base;
-      for (int ch = rq; ch < n_chunks16; ch += 4) {
-        uint32_t a[16];
-        tmem_ld16(tmem_acc + lane_off + (uint32_t)(acc * p.acc_stride + ch * 16), a);
-        tmem_ld_wait();
-        int j = (ch * 16) / p.R, t = ch * 16 - j * p.R;     // column n = j*R + t  ->  row group j, frame t
-        if (co_ok) {
+      uint32_t a[kMaxChunks][2][8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (j < p.G && t < p.T) {
-              const int r = j * p.T + t;                    // staging row
-              const float v = fmaxf(__uint_as_float(a[i]) + bias, 0.f);
-              *reinterpret_cast<__nv_bfloat16*>(st + (size_t)r * 128 + ((piece ^ (uint32_t)(r & 7)) << 4)) = __float2bfloat16_rn(v);
+      for (int q = 0; q < kMaxChunks; ++q) {
+        const int ch = rq + 4 * q;
+        if (ch < n_chunks16) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            tmem_ld_16x256b_x2(tmem_acc + ((uint32_t)(lane_grp * 32 + 16 * h) << 16) + (uint32_t)(acc * p.acc_stride + ch * 16), a[q][h]);
+        }
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);          // accumulator is in registers: hand it back right away
+      mbar_wait(&stage_empty[sbuf], sphase ^ 1);
+      if (grp_ok) {
+        const uint32_t st_u32 = smem_u32(s_stage + (size_t)sbuf * regions * p.region_bytes);
+#pragma unroll
+        for (int q = 0; q < kMaxChunks; ++q) {
+          const int ch = rq + 4 * q;
+          if (ch < n_chunks16) {
+            const int n = ch * 16 + a_col;                  // column n = j*R + t  ->  row group j, frame t
+            const int j = n / p.R, t = n - j * p.R;
+            const bool ok = j < p.G && t < p.T;
+            const int r = j * p.T + t;                      // staging row
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int co0 = lane_grp * 32 + 16 * h;
+              const uint32_t piece = (uint32_t)(((co0 & 63) >> 3) + a_piece);
+              uint32_t m[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)                   // u = 2*(8-column block) + (channel half)
+                m[u] = pack_bf16x2_relu(__uint_as_float(a[q][h][2 * u]) + bias[h][u & 1], __uint_as_float(a[q][h][2 * u + 1]) + bias[h][u & 1]);
+              const uint32_t addr = ok ? st_u32 + (uint32_t)(co0 >> 6) * (uint32_t)p.region_bytes + (uint32_t)r * 128u + ((piece ^ (uint32_t)(r & 7)) << 4)
+                                       : sink;
+              stmatrix_x4_trans(addr, m[0], m[1], m[2], m[3]);
             }
-            if (++t == p.R) { t = 0; ++j; }
           }
         }
       }
-      // every chunk of this accumulator has been read by this warp: hand it back, publish the staging tile
-      tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&tmem_empty[acc]); mbar_arrive(&stage_full[sbuf]); }
+      if (lane == 0) mbar_arrive(&stage_full[sbuf]);
       if (p.stage_bufs == 2) { if (++sbuf == 2) { sbuf = 0; sphase ^= 1; } } else { sphase ^= 1; }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -267,12 +296,12 @@ int tcn_halo_prepare(const void* h, const void* x, const void* w, const float* b
   p.region_bytes = (p.G * T * 128 + 1023) / 1024 * 1024;
   const int regions = c / 64;
   p.stage_bufs = 2;
-  p.stages = (kThSmemBudget - 256 - p.stage_bufs * regions * p.region_bytes) / p.stage_bytes;
+  p.stages = (kThSmemBudget - 768 - p.stage_bufs * regions * p.region_bytes) / p.stage_bytes;
   if (p.stages > kThMaxStages) p.stages = kThMaxStages;
   if (p.stages < 2) { delete g; set_error("halo temporal conv: shared-memory plan does not fit"); return TIK_ERR_UNSUPPORTED; }
   p.off_stage = p.stages * p.stage_bytes;
   p.off_bar = p.off_stage + p.stage_bufs * regions * p.region_bytes;
-  g->smem_bytes = p.off_bar + 256 + 1024;
+  g->smem_bytes = p.off_bar + 256 + 512 + 1024;            // barriers, stmatrix sink, alignment slack
   g->nv_cap = nv_cap;
   int rc;
   {

@@ -150,6 +150,11 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* r) 
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
 // Four 8x8 b16 matrices, stored TRANSPOSED: lane 8i+k supplies the address of the 16-byte row that receives column k
 // of matrix i (fragment convention: thread t holds elements (row t/4, columns 2(t%4), +1) of each matrix).
 __device__ __forceinline__ void stmatrix_x4_trans(uint32_t smem_addr, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
