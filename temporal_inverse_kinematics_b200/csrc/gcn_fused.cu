@@ -39,6 +39,7 @@ struct GcnFusedParams {
   int32_t sbufs;                          // staging tiles (2: the store of tile i-1 may still be reading while tile i is staged)
   int32_t off_w, off_x, off_stage, off_bias, off_bar;
   const float* bias;                      // (V, COUT)
+  const __nv_bfloat16* abd;               // (128, 128) row-major block-structured adjacency, copied to tensor memory
   int32_t relu;
 };
 
@@ -46,12 +47,13 @@ template <int CIN, int COUT>
 __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_constant__ GcnFusedParams p) {
   constexpr int KC1 = CIN / 64;                       // 64-channel slabs of the input
   constexpr int KC2 = COUT / 64;
-  constexpr int ND2 = (2 * CIN + 2 * COUT) <= 512 ? 2 : 1;   // D1 is always double buffered, D2 when it fits
-  constexpr int TMEM_NEED = 2 * CIN + ND2 * COUT;
+  // tensor memory: [Abd 64 columns][D1 x ND1, CIN columns each; the bf16 Xagg of a tile overwrites its D1][D2 x ND2]
+  constexpr int ND1 = (64 + 2 * CIN + COUT) <= 512 ? 2 : 1;
+  constexpr int ND2 = (64 + ND1 * CIN + 2 * COUT) <= 512 ? 2 : 1;
+  constexpr int TMEM_NEED = 64 + ND1 * CIN + ND2 * COUT;
   constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* s_abd = smem;                              // 2 slabs (K = 0..63, 64..127) of 128 rows
   uint8_t* s_w = smem + p.off_w;                      // KC1 slabs of COUT rows x 128 B
   uint8_t* s_x = smem + p.off_x;                      // xbufs x KC1 slabs
   uint8_t* s_stage = smem + p.off_stage;              // KC2 slabs
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
   const uint32_t x_bytes = (uint32_t)(KC1 * rows_valid * 128);
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.map_x); tma_prefetch_desc(&p.map_out); tma_prefetch_desc(&p.map_abd); tma_prefetch_desc(&p.map_w);
+    tma_prefetch_desc(&p.map_x); tma_prefetch_desc(&p.map_out); tma_prefetch_desc(&p.map_w);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kGfMaxBufs; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
@@ -100,14 +102,29 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + 2 * CIN;
+  const uint32_t tmem_abd = tmem_base, tmem_d1 = tmem_base + 64, tmem_d2 = tmem_base + 64 + ND1 * CIN;
+  // ---- block-structured adjacency -> tensor memory (once per CTA): the A operand of every aggregation MMA
+  if (warp >= 2 && warp < 6) {
+    const int r = (warp & 3) * 32 + lane;
+    const uint4* arow = reinterpret_cast<const uint4*>(p.abd + (size_t)r * 128);
+    uint4 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = __ldg(arow + u);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t w8[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w, v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
+      tmem_st8(tmem_abd + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(8 * u), w8);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(w_full, (uint32_t)(2 * kGfTile + KC1 * COUT * 128));
-      tma_load_2d(s_abd, &p.map_abd, w_full, 0, 0);
-      tma_load_2d(s_abd + kGfTile, &p.map_abd, w_full, 64, 0);
+      mbar_expect_tx(w_full, (uint32_t)(KC1 * COUT * 128));
       for (int kc = 0; kc < KC1; ++kc) tma_load_2d(s_w + (size_t)kc * COUT * 128, &p.map_w, w_full, kc * 64, 0);
       int b = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -128,16 +145,17 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
     constexpr uint32_t idesc2 = make_idesc_bf16(128, COUT);
     const bool leader = lane == 0;
     mbar_wait(w_full, 0);
-    const uint32_t abd_u32 = smem_u32(s_abd), w_u32 = smem_u32(s_w), x_u32 = smem_u32(s_x);
-    auto issue_mma1 = [&](uint32_t xb, int s) {
+    const uint32_t w_u32 = smem_u32(s_w), x_u32 = smem_u32(s_x);
+    // MMA 1: D1 = Abd (tensor memory) . Xtile (shared memory, MN-major B); the X buffer is free as soon as it has run
+    auto issue_mma1 = [&](uint32_t xb, int s1, int buf) {
       if (leader) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const uint64_t da = make_smem_desc_kmajor_sw128(abd_u32 + (uint32_t)(k >> 2) * kGfTile + (uint32_t)(k & 3) * 32u);
           const uint64_t db = make_smem_desc_mnmajor_sw128(xb + (uint32_t)k * 2048u, (uint32_t)kGfTile);
-          umma_bf16(tmem_d1 + (uint32_t)(s * CIN), da, db, idesc1, k != 0 ? 1u : 0u);
+          umma_bf16_ts(tmem_d1 + (uint32_t)(s1 * CIN), tmem_abd + (uint32_t)(8 * k), db, idesc1, k != 0 ? 1u : 0u);
         }
-        umma_commit(&d1_full[s]);
+        umma_commit(&d1_full[s1]);
+        umma_commit(&x_empty[buf]);
       }
       __syncwarp();
     };
@@ -145,24 +163,23 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
     if (my_tiles > 0) {
       mbar_wait(&x_full[0], 0);
       tc_fence_after();
-      issue_mma1(x_u32, 0);
+      issue_mma1(x_u32, 0, 0);
     }
+    // With two D1 buffers and two X buffers the aggregation MMA of tile it+1 goes out before the channel MMA of tile
+    // it, so the mid group works on tile it+1 while the final group drains tile it.
+    const bool early = ND1 == 2 && p.xbufs >= 2;
     for (int it = 0; it < my_tiles; ++it) {
-      const uint32_t xb = x_u32 + (uint32_t)b * (uint32_t)(KC1 * kGfTile);
-      const int s = it & 1;
-      const int s2 = ND2 == 2 ? s : 0;
+      const int s1 = ND1 == 2 ? (it & 1) : 0;
+      const int s2 = ND2 == 2 ? (it & 1) : 0;
       int nb = b + 1; uint32_t nphase = phase;
       if (nb == p.xbufs) { nb = 0; nphase ^= 1; }
-      // ---- MMA 1 of the NEXT tile: D1[(it+1)&1] was drained by the mid pass of tile it-1 (its xagg_full was waited on).
-      // With a single X buffer the next tile cannot land before this tile's channel MMA has released it.
-      const bool early = p.xbufs >= 2;
       if (early && it + 1 < my_tiles) {
         mbar_wait(&x_full[nb], nphase);
         tc_fence_after();
-        issue_mma1(x_u32 + (uint32_t)nb * (uint32_t)(KC1 * kGfTile), s ^ 1);
+        issue_mma1(x_u32 + (uint32_t)nb * (uint32_t)(KC1 * kGfTile), s1 ^ 1, nb);
       }
-      // ---- MMA 2: D2 = Xagg . Wg^T once the mid group has rewritten the tile as bf16 Xagg
-      mbar_wait(&xagg_full[s], (uint32_t)((it >> 1) & 1));
+      // ---- MMA 2: D2 = Xagg (tensor memory, written over D1 by the mid group) . Wg^T (shared memory)
+      mbar_wait(&xagg_full[it & 1], (uint32_t)((it >> 1) & 1));
       mbar_wait(&d2_empty[s2], (uint32_t)(((ND2 == 2 ? (it >> 1) : it) & 1) ^ 1));   // that accumulator has been read
       tc_fence_after();
       if (leader) {
@@ -170,55 +187,52 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
         for (int kc = 0; kc < KC1; ++kc) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t da = make_smem_desc_kmajor_sw128(xb + (uint32_t)kc * kGfTile + (uint32_t)k * 32u);
             const uint64_t db = make_smem_desc_kmajor_sw128(w_u32 + (uint32_t)kc * (COUT * 128) + (uint32_t)k * 32u);
-            umma_bf16(tmem_d2 + (uint32_t)(s2 * COUT), da, db, idesc2, (kc | k) != 0 ? 1u : 0u);
+            // channels c0 = kc*64 + k*16 live at column half*(CIN/2) + (c0 - half*(CIN/2)) / 2 of this tile's D1 (mid group)
+            constexpr int HC = CIN / 2;
+            const int c0 = kc * 64 + k * 16;
+            const int xcol = (c0 / HC) * HC + (c0 % HC) / 2;
+            umma_bf16_ts(tmem_d2 + (uint32_t)(s2 * COUT), tmem_d1 + (uint32_t)(s1 * CIN + xcol), db, idesc2, (kc | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(&d2_full[s2]);
-        umma_commit(&x_empty[b]);                            // the tile buffer may be refilled once MMA 2 has read it
       }
       __syncwarp();
-      if (!early && it + 1 < my_tiles) {
+      if (!early && it + 1 < my_tiles) {                     // D1 / Xagg of this tile is dead once MMA 2 above has run (in order)
         mbar_wait(&x_full[nb], nphase);
         tc_fence_after();
-        issue_mma1(x_u32 + (uint32_t)nb * (uint32_t)(KC1 * kGfTile), s ^ 1);
+        issue_mma1(x_u32 + (uint32_t)nb * (uint32_t)(KC1 * kGfTile), ND1 == 2 ? (s1 ^ 1) : 0, nb);
       }
       b = nb; phase = nphase;
     }
   } else if (warp < 2 + kGfGroupWarps) {
-    // ===================== mid group (8 warps): D1 -> bf16 Xagg, in place over the X tile =====================
-    constexpr int CW1 = CIN / 2;                             // columns per thread: TMEM lane group x column half
+    // ===================== mid group (8 warps): D1 (fp32) -> Xagg (bf16 pairs), in place in tensor memory =====================
+    // Xagg is the A operand of MMA 2 (TS mode): it never touches shared memory.  Thread = tile row x column half; each
+    // half packs into the first half of ITS OWN source columns (channels [h*CW1, +CW1) -> columns h*CW1 + [0, CW1/2)),
+    // so no thread overwrites data another thread still has to load.
+    constexpr int CW1 = CIN / 2;
     const int lane_grp = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int r = lane_grp * 32 + lane;
     const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
-    int b = 0;
     for (int it = 0; it < my_tiles; ++it) {
-      const int s = it & 1;
-      uint8_t* xrow = s_x + (size_t)b * KC1 * kGfTile + (size_t)r * 128;
-      mbar_wait(&d1_full[s], (uint32_t)((it >> 1) & 1));
+      const int s1 = ND1 == 2 ? (it & 1) : 0;
+      mbar_wait(&d1_full[s1], (uint32_t)((ND1 == 2 ? (it >> 1) : it) & 1));
       tc_fence_after();
       uint32_t a[CW1];
 #pragma unroll
-      for (int i = 0; i < CW1 / 16; ++i) tmem_ld16(tmem_d1 + lane_off + (uint32_t)(s * CIN + half * CW1 + 16 * i), a + 16 * i);
+      for (int i = 0; i < CW1 / 16; ++i) tmem_ld16(tmem_d1 + lane_off + (uint32_t)(s1 * CIN + half * CW1 + 16 * i), a + 16 * i);
       tmem_ld_wait();
 #pragma unroll
-      for (int q = 0; q < CW1 / 8; ++q) {
-        uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(a[8 * q + 0]), __uint_as_float(a[8 * q + 1]));
-        u.y = pack_bf16x2(__uint_as_float(a[8 * q + 2]), __uint_as_float(a[8 * q + 3]));
-        u.z = pack_bf16x2(__uint_as_float(a[8 * q + 4]), __uint_as_float(a[8 * q + 5]));
-        u.w = pack_bf16x2(__uint_as_float(a[8 * q + 6]), __uint_as_float(a[8 * q + 7]));
-        const int col = half * CW1 + 8 * q;
-        const int j = (col & 63) >> 3;
-        *reinterpret_cast<uint4*>(xrow + (size_t)(col >> 6) * kGfTile + ((j ^ (r & 7)) << 4)) = u;
+      for (int q = 0; q < CW1 / 16; ++q) {                   // 16 fp32 columns -> 8 packed columns per store
+        uint32_t w8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w8[e] = pack_bf16x2(__uint_as_float(a[16 * q + 2 * e]), __uint_as_float(a[16 * q + 2 * e + 1]));
+        tmem_st8(tmem_d1 + lane_off + (uint32_t)(s1 * CIN + half * CW1 + 8 * q), w8);   // inside this thread's own source columns
       }
+      tmem_st_wait();
       tc_fence_before();
-      fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&xagg_full[s]);
-      if (++b == p.xbufs) b = 0;
+      if (lane == 0) mbar_arrive(&xagg_full[it & 1]);
     }
   } else {
     // ===================== final group (8 warps): D2 + bias -> ReLU -> bf16 -> staging -> TMA store =====================
@@ -337,7 +351,7 @@ int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float
   p.n_clips = (int32_t)n_clips; p.T = T; p.V = V;
   p.ttg = T < 7 ? T : 7;
   p.tiles_t = (T + p.ttg - 1) / p.ttg;
-  p.bias = bias; p.relu = relu;
+  p.bias = bias; p.relu = relu; p.abd = reinterpret_cast<const __nv_bfloat16*>(abd);
   int rc = TIK_OK;
   {
     uint64_t dims[4] = {(uint64_t)cin, (uint64_t)T, (uint64_t)V, (uint64_t)n_clips};
@@ -369,10 +383,10 @@ int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float
   const int bias_bytes = (V * (cout + 4) * 4 + 1023) / 1024 * 1024;
   // two staging tiles when at least three input tiles still fit beside them (measured: input depth matters more)
   p.sbufs = 2;
-  int fixed = 2 * kGfTile + w_bytes + p.sbufs * kc2 * kGfTile + bias_bytes + 256;
+  int fixed = w_bytes + p.sbufs * kc2 * kGfTile + bias_bytes + 256;
   if ((kGfSmemBudget - fixed) / (kc1 * kGfTile) < 3) {
     p.sbufs = 1;
-    fixed = 2 * kGfTile + w_bytes + kc2 * kGfTile + bias_bytes + 256;
+    fixed = w_bytes + kc2 * kGfTile + bias_bytes + 256;
   }
   p.xbufs = (kGfSmemBudget - fixed) / (kc1 * kGfTile);
   if (p.xbufs > kGfMaxBufs) p.xbufs = kGfMaxBufs;
@@ -381,7 +395,7 @@ int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float
     set_error("fused gcn: shared memory plan does not fit");
     return TIK_ERR_UNSUPPORTED;
   }
-  p.off_w = 2 * kGfTile;
+  p.off_w = 0;
   p.off_x = p.off_w + (w_bytes + 1023) / 1024 * 1024;
   p.off_stage = p.off_x + p.xbufs * kc1 * kGfTile;
   p.off_bias = p.off_stage + p.sbufs * kc2 * kGfTile;
