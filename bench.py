@@ -68,7 +68,7 @@ def _ncu_traffic_per_launch():
     hdr = rows[0]
     ki, mi, vi, ii = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
     for r in rows[1:]:
-        if any(k in r[ki] for k in ("rowgemm_umma", "rowgemm_ts", "gcn_fused", "stem_block")) and r[mi].startswith("dram__bytes"):
+        if any(k in r[ki] for k in ("rowgemm_umma", "rowgemm_ts", "tcn_halo", "gcn_fused", "stem_block")) and r[mi].startswith("dram__bytes"):
             per[r[ii]] = per.get(r[ii], 0.0) + float(r[vi].replace(",", ""))
     return sum(per.values()) / len(per) if per else None
 
@@ -282,7 +282,7 @@ def run_ours(args):
         achieved = gemm_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
         peak = peaks["bf16_tflops_sustained"] if args.dtype == "bf16" else 74.0
         launches_per_step = plan.launches(B) + 1                 # + FK
-        roofline = {"bound": "tensor", "kernel": "tcgen05 family: rowgemm_umma_kernel / rowgemm_ts_kernel / gcn_fused_kernel / stem_block_kernel" if args.dtype == "bf16" else "rowgemm_f32_kernel",
+        roofline = {"bound": "tensor", "kernel": "tcgen05 family: rowgemm_umma_kernel / rowgemm_ts_kernel / tcn_halo_kernel / gcn_fused_kernel / stem_block_kernel" if args.dtype == "bf16" else "rowgemm_f32_kernel",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_source": (peak_src + " bf16_tflops_sustained (kernel timed inside a long step)") if args.dtype == "bf16" else "nominal fp32 SIMT 148 SM x 128 FMA x 2 x 1.965 GHz",
                     "launches": g_n, "avg_launch_us": g_ms * 1e3 / max(g_n, 1), "flops_per_step": gemm_flops,
