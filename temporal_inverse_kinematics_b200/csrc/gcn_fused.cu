@@ -303,6 +303,263 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------------ 64-channel inputs: two tiles per pass
+// At Cin = 64 a tile is only 16 KB and the single MMA-issuing thread (8 aggregation MMAs of N = 64, ~65 cycles each, plus
+// the barrier hand-offs) bounds the kernel well above its HBM time.  Two tiles that share the adjacency are therefore
+// aggregated by ONE set of N = 128 MMAs -- their X boxes sit in adjacent 16 KB slabs, exactly the layout of a
+// 128-channel tile -- and only the channel GEMM runs per tile (its A operand is that tile's half of the TMEM-resident
+// aggregate).  Half the aggregation MMAs, half the hand-offs per tile.
+template <int COUT>
+__global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_pair_kernel(const __grid_constant__ GcnFusedParams p) {
+  constexpr int KC2 = COUT / 64;
+  constexpr int ND1 = (64 + 2 * 128 + 2 * COUT) <= 512 ? 2 : 1;
+  constexpr int ND2 = (64 + ND1 * 128 + 4 * COUT) <= 512 ? 2 : 1;
+  constexpr int TMEM_NEED = 64 + ND1 * 128 + ND2 * 2 * COUT;
+  constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_w = smem + p.off_w;                      // COUT rows x 128 B
+  uint8_t* s_x = smem + p.off_x;                      // xbufs stages x 2 slabs (tile A, tile B)
+  uint8_t* s_stage = smem + p.off_stage;              // 2 staging tiles (A, B) of KC2 slabs
+  float* s_bias = reinterpret_cast<float*>(smem + p.off_bias);
+  uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* x_empty = x_full + kGfMaxBufs;
+  uint64_t* w_full = x_empty + kGfMaxBufs;
+  uint64_t* d1_full = w_full + 1;
+  uint64_t* xagg_full = d1_full + 2;
+  uint64_t* d2_full = xagg_full + 2;
+  uint64_t* d2_empty = d2_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = p.n_clips * p.tiles_t;
+  const int n_pairs = (n_tiles + 1) / 2;
+  const int my_pairs = n_pairs > (int)blockIdx.x ? (n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int rows_valid = p.ttg * p.V;
+  const uint32_t x_bytes = (uint32_t)(rows_valid * 128);
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.map_x); tma_prefetch_desc(&p.map_out); tma_prefetch_desc(&p.map_w); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kGfMaxBufs; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&d1_full[i], 1); mbar_init(&xagg_full[i], kGfGroupWarps); mbar_init(&d2_full[i], 1); mbar_init(&d2_empty[i], kGfGroupWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  for (int i = threadIdx.x; i < p.V * COUT; i += kGfThreads) s_bias[(i / COUT) * (COUT + 4) + (i % COUT)] = __ldg(p.bias + i);
+  {
+    const int pad_rows = 128 - rows_valid;
+    const int total16 = p.xbufs * 2 * pad_rows * 8;
+    for (int i = threadIdx.x; i < total16; i += kGfThreads) {
+      const int piece = i & 7, rr = (i >> 3) % pad_rows, slab = (i >> 3) / pad_rows;
+      *reinterpret_cast<uint4*>(s_x + (size_t)slab * kGfTile + (size_t)(rows_valid + rr) * 128 + piece * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_abd = tmem_base, tmem_d1 = tmem_base + 64, tmem_d2 = tmem_base + 64 + ND1 * 128;
+  if (warp >= 2 && warp < 6) {
+    const int r = (warp & 3) * 32 + lane;
+    const uint4* arow = reinterpret_cast<const uint4*>(p.abd + (size_t)r * 128);
+    uint4 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = __ldg(arow + u);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t w8[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w, v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
+      tmem_st8(tmem_abd + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(8 * u), w8);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // tile coordinates of pair `it`, slot h (a trailing odd tile is loaded twice and stored once)
+  auto tile_of = [&](int it, int h, int& n, int& t0, bool& valid) {
+    int tile = 2 * ((int)blockIdx.x + it * (int)gridDim.x) + h;
+    valid = tile < n_tiles;
+    if (!valid) tile = n_tiles - 1;
+    n = tile / p.tiles_t;
+    const int tt = tile - n * p.tiles_t;
+    t0 = min(tt * p.ttg, p.T - p.ttg);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(w_full, (uint32_t)(COUT * 128));
+      tma_load_2d(s_w, &p.map_w, w_full, 0, 0);
+      int b = 0; uint32_t phase = 0;
+      for (int it = 0; it < my_pairs; ++it) {
+        mbar_wait(&x_empty[b], phase ^ 1);
+        mbar_expect_tx(&x_full[b], 2 * x_bytes);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          int n, t0; bool valid;
+          tile_of(it, h, n, t0, valid);
+          tma_load_4d(s_x + ((size_t)b * 2 + h) * kGfTile, &p.map_x, &x_full[b], 0, t0, 0, n);
+        }
+        if (++b == p.xbufs) { b = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc1 = make_idesc_bf16(128, 128) | (1u << 16);   // both tiles at once; B operand MN-major
+    constexpr uint32_t idesc2 = make_idesc_bf16(128, COUT);
+    const bool leader = lane == 0;
+    mbar_wait(w_full, 0);
+    const uint32_t w_u32 = smem_u32(s_w), x_u32 = smem_u32(s_x);
+    auto issue_mma1 = [&](uint32_t xb, int s1, int buf) {
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t db = make_smem_desc_mnmajor_sw128(xb + (uint32_t)k * 2048u, (uint32_t)kGfTile);
+          umma_bf16_ts(tmem_d1 + (uint32_t)(s1 * 128), tmem_abd + (uint32_t)(8 * k), db, idesc1, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&d1_full[s1]);
+        umma_commit(&x_empty[buf]);
+      }
+      __syncwarp();
+    };
+    int b = 0; uint32_t phase = 0;
+    if (my_pairs > 0) {
+      mbar_wait(&x_full[0], 0);
+      tc_fence_after();
+      issue_mma1(x_u32, 0, 0);
+    }
+    const bool early = ND1 == 2 && p.xbufs >= 2;
+    for (int it = 0; it < my_pairs; ++it) {
+      const int s1 = ND1 == 2 ? (it & 1) : 0;
+      const int s2 = ND2 == 2 ? (it & 1) : 0;
+      int nb = b + 1; uint32_t nphase = phase;
+      if (nb == p.xbufs) { nb = 0; nphase ^= 1; }
+      if (early && it + 1 < my_pairs) {
+        mbar_wait(&x_full[nb], nphase);
+        tc_fence_after();
+        issue_mma1(x_u32 + (uint32_t)nb * (uint32_t)(2 * kGfTile), s1 ^ 1, nb);
+      }
+      mbar_wait(&xagg_full[it & 1], (uint32_t)((it >> 1) & 1));
+      mbar_wait(&d2_empty[s2], (uint32_t)(((ND2 == 2 ? (it >> 1) : it) & 1) ^ 1));
+      tc_fence_after();
+      if (leader) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                        // tile h: its 64 aggregated channels are bf16 pairs at D1 columns h*64 + [0, 32)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t db = make_smem_desc_kmajor_sw128(w_u32 + (uint32_t)k * 32u);
+            umma_bf16_ts(tmem_d2 + (uint32_t)(s2 * 2 * COUT + h * COUT), tmem_d1 + (uint32_t)(s1 * 128 + h * 64 + k * 8), db, idesc2, k != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&d2_full[s2]);
+      }
+      __syncwarp();
+      if (!early && it + 1 < my_pairs) {
+        mbar_wait(&x_full[nb], nphase);
+        tc_fence_after();
+        issue_mma1(x_u32 + (uint32_t)nb * (uint32_t)(2 * kGfTile), ND1 == 2 ? (s1 ^ 1) : 0, nb);
+      }
+      b = nb; phase = nphase;
+    }
+  } else if (warp < 2 + kGfGroupWarps) {
+    // ===================== mid group: D1 (fp32, both tiles) -> bf16 pairs in place (column half = tile) =====================
+    const int lane_grp = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
+    for (int it = 0; it < my_pairs; ++it) {
+      const int s1 = ND1 == 2 ? (it & 1) : 0;
+      mbar_wait(&d1_full[s1], (uint32_t)((ND1 == 2 ? (it >> 1) : it) & 1));
+      tc_fence_after();
+      uint32_t a[64];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tmem_ld16(tmem_d1 + lane_off + (uint32_t)(s1 * 128 + half * 64 + 16 * i), a + 16 * i);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t w8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w8[e] = pack_bf16x2(__uint_as_float(a[16 * q + 2 * e]), __uint_as_float(a[16 * q + 2 * e + 1]));
+        tmem_st8(tmem_d1 + lane_off + (uint32_t)(s1 * 128 + half * 64 + 8 * q), w8);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xagg_full[it & 1]);
+    }
+  } else {
+    // ===================== final group: both tiles' D2 + bias -> ReLU -> bf16 -> staging A / B -> TMA stores =====================
+    constexpr int CW2 = COUT / 2;
+    const int lane_grp = warp & 3;
+    const int half = (warp - 2 - kGfGroupWarps) >> 2;
+    const int r = lane_grp * 32 + lane;
+    const int node = r / p.ttg;
+    const float* bias = s_bias + (node < p.V ? node : 0) * (COUT + 4) + half * CW2;
+    const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
+    const bool issuer = threadIdx.x == 32 * (2 + kGfGroupWarps);
+    for (int it = 0; it < my_pairs; ++it) {
+      const int s2 = ND2 == 2 ? (it & 1) : 0;
+      if (issuer) tma_store_wait_read0();                    // both staging tiles of the previous pair have been read
+      mbar_wait(&d2_full[s2], (uint32_t)((ND2 == 2 ? (it >> 1) : it) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t a[CW2];
+#pragma unroll
+        for (int i = 0; i < CW2 / 16; ++i)
+          tmem_ld16(tmem_d2 + lane_off + (uint32_t)(s2 * 2 * COUT + h * COUT + half * CW2 + 16 * i), a + 16 * i);
+        tmem_ld_wait();
+        if (h == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&d2_empty[s2]);
+        }
+        if (h == 0) named_bar_sync(1, 32 * kGfGroupWarps);   // staging tiles free (issuer passed wait_read)
+        uint8_t* stage = s_stage + (size_t)h * (KC2 * kGfTile);
+#pragma unroll
+        for (int q = 0; q < CW2 / 8; ++q) {
+          const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * q);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * q + 4);
+          const float v0 = __uint_as_float(a[8 * q + 0]) + b0.x, v1 = __uint_as_float(a[8 * q + 1]) + b0.y;
+          const float v2 = __uint_as_float(a[8 * q + 2]) + b0.z, v3 = __uint_as_float(a[8 * q + 3]) + b0.w;
+          const float v4 = __uint_as_float(a[8 * q + 4]) + b1.x, v5 = __uint_as_float(a[8 * q + 5]) + b1.y;
+          const float v6 = __uint_as_float(a[8 * q + 6]) + b1.z, v7 = __uint_as_float(a[8 * q + 7]) + b1.w;
+          uint4 u;
+          if (p.relu) { u.x = pack_bf16x2_relu(v0, v1); u.y = pack_bf16x2_relu(v2, v3); u.z = pack_bf16x2_relu(v4, v5); u.w = pack_bf16x2_relu(v6, v7); }
+          else { u.x = pack_bf16x2(v0, v1); u.y = pack_bf16x2(v2, v3); u.z = pack_bf16x2(v4, v5); u.w = pack_bf16x2(v6, v7); }
+          const int col = half * CW2 + 8 * q;
+          const int j = (col & 63) >> 3;
+          *reinterpret_cast<uint4*>(stage + (size_t)(col >> 6) * kGfTile + (size_t)r * 128 + ((j ^ (r & 7)) << 4)) = u;
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(2, 32 * kGfGroupWarps);
+      if (issuer) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          int n, t0; bool valid;
+          tile_of(it, h, n, t0, valid);
+          if (valid)
+            for (int c = 0; c < KC2; ++c) tma_store_4d(&p.map_out, s_stage + (size_t)h * (KC2 * kGfTile) + (size_t)c * kGfTile, c * 64, t0, 0, n);
+        }
+        tma_store_commit();
+      }
+    }
+    if (issuer) tma_store_wait0();
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -333,6 +590,7 @@ int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
 struct GcnFusedPrepared {
   GcnFusedParams p;
   int cin, cout, smem_bytes;
+  bool pair;                               // Cin = 64: two tiles per aggregation pass (gcn_fused_pair_kernel)
 };
 
 bool gcn_fused_supported(int cin, int cout, int V, int K) {
@@ -381,14 +639,18 @@ int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float
   const int kc1 = cin / 64, kc2 = cout / 64;
   const int w_bytes = kc1 * cout * 128;
   const int bias_bytes = (V * (cout + 4) * 4 + 1023) / 1024 * 1024;
-  // two staging tiles when at least three input tiles still fit beside them (measured: input depth matters more)
+  // 64 -> 128 would need 576 TMEM columns to keep D1 double buffered as a pair; single-buffered it is slower (360 vs 324 us)
+  g->pair = cin == 64 && cout == 64 && !getenv("TIK_NO_GCN_PAIR");
+  const int stage_tiles = g->pair ? 2 : 1;                // input tiles per ring stage
+  // two staging tiles when at least three input stages still fit beside them (measured: input depth matters more);
+  // the pair kernel always stages both of its tiles
   p.sbufs = 2;
   int fixed = w_bytes + p.sbufs * kc2 * kGfTile + bias_bytes + 256;
-  if ((kGfSmemBudget - fixed) / (kc1 * kGfTile) < 3) {
+  if (!g->pair && (kGfSmemBudget - fixed) / (kc1 * kGfTile) < 3) {
     p.sbufs = 1;
     fixed = w_bytes + kc2 * kGfTile + bias_bytes + 256;
   }
-  p.xbufs = (kGfSmemBudget - fixed) / (kc1 * kGfTile);
+  p.xbufs = (kGfSmemBudget - fixed) / (stage_tiles * kc1 * kGfTile);
   if (p.xbufs > kGfMaxBufs) p.xbufs = kGfMaxBufs;
   if (p.xbufs < 1) {
     delete g;
@@ -397,7 +659,7 @@ int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float
   }
   p.off_w = 0;
   p.off_x = p.off_w + (w_bytes + 1023) / 1024 * 1024;
-  p.off_stage = p.off_x + p.xbufs * kc1 * kGfTile;
+  p.off_stage = p.off_x + p.xbufs * stage_tiles * kc1 * kGfTile;
   p.off_bias = p.off_stage + p.sbufs * kc2 * kGfTile;
   p.off_bar = p.off_bias + bias_bytes;
   g->smem_bytes = p.off_bar + 256 + 1024;
@@ -420,6 +682,21 @@ static int gf_launch_variant(const GcnFusedPrepared* g, unsigned grid, cudaStrea
   return TIK_OK;
 }
 
+template <int COUT>
+static int gf_launch_pair(const GcnFusedPrepared* g, unsigned grid, cudaStream_t s) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  TIK_CUDA(cudaGetDevice(&dev));
+  if (!attr_done[dev & 63]) {
+    TIK_CUDA(cudaFuncSetAttribute(gcn_fused_pair_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGfSmemBudget + 2048));
+    TIK_CUDA(cudaFuncSetAttribute(gcn_fused_pair_kernel<COUT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_done[dev & 63] = true;
+  }
+  gcn_fused_pair_kernel<COUT><<<grid, kGfThreads, g->smem_bytes, s>>>(g->p);
+  TIK_LAUNCH_CHECK();
+  return TIK_OK;
+}
+
 int gcn_fused_launch(GcnFusedPrepared* g, int64_t n_clips, cudaStream_t s) {
   TIK_CHECK_ARG(n_clips <= g->p.n_clips || true, "n_clips");
   GcnFusedParams& p = g->p;
@@ -431,9 +708,11 @@ int gcn_fused_launch(GcnFusedPrepared* g, int64_t n_clips, cudaStream_t s) {
   int sms = 148;
   { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int64_t tiles = n_clips * p.tiles_t;
-  const unsigned grid = (unsigned)std::min<int64_t>(tiles, sms);
+  const unsigned grid = (unsigned)std::min<int64_t>(g->pair ? (tiles + 1) / 2 : tiles, sms);
   int rc;
-  if (g->cin == 64 && g->cout == 64) rc = gf_launch_variant<64, 64>(g, grid, s);
+  if (g->pair && g->cout == 64) rc = gf_launch_pair<64>(g, grid, s);
+  else if (g->pair && g->cout == 128) rc = gf_launch_pair<128>(g, grid, s);
+  else if (g->cin == 64 && g->cout == 64) rc = gf_launch_variant<64, 64>(g, grid, s);
   else if (g->cin == 64 && g->cout == 128) rc = gf_launch_variant<64, 128>(g, grid, s);
   else if (g->cin == 128 && g->cout == 128) rc = gf_launch_variant<128, 128>(g, grid, s);
   else rc = gf_launch_variant<128, 256>(g, grid, s);
