@@ -37,7 +37,7 @@ extern "C" {
 
 #define TIK_MAX_BLOCKS 16
 #define TIK_MAX_SLABS 6
-#define TIK_MAX_JOINTS 32
+#define TIK_MAX_JOINTS 64
 
 int tik_version(void);
 const char* tik_last_error(void);

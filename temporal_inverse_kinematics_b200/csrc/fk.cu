@@ -9,6 +9,8 @@
 // instead of one round per tree level.  Inputs/outputs are staged per warp through shared memory so
 // that global traffic is contiguous.  HBM-bound: 264 B in, 264 + 792 B out per frame (aa in,
 // joints + local rotmats out).
+#include <string.h>
+
 #include "tik_common.cuh"
 
 namespace tik {
@@ -45,7 +47,7 @@ __global__ void __launch_bounds__(kFkWarps * 32)
 fk_kernel(const float* __restrict__ pose, const float* __restrict__ transl, float* __restrict__ joints,
           float* __restrict__ localR, float* __restrict__ globalR, int64_t F, const __grid_constant__ FkParams p) {
   constexpr int IN = kRotIn ? 9 : 3;
-  __shared__ __align__(16) float s_io[kFkWarps][TIK_MAX_JOINTS * 9];
+  __shared__ __align__(16) float s_io[kFkWarps][32 * 9];     // this kernel serves J <= 32 (one lane per joint)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int J = p.J;
   const bool active = lane < J;
@@ -232,6 +234,173 @@ fk_body22_kernel(const float* __restrict__ pose, const float* __restrict__ trans
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Trees of up to 64 joints (the full 55-joint SMPL-X skeleton: body + jaw + eyes + 2 x 15 finger joints, plus rigid
+// landmark pseudo-joints such as nose / ears hanging off the head with identity rotation; SURVEY.md 8f row 3,
+// common/smpl_util.py:61-69, data_amass.py:176-218).  One warp per frame; the warp keeps every joint's global
+// transform in shared memory and walks the tree LEVEL BY LEVEL (host-sorted order), one lane per joint of the level,
+// so a level costs one pass however many joints it holds (11 levels for SMPL-X).  All global traffic is staged
+// through the warp's shared-memory rows and is contiguous.
+constexpr int kTreeMaxJ = 64;
+constexpr int kTreeWarps = 4;
+constexpr int kTreeMaxLevels = 24;
+
+struct FkTreeParams {
+  float rest[kTreeMaxJ * 3];        // offset to parent (root: rest position)
+  int8_t parent[kTreeMaxJ];
+  uint8_t order[kTreeMaxJ];         // joints sorted by tree level
+  uint8_t level_start[kTreeMaxLevels + 1];
+  int32_t n_levels, J;
+};
+
+template <bool kRotIn>
+__global__ void __launch_bounds__(kTreeWarps * 32)
+fk_tree_kernel(const float* __restrict__ pose, const float* __restrict__ transl, float* __restrict__ joints,
+               float* __restrict__ localR, float* __restrict__ globalR, int64_t F, const __grid_constant__ FkTreeParams p) {
+  constexpr int IN = kRotIn ? 9 : 3;
+  __shared__ __align__(16) float s_R[kTreeWarps][kTreeMaxJ * 9];     // pose in, then local rotations
+  __shared__ __align__(16) float s_G[kTreeWarps][kTreeMaxJ * 12];    // global [R | t] per joint
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int J = p.J;
+  float* sr = s_R[warp];
+  float* sg = s_G[warp];
+  const int64_t warps_total = (int64_t)gridDim.x * kTreeWarps;
+  for (int64_t f = (int64_t)blockIdx.x * kTreeWarps + warp; f < F; f += warps_total) {
+    const float* gp = pose + f * (int64_t)J * IN;
+    for (int i = lane; i < J * IN; i += 32) sr[i] = __ldg(gp + i);
+    __syncwarp();
+    if (!kRotIn) {
+      // axis-angle -> rotation matrix, two joints per lane; inputs are read before any 9-float row is written
+      float R0[9], R1[9];
+      const int j0 = lane, j1 = lane + 32;
+      if (j0 < J) rodrigues_q(sr[j0 * 3], sr[j0 * 3 + 1], sr[j0 * 3 + 2], R0);
+      if (j1 < J) rodrigues_q(sr[j1 * 3], sr[j1 * 3 + 1], sr[j1 * 3 + 2], R1);
+      __syncwarp();
+      if (j0 < J) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) sr[j0 * 9 + k] = R0[k];
+      }
+      if (j1 < J) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) sr[j1 * 9 + k] = R1[k];
+      }
+      __syncwarp();
+    }
+    if (localR != nullptr) {
+      float* go = localR + f * (int64_t)J * 9;
+      for (int i = lane; i < J * 9; i += 32) go[i] = sr[i];
+    }
+    float tx = 0.f, ty = 0.f, tz = 0.f;
+    if (transl != nullptr) { tx = __ldg(transl + f * 3); ty = __ldg(transl + f * 3 + 1); tz = __ldg(transl + f * 3 + 2); }
+    for (int l = 0; l < p.n_levels; ++l) {
+      for (int q = p.level_start[l] + lane; q < p.level_start[l + 1]; q += 32) {
+        const int j = p.order[q];
+        const int par = p.parent[j];
+        const float* R = sr + j * 9;
+        const float dx = p.rest[j * 3], dy = p.rest[j * 3 + 1], dz = p.rest[j * 3 + 2];
+        float* G = sg + j * 12;
+        if (par < 0) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) G[k] = R[k];
+          G[9] = dx + tx; G[10] = dy + ty; G[11] = dz + tz;
+        } else {
+          const float* A = sg + par * 12;
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) G[a * 3 + b] = A[a * 3] * R[b] + A[a * 3 + 1] * R[3 + b] + A[a * 3 + 2] * R[6 + b];
+          G[9] = A[0] * dx + A[1] * dy + A[2] * dz + A[9];
+          G[10] = A[3] * dx + A[4] * dy + A[5] * dz + A[10];
+          G[11] = A[6] * dx + A[7] * dy + A[8] * dz + A[11];
+        }
+      }
+      __syncwarp();
+    }
+    float* gj = joints + f * (int64_t)J * 3;
+    for (int i = lane; i < J * 3; i += 32) gj[i] = sg[(i / 3) * 12 + 9 + i % 3];
+    if (globalR != nullptr) {
+      float* gg = globalR + f * (int64_t)J * 9;
+      for (int i = lane; i < J * 9; i += 32) gg[i] = sg[(i / 9) * 12 + i % 9];
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Thread-per-frame specialisation for the full SMPL-X skeleton + face landmarks (60 joints, the tree of
+// smpl_util.SyntheticBodyModel(skeleton='full')): same idea as fk_body22_kernel -- compile-time parents, fully unrolled,
+// every live transform in registers (at most the current chain: a wrist stays live while its 15 finger joints are
+// walked) -- ~5x fewer warp instructions per frame than the level-order kernel above.  Axis-angle in, joints out.
+constexpr int kF60 = 60;
+constexpr int kF60Threads = 64;
+constexpr int kF60ParentHost[kF60] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 15, 15, 15,
+                                      20, 25, 26, 20, 28, 29, 20, 31, 32, 20, 34, 35, 20, 37, 38,
+                                      21, 40, 41, 21, 43, 44, 21, 46, 47, 21, 49, 50, 21, 52, 53, 15, 15, 15, 15, 15};
+__host__ __device__ constexpr int f60_parent(int j) {
+  constexpr int P[kF60] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 15, 15, 15,
+                           20, 25, 26, 20, 28, 29, 20, 31, 32, 20, 34, 35, 20, 37, 38,
+                           21, 40, 41, 21, 43, 44, 21, 46, 47, 21, 49, 50, 21, 52, 53, 15, 15, 15, 15, 15};
+  return P[j];
+}
+struct Fk60Params { float rest[kF60 * 3]; };
+
+__global__ void __launch_bounds__(kF60Threads)
+fk_full60_kernel(const float* __restrict__ pose, const float* __restrict__ transl, float* __restrict__ joints, int64_t F,
+                 const __grid_constant__ Fk60Params p) {
+  constexpr int LD = kF60 * 3 + 1;                 // odd row pitch: conflict-free per-thread rows
+  extern __shared__ __align__(16) float fk_smem[];
+  float* s_io = fk_smem;                           // [64][LD]: pose in, joints out
+  const int tid = threadIdx.x;
+  const int64_t tiles = (F + kF60Threads - 1) / kF60Threads;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t f0 = tile * kF60Threads;
+    const int nf = (int)min((int64_t)kF60Threads, F - f0);
+    const float* gp = pose + f0 * (kF60 * 3);
+    const int n_io = nf * kF60 * 3;
+#pragma unroll 8
+    for (int i = tid; i < n_io; i += kF60Threads) s_io[i / (kF60 * 3) * LD + i % (kF60 * 3)] = __ldg(gp + i);
+    __syncthreads();
+    if (tid < nf) {
+      float* row = s_io + tid * LD;
+      float GR[kF60][9];
+      float Gt[kF60][3];
+#pragma unroll
+      for (int j = 0; j < kF60; ++j) {
+        float R[9];
+        rodrigues_q(row[j * 3], row[j * 3 + 1], row[j * 3 + 2], R);
+        const float dx = p.rest[j * 3], dy = p.rest[j * 3 + 1], dz = p.rest[j * 3 + 2];
+        constexpr int kNone = -1;
+        const int par = f60_parent(j);
+        if (par == kNone) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) GR[j][k] = R[k];
+          Gt[j][0] = dx; Gt[j][1] = dy; Gt[j][2] = dz;
+        } else {
+          const float* A = GR[par];
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) GR[j][a * 3 + b] = A[a * 3] * R[b] + A[a * 3 + 1] * R[3 + b] + A[a * 3 + 2] * R[6 + b];
+          Gt[j][0] = A[0] * dx + A[1] * dy + A[2] * dz + Gt[par][0];
+          Gt[j][1] = A[3] * dx + A[4] * dy + A[5] * dz + Gt[par][1];
+          Gt[j][2] = A[6] * dx + A[7] * dy + A[8] * dz + Gt[par][2];
+        }
+      }
+      float tx = 0.f, ty = 0.f, tz = 0.f;
+      if (transl != nullptr) {
+        tx = __ldg(transl + (f0 + tid) * 3); ty = __ldg(transl + (f0 + tid) * 3 + 1); tz = __ldg(transl + (f0 + tid) * 3 + 2);
+      }
+#pragma unroll
+      for (int j = 0; j < kF60; ++j) { row[j * 3] = Gt[j][0] + tx; row[j * 3 + 1] = Gt[j][1] + ty; row[j * 3 + 2] = Gt[j][2] + tz; }
+    }
+    __syncthreads();
+    float* gj = joints + f0 * (kF60 * 3);
+#pragma unroll 8
+    for (int i = tid; i < n_io; i += kF60Threads) gj[i] = s_io[i / (kF60 * 3) * LD + i % (kF60 * 3)];
+    __syncthreads();
+  }
+}
+
 template <bool kRotIn, bool kLocalOut>
 static int launch_body22(const float* pose, const float* transl, float* joints, float* localR, int64_t F,
                          const Fk22Params& p, cudaStream_t s) {
@@ -291,6 +460,51 @@ extern "C" int tik_fk_body(const float* pose_dev, int pose_is_rotmat, const floa
       return launch_body22<false, false>(pose_dev, transl_dev, joints_dev, nullptr, F, q, s);
     }
     return launch_body22<false, false>(pose_dev, transl_dev, joints_dev, nullptr, F, q, s);
+  }
+  if (J == kF60 && !pose_is_rotmat && local_R_dev == nullptr && global_R_dev == nullptr) {
+    bool full60 = true;
+    for (int i = 0; full60 && i < J; ++i) full60 = parents_host[i] == kF60ParentHost[i];
+    if (full60) {
+      Fk60Params q;
+      for (int i = 0; i < kF60 * 3; ++i) q.rest[i] = p.rest[i];
+      const size_t smem = sizeof(float) * (size_t)kF60Threads * (kF60 * 3 + 1);
+      static bool attr_set[64] = {};
+      int dev = 0;
+      TIK_CUDA(cudaGetDevice(&dev));
+      if (!attr_set[dev & 63]) {
+        TIK_CUDA(cudaFuncSetAttribute(fk_full60_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_set[dev & 63] = true;
+      }
+      int64_t blocks = ceil_div(F, kF60Threads);
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      fk_full60_kernel<<<(unsigned)blocks, kF60Threads, smem, s>>>(pose_dev, transl_dev, joints_dev, F, q);
+      TIK_LAUNCH_CHECK();
+      return TIK_OK;
+    }
+  }
+  if (J > 32) {
+    FkTreeParams q;
+    memset(&q, 0, sizeof(q));
+    q.J = J;
+    int nl = 0;
+    for (int i = 0; i < J; ++i) { q.parent[i] = p.parent[i]; for (int k = 0; k < 3; ++k) q.rest[i * 3 + k] = p.rest[i * 3 + k]; }
+    TIK_CHECK_ARG(maxd + 1 <= kTreeMaxLevels, "kinematic tree deeper than %d levels", kTreeMaxLevels);
+    int pos = 0;
+    for (int l = 0; l <= maxd; ++l) {
+      q.level_start[l] = (uint8_t)pos;
+      for (int i = 0; i < J; ++i) if (depth[i] == l) q.order[pos++] = (uint8_t)i;
+      nl = l + 1;
+    }
+    q.level_start[nl] = (uint8_t)pos;
+    q.n_levels = nl;
+    int64_t blocks = ceil_div(F, kTreeWarps);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (pose_is_rotmat)
+      fk_tree_kernel<true><<<(unsigned)blocks, kTreeWarps * 32, 0, s>>>(pose_dev, transl_dev, joints_dev, local_R_dev, global_R_dev, F, q);
+    else
+      fk_tree_kernel<false><<<(unsigned)blocks, kTreeWarps * 32, 0, s>>>(pose_dev, transl_dev, joints_dev, local_R_dev, global_R_dev, F, q);
+    TIK_LAUNCH_CHECK();
+    return TIK_OK;
   }
   p.J = J;
   p.rounds = 0;

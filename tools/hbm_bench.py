@@ -54,6 +54,15 @@ def main():
         gbs = byts / t / 1e9
         out[name] = {"ms": t * 1e3, "GB/s": gbs, "frac_of_measured_hbm": gbs / peak, "frames_per_s": F / t}
         print(f"{name:34s} {t * 1e3:8.3f} ms  {gbs:8.1f} GB/s  frac {gbs / peak:5.3f}  {F / t / 1e9:6.3f} G frames/s", flush=True)
+    # full SMPL-X skeleton (55 joints + 5 landmarks, level-order tree kernel), F/4 frames: 720 B in + 720 B out per frame
+    del x6, R
+    m = SU.SyntheticBodyModel("neutral", skeleton="full")
+    F2 = F // 4
+    pose60 = torch.randn(F2, 60, 3, device="cuda") * 0.5
+    t = timed(lambda: SU.fk_body(pose60, m.rest_joints, m.parents))
+    gbs = F2 * 1440 / t / 1e9
+    out["fk_body full skeleton (60 joints)"] = {"ms": t * 1e3, "GB/s": gbs, "frac_of_measured_hbm": gbs / peak, "frames_per_s": F2 / t}
+    print(f"{'fk_body full skeleton (60 joints)':34s} {t * 1e3:8.3f} ms  {gbs:8.1f} GB/s  frac {gbs / peak:5.3f}  {F2 / t / 1e9:6.3f} G frames/s", flush=True)
     json.dump({"F": F, "J": J, "hbm_peak_gbs": peak, "kernels": out}, open(os.path.join(ROOT, "gpurun_out", "hbm_bench.json"), "w"), indent=1)
 
 
