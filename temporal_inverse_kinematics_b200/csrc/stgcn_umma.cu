@@ -11,13 +11,14 @@
 // The box lands in shared memory in the 128-byte-swizzled K-major layout that the UMMA shared-memory
 // descriptor consumes directly.
 //
-// Persistent kernel, one CTA per SM, static round-robin tile schedule.  Warp roles (192 threads):
-//   warp 0   TMA producer: streams A chunks (and W chunks when the weights do not fit) through a
-//            STAGES-deep ring, running ahead across tile boundaries;
-//   warp 1   MMA issuer (one lane): 4 x tcgen05.mma (M=128, N=BN, K=16) per 64-channel chunk into one of
-//            two TMEM accumulators, tcgen05.commit frees ring slots / publishes the accumulator;
-//   warps 2-5 epilogue: TMEM -> registers -> bias / residual / activation -> global, overlapped with the
-//            next tile's main loop through the second accumulator.
+// Persistent kernel, one CTA per SM, static round-robin tile schedule.  Warp roles (640 threads):
+//   warp 0     TMA producer: streams A chunks (and W chunks when the weights do not fit) through a ring whose stages
+//              hold 1, 2 or 4 K chunks each (one barrier hand-off per stage), running ahead across tile boundaries;
+//   warp 1     MMA issuer (warp-uniform loop, one lane issues): 4 x tcgen05.mma (M=128, N=BN, K=16) per 64-channel
+//              chunk into one of two TMEM accumulators, tcgen05.commit frees ring stages / publishes the accumulator;
+//   warps 2-17 epilogue (TMEM lane group x column quarter): tcgen05.ld up front, accumulator handed back at once,
+//              bias / activation / bf16 -> 128B-swizzled staging tile, overlapped with the next tile's main loop;
+//   warp 18    TMA-store warp: one cp.async.bulk.tensor store per 64-column slab, two staging tiles in flight.
 // When (c_out x K_total) bf16 weights fit beside the ring they are loaded into shared memory once per CTA
 // and stay resident for all its tiles (they are the larger half of the per-tile operand bytes otherwise).
 //
