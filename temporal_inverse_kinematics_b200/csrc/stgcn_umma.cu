@@ -70,6 +70,7 @@ struct UmmaParams {
   int32_t res_kind; const void* res; const float* res_w; int32_t res_cin, res_t_mul, res_t_in;
   void* out; int32_t out_layout;
   int32_t ts;                      // weights stationary in tensor memory (rowgemm_ts_kernel)
+  int32_t two_cta;                 // CTA pairs sharing one weight stream (rowgemm_umma2_kernel)
   const __nv_bfloat16* w_gmem;     // ts: (c_out, ktot) row-major weights
   int32_t ktot;
   unsigned long long* dbg_times;   // probe hook: clock64 timeline of CTA 0 (tools/umma_probe.py)
@@ -396,6 +397,251 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
     tmem_dealloc<2 * BN>(tmem_base);
   }
   if (threadIdx.x == 64) TIK_T(10);
+}
+
+// ------------------------------------------------------------------------------------------------ CTA-pair variant (cta_group::2)
+// The 256-channel layers (K up to 896, weights 448 KB) can keep their weights neither beside the ring nor in tensor
+// memory: every 128-row tile streams all of W from L2 again, and each MMA reads a 128 x 16 A slice plus a 256 x 16 B
+// slice (12 KB) from shared memory.  Here two CTAs of a cluster work on two row tiles with ONE weight stream: each CTA
+// loads its own A chunk and HALF of the W chunk (128 of the 256 output channels), and the leader CTA issues
+// tcgen05.mma.cta_group::2 with M = 256 -- the tensor cores of both SMs read their own A tile and both B halves, so a
+// CTA moves 16 + 16 KB per chunk through its ring instead of 16 + 32 and reads 8 KB instead of 12 per MMA.
+// Barriers: the ring's "full" barrier lives in the leader and counts the bytes of all four TMA loads of a stage
+// (cta_group::2 loads may signal the peer's barrier); "empty" and "accumulator full" are committed to both CTAs
+// (multicast commit); the peer's epilogue warps arrive remotely on the leader's "accumulator empty".
+// STATUS: experiment (TIK_2CTA=1).  Results match the one-CTA kernel, but with one K chunk per cross-CTA hand-off it
+// is 1.1-1.7x slower; it needs multi-chunk stages before it can pay.
+template <int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1) rowgemm_umma2_kernel(const __grid_constant__ UmmaParams p) {
+  constexpr int BN = 256;
+  constexpr int kBHalf = (BN / 2) * kChunkK * 2;            // this CTA's half of a W chunk: 16 KB
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = smem + p.off_ring;
+  float* s_bias = reinterpret_cast<float*>(smem + p.off_bias);
+  uint8_t* s_stage = smem + p.off_stage;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;             // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                     // [2]
+  uint64_t* w_full = tmem_empty + 2;                        // unused
+  uint64_t* stage_full = w_full + 1;                        // [2]
+  uint64_t* stage_empty = stage_full + 2;                   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = (int)blockIdx.x >> 1, n_clusters = (int)gridDim.x >> 1;
+  const int stages = p.stages;
+  const int stage_bytes = kABytes + kBHalf;
+  const int ntn = p.n_tiles_n;
+  const int pairs_m = (int)((p.tiles_m + 1) / 2);
+  const int n_pairs = pairs_m * ntn;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.n_slabs; ++s) tma_prefetch_desc(&p.map_a[s]);
+    tma_prefetch_desc(&p.map_w);
+    if (p.tma_store) tma_prefetch_desc(&p.map_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&stage_full[i], kEpiWarps); mbar_init(&stage_empty[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm<512>(tmem_slot);
+  for (int i = threadIdx.x; i < p.bias_rows * p.c_out; i += kUmmaThreads) s_bias[(i / p.c_out) * (p.c_out + 4) + (i % p.c_out)] = __ldg(p.bias + i);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                       // the peer's barriers are initialised before anyone signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // pair index -> (row tile of this CTA, output-channel tile)
+  auto tile_of = [&](int pr, int& tm, int& n0) {
+    const int q = pr / ntn;
+    n0 = (pr - q * ntn) * BN;
+    tm = 2 * q + (int)rank;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs): own A chunk + own half of the W chunk =====================
+    if (lane == 0) {
+      const uint32_t tx_pair = 2u * (uint32_t)(p.a_box_bytes + kBHalf);
+      int stage = 0; uint32_t phase = 0;
+      for (int pr = cluster_id; pr < n_pairs; pr += n_clusters) {
+        int tm, n0;
+        tile_of(pr, tm, n0);
+        const int tile_nv = tm / p.tiles_t;
+        const int t0 = (tm - tile_nv * p.tiles_t) * p.tt;
+        const int nv0 = tile_nv * p.vv;
+        int kw = 0;
+        for (int s = 0; s < p.n_slabs; ++s) {
+          const int ts = t0 * p.t_mul[s] + p.t_off[s];
+          for (int c = 0; c < p.chunks[s]; ++c, ++kw) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_pair);
+            else mbar_arrive_cluster(full_leader);
+            uint8_t* sa = ring + (size_t)stage * stage_bytes;
+            tma_load_3d_2sm(sa, &p.map_a[s], full_leader, c * kChunkK, ts, nv0);
+            tma_load_2d_2sm(sa + kABytes, &p.map_w, full_leader, kw * kChunkK, n0 + (int)rank * (BN / 2));
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: leader CTA only =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN);
+      const bool leader = lane == 0;
+      const uint32_t ring_u32 = smem_u32(ring);
+      const uint64_t desc_hi = make_smem_desc_kmajor_sw128(0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      const int total_chunks = p.total_chunks;
+      for (int pr = cluster_id; pr < n_pairs; pr += n_clusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);          // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kc = 0; kc < total_chunks; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = ring_u32 + (uint32_t)stage * (uint32_t)stage_bytes;
+          const uint64_t da = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
+          const uint64_t db = desc_hi | (uint64_t)(((sa + kABytes) >> 4) & 0x3FFF);
+          if (leader) {
+#pragma unroll
+            for (int k = 0; k < kChunkK / 16; ++k)
+              umma_bf16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage]);              // frees this ring slot in both CTAs
+          }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        if (leader) umma_commit_2sm(&tmem_full[acc]);        // accumulator complete -> both epilogues
+        __syncwarp();
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp == 2 + kEpiWarps) {
+    // ===================== TMA-store warp =====================
+    if (lane == 0 && p.tma_store) {
+      int sbuf = 0; uint32_t sphase = 0;
+      int prev = -1;
+      for (int pr = cluster_id; pr < n_pairs; pr += n_clusters) {
+        int tm, n0;
+        tile_of(pr, tm, n0);
+        const int tile_nv = tm / p.tiles_t, tile_t = tm - tile_nv * p.tiles_t;
+        mbar_wait(&stage_full[sbuf], sphase);
+        for (int c = 0; c < BN / 64; ++c)
+          tma_store_3d(&p.map_out, s_stage + ((size_t)sbuf * (BN / 64) + c) * kABytes, n0 + c * 64, tile_t * p.tt, tile_nv * p.vv);
+        tma_store_commit();
+        if (p.stage_bufs == 2) {
+          tma_store_wait_read1();
+          if (prev >= 0) mbar_arrive(&stage_empty[prev]);
+          prev = sbuf;
+          if (++sbuf == 2) { sbuf = 0; sphase ^= 1; }
+        } else {
+          tma_store_wait_read0();
+          mbar_arrive(&stage_empty[0]);
+          sphase ^= 1;
+        }
+      }
+      tma_store_wait0();
+    }
+  } else {
+    // ===================== epilogue (both CTAs, each its own 128 rows): as rowgemm_umma_kernel =====================
+    constexpr int CW = BN / 4;
+    const int lane_grp = warp & 3;
+    const int cq = (warp - 2) >> 2;
+    const int r = lane_grp * 32 + lane;
+    const int nv_l = r / p.tt, t_l = r - nv_l * p.tt;
+    int acc = 0; uint32_t acc_phase = 0;
+    int sbuf = 0; uint32_t sphase = 0;
+    for (int pr = cluster_id; pr < n_pairs; pr += n_clusters) {
+      int tm, n0;
+      tile_of(pr, tm, n0);
+      const int tile_nv = tm / p.tiles_t, tile_t = tm - tile_nv * p.tiles_t;
+      const int t = tile_t * p.tt + t_l;
+      const int nv = tile_nv * p.vv + nv_l;
+      const bool valid = (nv_l < p.vv) && (nv < (int)p.nv) && (t < p.t_out) && (tm < (int)p.tiles_m);
+      const int n = nv / p.v, node = nv - n * p.v;
+      const int64_t row = (int64_t)nv * p.t_out + t;
+      const int cb = cq * CW;
+      const float* bias = s_bias + (p.bias_per_node ? (valid ? node : 0) * (p.c_out + 4) : 0) + n0 + cb;
+      int64_t out_off;
+      if (p.out_layout == TIK_OUT_NODE_MAJOR) out_off = row * p.c_out + n0 + cb;
+      else if (p.out_layout == TIK_OUT_TIME_MAJOR) out_off = (((int64_t)n * p.t_out + t) * p.v + node) * (int64_t)p.c_out + n0 + cb;
+      else out_off = row * p.c_out_valid + n0 + cb;
+      uint8_t* stage_row = s_stage + (size_t)sbuf * (BN / 64) * kABytes + (size_t)r * 128;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN + cb) + ((uint32_t)(lane_grp * 32) << 16);
+      uint32_t a[CW];
+#pragma unroll
+      for (int i = 0; i < CW / 16; ++i) tmem_ld16(tmem_d + (uint32_t)(16 * i), a + 16 * i);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));   // the leader's barrier counts both CTAs
+      if (p.tma_store) mbar_wait(&stage_empty[sbuf], sphase ^ 1);
+      if (valid || p.tma_store) {
+#pragma unroll
+        for (int q = 0; q < CW / 8; ++q) {
+          const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * q);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * q + 4);
+          float v[8] = {__uint_as_float(a[8 * q + 0]) + b0.x, __uint_as_float(a[8 * q + 1]) + b0.y,
+                        __uint_as_float(a[8 * q + 2]) + b0.z, __uint_as_float(a[8 * q + 3]) + b0.w,
+                        __uint_as_float(a[8 * q + 4]) + b1.x, __uint_as_float(a[8 * q + 5]) + b1.y,
+                        __uint_as_float(a[8 * q + 6]) + b1.z, __uint_as_float(a[8 * q + 7]) + b1.w};
+          if (ACT == TIK_ACT_LEAKY) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * p.slope;
+          }
+          if (p.out_layout == TIK_OUT_ROWS_F32) {
+            float* o = reinterpret_cast<float*>(p.out) + out_off + 8 * q;
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (valid && n0 + cb + 8 * q + e < p.c_out_valid) o[e] = (ACT == TIK_ACT_RELU) ? fmaxf(v[e], 0.f) : v[e];
+          } else {
+            uint4 u;
+            if (ACT == TIK_ACT_RELU) {
+              u.x = pack_bf16x2_relu(v[0], v[1]); u.y = pack_bf16x2_relu(v[2], v[3]);
+              u.z = pack_bf16x2_relu(v[4], v[5]); u.w = pack_bf16x2_relu(v[6], v[7]);
+            } else {
+              u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+              u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+            }
+            if (p.tma_store) {
+              const int col = cb + 8 * q;
+              const int j = (col & 63) >> 3;
+              *reinterpret_cast<uint4*>(stage_row + (size_t)(col >> 6) * kABytes + ((j ^ (r & 7)) << 4)) = u;
+            } else if (valid) {
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + 8 * q) = u;
+            }
+          }
+        }
+      }
+      if (p.tma_store) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stage_full[sbuf]);
+        if (p.stage_bufs == 2) { if (++sbuf == 2) { sbuf = 0; sphase ^= 1; } } else { sphase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                       // no CTA leaves while its peer may still signal its barriers / read its smem
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ weight-stationary variant
@@ -824,13 +1070,30 @@ int umma_prepare(const TikRowGemm* d, int64_t nv_capacity, UmmaPrepared** out) {
       }
     }
   }
+  // CTA-pair kernel for the 256-column layers whose weights have to be streamed: ring stage = A chunk + half a W chunk
+  // EXPERIMENT, opt-in (TIK_2CTA=1): parity-green but slower than one CTA per tile today (b6 temporal conv 418 vs
+  // 269 us, head 131 vs 84 us; profiles/r1_notes.md) -- one K chunk per cross-CTA hand-off is too fine-grained
+  p.two_cta = (!p.ts && u->bn == 256 && !w_res && d->res_kind == TIK_RES_NONE && getenv("TIK_2CTA")) ? 1 : 0;
+  if (p.two_cta) {
+    group = 1;
+    sbufs = 2;
+    int fit = (kSmemBudget - bar_bytes - bias_bytes - sbufs * one_stage_tile) / (kABytes + b_bytes / 2);
+    if (fit < 4) { sbufs = 1; fit = (kSmemBudget - bar_bytes - bias_bytes - one_stage_tile) / (kABytes + b_bytes / 2); }
+    stages = fit > kMaxStages ? kMaxStages : fit;
+    uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d->c_out};
+    uint64_t strides[1] = {(uint64_t)ktot * 2};
+    uint32_t box[2] = {(uint32_t)kChunkK, (uint32_t)(u->bn / 2)};
+    uint32_t estr[2] = {1, 1};
+    int rc = encode_map(&p.map_w, d->w_dev, 2, dims, strides, box, estr);
+    if (rc != TIK_OK) { delete u; return rc; }
+  }
   p.group = group;
   p.stage_bufs = sbufs;
   const int stage_out_bytes = sbufs * one_stage_tile;
   if (stages < 2) { delete u; set_error("bf16 path: bias table too large for shared memory"); return TIK_ERR_UNSUPPORTED; }
   p.w_resident = w_res; p.stages = stages;
   p.off_ring = (w_res && !p.ts) ? w_bytes : 0;
-  p.off_stage = p.off_ring + stages * group * (kABytes + (w_res ? 0 : b_bytes));
+  p.off_stage = p.off_ring + stages * group * (kABytes + (w_res ? 0 : (p.two_cta ? b_bytes / 2 : b_bytes)));
   p.off_bias = p.off_stage + stage_out_bytes;
   p.off_bar = p.off_bias + bias_bytes;
   if (p.tma_store) {
@@ -874,6 +1137,25 @@ int umma_launch(UmmaPrepared* u, const TikRowGemm* d, cudaStream_t s) {
     if (d->act == TIK_ACT_LEAKY) return launch_variant<BN_, TIK_ACT_LEAKY>(p, u->smem_bytes, grid, s);  \
     return launch_variant<BN_, TIK_ACT_NONE>(p, u->smem_bytes, grid, s);                              \
   } while (0)
+  if (p.two_cta) {
+    static int attr2[64] = {};
+    int dev = 0;
+    TIK_CUDA(cudaGetDevice(&dev));
+    if (!attr2[dev & 63]) {
+      TIK_CUDA(cudaFuncSetAttribute(rowgemm_umma2_kernel<TIK_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048));
+      TIK_CUDA(cudaFuncSetAttribute(rowgemm_umma2_kernel<TIK_ACT_LEAKY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048));
+      TIK_CUDA(cudaFuncSetAttribute(rowgemm_umma2_kernel<TIK_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048));
+      attr2[dev & 63] = 1;
+    }
+    TIK_CHECK_ARG(d->res_kind == TIK_RES_NONE, "CTA-pair kernel: residual changed after prepare");
+    const int64_t n_pairs = ((p.tiles_m + 1) / 2) * p.n_tiles_n;
+    const unsigned grid2 = 2u * (unsigned)std::min<int64_t>(n_pairs, num_sms() / 2);
+    if (d->act == TIK_ACT_RELU) rowgemm_umma2_kernel<TIK_ACT_RELU><<<grid2, kUmmaThreads, u->smem_bytes, s>>>(p);
+    else if (d->act == TIK_ACT_LEAKY) rowgemm_umma2_kernel<TIK_ACT_LEAKY><<<grid2, kUmmaThreads, u->smem_bytes, s>>>(p);
+    else rowgemm_umma2_kernel<TIK_ACT_NONE><<<grid2, kUmmaThreads, u->smem_bytes, s>>>(p);
+    TIK_LAUNCH_CHECK();
+    return TIK_OK;
+  }
   if (p.ts) {
     static int ts_attr[64] = {};
     int dev = 0;
