@@ -409,8 +409,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
 // Barriers: the ring's "full" barrier lives in the leader and counts the bytes of all four TMA loads of a stage
 // (cta_group::2 loads may signal the peer's barrier); "empty" and "accumulator full" are committed to both CTAs
 // (multicast commit); the peer's epilogue warps arrive remotely on the leader's "accumulator empty".
-// STATUS: experiment (TIK_2CTA=1).  Results match the one-CTA kernel, but with one K chunk per cross-CTA hand-off it
-// is 1.1-1.7x slower; it needs multi-chunk stages before it can pay.
+// STATUS: experiment (TIK_2CTA=1).  Results match the one-CTA kernel; a cross-CTA hand-off costs about twice a local
+// one, and with the two K chunks per stage that fit beside the staging tile it is still 0-25 % slower.
 template <int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1) rowgemm_umma2_kernel(const __grid_constant__ UmmaParams p) {
   constexpr int BN = 256;
@@ -433,7 +433,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1) row
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = (int)blockIdx.x >> 1, n_clusters = (int)gridDim.x >> 1;
   const int stages = p.stages;
-  const int stage_bytes = kABytes + kBHalf;
+  const int group = p.group;                                // K chunks per ring stage (one cross-CTA hand-off per stage)
+  const int chunk_bytes = kABytes + kBHalf;
+  const int stage_bytes = group * chunk_bytes;
   const int ntn = p.n_tiles_n;
   const int pairs_m = (int)((p.tiles_m + 1) / 2);
   const int n_pairs = pairs_m * ntn;
@@ -468,6 +470,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1) row
     // ===================== TMA producer (both CTAs): own A chunk + own half of the W chunk =====================
     if (lane == 0) {
       const uint32_t tx_pair = 2u * (uint32_t)(p.a_box_bytes + kBHalf);
+      const int total_chunks = p.total_chunks;
       int stage = 0; uint32_t phase = 0;
       for (int pr = cluster_id; pr < n_pairs; pr += n_clusters) {
         int tm, n0;
@@ -475,18 +478,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1) row
         const int tile_nv = tm / p.tiles_t;
         const int t0 = (tm - tile_nv * p.tiles_t) * p.tt;
         const int nv0 = tile_nv * p.vv;
-        int kw = 0;
+        int kw = 0, j = 0;
+        uint32_t full_leader = 0;
         for (int s = 0; s < p.n_slabs; ++s) {
           const int ts = t0 * p.t_mul[s] + p.t_off[s];
           for (int c = 0; c < p.chunks[s]; ++c, ++kw) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_pair);
-            else mbar_arrive_cluster(full_leader);
-            uint8_t* sa = ring + (size_t)stage * stage_bytes;
+            if (j == 0) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              const int in_stage = min(group, total_chunks - kw);
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_pair * (uint32_t)in_stage);
+              else mbar_arrive_cluster(full_leader);
+            }
+            uint8_t* sa = ring + (size_t)stage * stage_bytes + (size_t)j * chunk_bytes;
             tma_load_3d_2sm(sa, &p.map_a[s], full_leader, c * kChunkK, ts, nv0);
             tma_load_2d_2sm(sa + kABytes, &p.map_w, full_leader, kw * kChunkK, n0 + (int)rank * (BN / 2));
-            if (++stage == stages) { stage = 0; phase ^= 1; }
+            if (++j == group || kw + 1 == total_chunks) {
+              j = 0;
+              if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
           }
         }
       }
@@ -505,18 +515,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1) row
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);          // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kc = 0; kc < total_chunks; ++kc) {
+        for (int kc = 0; kc < total_chunks; kc += group) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = ring_u32 + (uint32_t)stage * (uint32_t)stage_bytes;
-          const uint64_t da = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
-          const uint64_t db = desc_hi | (uint64_t)(((sa + kABytes) >> 4) & 0x3FFF);
-          if (leader) {
+          const int in_stage = min(group, total_chunks - kc);
+          for (int j = 0; j < in_stage; ++j) {
+            const uint32_t sa = ring_u32 + (uint32_t)stage * (uint32_t)stage_bytes + (uint32_t)j * (uint32_t)chunk_bytes;
+            const uint64_t da = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
+            const uint64_t db = desc_hi | (uint64_t)(((sa + kABytes) >> 4) & 0x3FFF);
+            if (leader) {
 #pragma unroll
-            for (int k = 0; k < kChunkK / 16; ++k)
-              umma_bf16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
-            umma_commit_2sm(&empty_bar[stage]);              // frees this ring slot in both CTAs
+              for (int k = 0; k < kChunkK / 16; ++k)
+                umma_bf16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | j | k) != 0 ? 1u : 0u);
+            }
           }
+          if (leader) umma_commit_2sm(&empty_bar[stage]);    // frees this ring stage in both CTAs
           __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
@@ -1071,15 +1084,17 @@ int umma_prepare(const TikRowGemm* d, int64_t nv_capacity, UmmaPrepared** out) {
     }
   }
   // CTA-pair kernel for the 256-column layers whose weights have to be streamed: ring stage = A chunk + half a W chunk
-  // EXPERIMENT, opt-in (TIK_2CTA=1): parity-green but slower than one CTA per tile today (b6 temporal conv 418 vs
-  // 269 us, head 131 vs 84 us; profiles/r1_notes.md) -- one K chunk per cross-CTA hand-off is too fine-grained
+  // EXPERIMENT, opt-in (TIK_2CTA=1): parity-green but slower than one CTA per tile today (b6 temporal conv 324 vs
+  // 269 us, head 98 vs 84 us with two chunks per hand-off; profiles/r1_notes.md)
   p.two_cta = (!p.ts && u->bn == 256 && !w_res && d->res_kind == TIK_RES_NONE && getenv("TIK_2CTA")) ? 1 : 0;
   if (p.two_cta) {
-    group = 1;
     sbufs = 2;
     int fit = (kSmemBudget - bar_bytes - bias_bytes - sbufs * one_stage_tile) / (kABytes + b_bytes / 2);
     if (fit < 4) { sbufs = 1; fit = (kSmemBudget - bar_bytes - bias_bytes - one_stage_tile) / (kABytes + b_bytes / 2); }
-    stages = fit > kMaxStages ? kMaxStages : fit;
+    group = env_g ? atoi(env_g) : 2;                      // chunks per cross-CTA hand-off
+    if (group < 1) group = 1;
+    while (group > 1 && fit / group < 2) group >>= 1;
+    stages = fit / group > kMaxStages ? kMaxStages : fit / group;
     uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d->c_out};
     uint64_t strides[1] = {(uint64_t)ktot * 2};
     uint32_t box[2] = {(uint32_t)kChunkK, (uint32_t)(u->bn / 2)};
