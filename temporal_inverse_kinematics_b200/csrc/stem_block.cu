@@ -51,8 +51,11 @@ constexpr int kSbOffBias1 = kSbOffH + 2 * kSbHBytes;
 constexpr int kSbBiasLd = kSbCout + 4;               // padded pitch: rows of different nodes start in different banks
 constexpr int kSbOffBias2 = kSbOffBias1 + kSbMaxV * kSbBiasLd * 4;
 constexpr int kSbOffAs = kSbOffBias2 + kSbMaxV * kSbBiasLd * 4;           // As[u][v][c] = A^[u,v] * s0[u,c]   (V*V*Cin fp32)
-constexpr int kSbOffNbr = kSbOffAs + kSbMaxV * kSbMaxV * 4 * 4;           // per node: count + source-node offsets of the non-zero A^[u,v]
-constexpr int kSbOffCst = kSbOffNbr + kSbMaxV * (kSbMaxV + 1) * 4;         // cst[v][c] = sum_u A^[u,v] o0[u,c]; sum[v][c] = sum_u As; scale[v][c]
+constexpr int kSbNbrLd = 20;                        // neighbour list pitch (ints): lists are read 4 entries at a time
+constexpr int kSbAsLd = 20 * 4;                     // weight row pitch (floats) for CIN <= 4, 16-byte aligned per node
+constexpr int kSbOffNbr = kSbOffAs + kSbMaxV * kSbAsLd * 4;             // per node: source-node offsets of the non-zero A^[u,v], zero padded
+constexpr int kSbOffCnt = kSbOffNbr + kSbMaxV * kSbNbrLd * 4;           // per node: number of 4-entry groups
+constexpr int kSbOffCst = kSbOffCnt + kSbMaxV * 4 + 8;         // cst[v][c] = sum_u A^[u,v] o0[u,c]; sum[v][c] = sum_u As; scale[v][c]
 constexpr int kSbRawBufs = 3;                                           // raw keypoint tiles in flight (cp.async)
 constexpr int kSbOffRaw = kSbOffCst + 3 * kSbMaxV * 4 * 4;              // kSbRawBufs x 14 x V*Cin fp32
 constexpr int kSbOffBar = (kSbOffRaw + kSbRawBufs * kSbL * kSbMaxV * 4 * 4 + 15) / 16 * 16;
@@ -90,7 +93,8 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
   float* s_bias1 = reinterpret_cast<float*>(smem + kSbOffBias1);
   float* s_bias2 = reinterpret_cast<float*>(smem + kSbOffBias2);
   float* s_as = reinterpret_cast<float*>(smem + kSbOffAs);
-  int* s_nbr = reinterpret_cast<int*>(smem + kSbOffNbr);   // [v][0] = count, [v][1 + k] = u_k * CIN
+  int* s_nbr = reinterpret_cast<int*>(smem + kSbOffNbr);   // [v][k] = u_k * CIN, padded with 0 (weight 0) to a multiple of 4
+  int* s_cnt4 = reinterpret_cast<int*>(smem + kSbOffCnt);  // [v] = groups of 4 neighbours
   float* s_cst = reinterpret_cast<float*>(smem + kSbOffCst);
   float* s_sum = s_cst + kSbMaxV * 4;
   float* s_scale = s_sum + kSbMaxV * 4;
@@ -136,12 +140,17 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
     for (int u = 0; u < V; ++u) {
       const float a = __ldg(p.agg + u * V + v);
       if (a != 0.f) {
-        s_nbr[v * (kSbMaxV + 1) + 1 + cnt] = u * CIN;
-        for (int c = 0; c < CIN; ++c) s_as[(v * kSbMaxV + cnt) * CIN + c] = a * __ldg(p.in_scale + u * CIN + c);
+        s_nbr[v * kSbNbrLd + cnt] = u * CIN;
+        for (int c = 0; c < CIN; ++c) s_as[v * kSbAsLd + cnt * CIN + c] = a * __ldg(p.in_scale + u * CIN + c);
         ++cnt;
       }
     }
-    s_nbr[v * (kSbMaxV + 1)] = cnt;
+    const int cnt4 = (cnt + 3) / 4;
+    for (int k = cnt; k < cnt4 * 4; ++k) {                   // padding entries: node 0 with weight 0
+      s_nbr[v * kSbNbrLd + k] = 0;
+      for (int c = 0; c < CIN; ++c) s_as[v * kSbAsLd + k * CIN + c] = 0.f;
+    }
+    s_cnt4[v] = cnt4;
   }
   for (int i = threadIdx.x; i < VC; i += kSbThreads) {
     const int v = i / CIN, c = i - v * CIN;
@@ -351,27 +360,33 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
     // so no bulk copy); one thread then builds one tile row.
     constexpr int NB = 32 * kSbBuildWarps;
     const int tid = threadIdx.x - 32 * (2 + kSbEpiWarps);
+    // this thread's (at most 3) elements of a raw tile: frame l and offset vc inside the frame never change
+    int el_l[3], el_vc[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int idx = tid + k * NB;
+      el_l[k] = idx < kSbL * VC ? idx / VC : -1;
+      el_vc[k] = idx - (idx / VC) * VC;
+    }
     auto prefetch = [&](int it) {
       if (it < my_tiles) {
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
         const int n = tile / p.tiles_t, tt = tile - n * p.tiles_t;
         const int t_first = tt * p.lo - 1;
-        float* dst = s_rawbuf + (it % kSbRawBufs) * (kSbL * kSbMaxV * 4);
-        for (int idx = tid; idx < kSbL * VC; idx += NB) {
-          const int l = idx / VC, vc = idx - l * VC;
-          const int t = t_first + l;
-          const bool ok = t >= 0 && t < p.T;
-          long long fi;
-          if (p.win.frames > 0) {
+        const uint32_t dst = smem_u32(s_rawbuf + (it % kSbRawBufs) * (kSbL * kSbMaxV * 4)) + (uint32_t)tid * 4u;
+        const long long base = p.win.frames > 0 ? (p.win_n0 + (long long)n) * p.win.stride + p.win.offset : (long long)n * p.T;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          if (el_l[k] >= 0) {
+            const int t = t_first + el_l[k];
+            const bool ok = t >= 0 && t < p.T;
+            long long fi = base + t;
             // window mode: clip n is a window of one resident sequence (F,V,C); frame = clamp(n*stride + t + offset),
             // i.e. sample_window's edge padding (data_amass.py:18-42)
-            fi = (p.win_n0 + (long long)n) * p.win.stride + t + p.win.offset;
-            fi = fi < 0 ? 0 : (fi >= p.win.frames ? p.win.frames - 1 : fi);
-          } else {
-            fi = (long long)n * p.T + t;
+            if (p.win.frames > 0) fi = fi < 0 ? 0 : (fi >= p.win.frames ? p.win.frames - 1 : fi);
+            const float* src = ok ? p.x + fi * VC + el_vc[k] : p.x;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + (uint32_t)(k * NB) * 4u), "l"(src), "r"(ok ? 4 : 0) : "memory");
           }
-          const float* src = ok ? p.x + fi * VC + vc : p.x;
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst + idx)), "l"(src), "r"(ok ? 4 : 0) : "memory");
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -402,12 +417,22 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
           agg[c] = s_cst[v * CIN + c] - root[c] * s_sum[v * CIN + c];
           xs[c] = (fr[v * CIN + c] - root[c]) * s_scale[v * CIN + c];
         }
-        const int* nbr = s_nbr + v * (kSbMaxV + 1);
-        const int cnt = nbr[0];
-        for (int k = 0; k < cnt; ++k) {
-          const float* xu = fr + nbr[1 + k];
+        // four neighbours per step: one 16-byte load of their offsets, then independent weight / value loads, so the
+        // shared-memory latencies overlap instead of chaining (the port is contended by the running tap MMAs)
+        const int cnt4 = s_cnt4[v];
+        for (int g4 = 0; g4 < cnt4; ++g4) {
+          const int4 off = *reinterpret_cast<const int4*>(s_nbr + v * kSbNbrLd + 4 * g4);
+          const float* wv = s_as + v * kSbAsLd + 4 * g4 * CIN;
+          const int o[4] = {off.x, off.y, off.z, off.w};
+          float w[4][CIN], xv[4][CIN];
 #pragma unroll
-          for (int c = 0; c < CIN; ++c) agg[c] = fmaf(s_as[(v * kSbMaxV + k) * CIN + c], xu[c], agg[c]);
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) { w[k][c] = wv[k * CIN + c]; xv[k][c] = fr[o[k] + c]; }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) agg[c] = fmaf(w[k][c], xv[k][c], agg[c]);
         }
         if (it == 4 && tid == 0) SB_T(25);
         // slots: [agg_hi(CIN) | agg_lo(CIN) | xs_hi(CIN) | xs_lo(CIN) | 0...]
