@@ -80,12 +80,15 @@ __global__ void __launch_bounds__(kThThreads, 1) tcn_halo_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_w = tmem_base;                        // ktot/2 columns of bf16 pairs, lane = output channel
   const uint32_t tmem_acc = tmem_base + (uint32_t)(p.ktot / 2);
-  // ---- weights -> tensor memory (once per CTA): warps 2-5 cover the 128 lanes (zero rows beyond c_out)
-  if (warp >= 2 && warp < 6) {
+  // ---- weights -> tensor memory (once per CTA; zero rows beyond c_out): the 16 epilogue warps share the work, four
+  // per TMEM lane quadrant, each taking a quarter of the K range
+  if (warp >= 2 && warp < 2 + kThEpiWarps) {
     const int co = (warp & 3) * 32 + lane;
+    const int part = (warp - 2) >> 2;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const uint4* wrow = reinterpret_cast<const uint4*>(p.w + (size_t)(co < p.c_out ? co : 0) * p.ktot);
-    for (int k8 = 0; k8 < p.ktot / 16; k8 += 4) {
+    const int n16 = p.ktot / 16;
+    for (int k8 = part * 4; k8 < n16; k8 += 16) {
       uint4 v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = co < p.c_out ? __ldg(wrow + 2 * k8 + u) : make_uint4(0, 0, 0, 0);
