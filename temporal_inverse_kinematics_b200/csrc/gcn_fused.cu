@@ -120,6 +120,8 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();                                               // adjacency / weights / bias are constants; X comes from the previous kernel
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -379,6 +381,8 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_pair_kernel(const __g
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();                                               // adjacency / weights / bias are constants; X comes from the previous kernel
 
   // tile coordinates of pair `it`, slot h (a trailing odd tile is loaded twice and stored once)
   auto tile_of = [&](int it, int h, int& n, int& t0, bool& valid) {
@@ -671,8 +675,7 @@ static int gf_launch_variant(const GcnFusedPrepared* g, unsigned grid, cudaStrea
     TIK_CUDA(cudaFuncSetAttribute(gcn_fused_kernel<CIN, COUT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_done[dev & 63] = true;
   }
-  gcn_fused_kernel<CIN, COUT><<<grid, kGfThreads, g->smem_bytes, s>>>(g->p);
-  TIK_LAUNCH_CHECK();
+  TIK_CUDA(launch_pdl(gcn_fused_kernel<CIN, COUT>, grid, kGfThreads, (size_t)g->smem_bytes, s, g->p));
   return TIK_OK;
 }
 
@@ -686,8 +689,7 @@ static int gf_launch_pair(const GcnFusedPrepared* g, unsigned grid, cudaStream_t
     TIK_CUDA(cudaFuncSetAttribute(gcn_fused_pair_kernel<COUT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_done[dev & 63] = true;
   }
-  gcn_fused_pair_kernel<COUT><<<grid, kGfThreads, g->smem_bytes, s>>>(g->p);
-  TIK_LAUNCH_CHECK();
+  TIK_CUDA(launch_pdl(gcn_fused_pair_kernel<COUT>, grid, kGfThreads, (size_t)g->smem_bytes, s, g->p));
   return TIK_OK;
 }
 

@@ -19,6 +19,12 @@ namespace tik {
 
 static thread_local char g_err[512] = "";
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("TIK_NO_PDL") ? 0 : 1;
+  return v != 0;
+}
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

@@ -166,6 +166,8 @@ __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();                                               // tables above are constants; x may come from a previous kernel
   if (threadIdx.x == 0) SB_T(0);
 
   if (warp == 0) {
@@ -580,8 +582,7 @@ int stem_block_launch(StemBlockPrepared* g, const float* x, int64_t n_clips, con
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = n_clips * p.tiles_t;
   const unsigned grid = (unsigned)std::min<int64_t>(tiles, sms);
-  stem_block_kernel<3><<<grid, kSbThreads, kSbSmemBytes, s>>>(p);
-  TIK_LAUNCH_CHECK();
+  TIK_CUDA(launch_pdl(stem_block_kernel<3>, grid, kSbThreads, (size_t)kSbSmemBytes, s, p));
   return TIK_OK;
 }
 

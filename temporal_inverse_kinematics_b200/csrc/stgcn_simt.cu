@@ -49,6 +49,8 @@ aggregate_kernel(const T* __restrict__ x, const float* __restrict__ agg, T* __re
   __shared__ float s_agg[5 * V * V];
   for (int i = threadIdx.x; i < K * V * V; i += kAggThreads) s_agg[i] = __ldg(agg + i);
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();                                               // x comes from the previous kernel
   constexpr int VN = Vec16<T>::N;
   const int cv = C / VN;                      // channel vectors per row
   const int64_t total = N * Tn * cv;
@@ -256,9 +258,8 @@ static int launch_agg_v(const void* x, const float* agg, void* out, int64_t N, i
     TIK_CUDA(cudaFuncSetAttribute(aggregate_kernel<T, V>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     carve[dev & 63] = true;
   }
-  aggregate_kernel<T, V><<<(unsigned)blocks, kAggThreads, 0, s>>>(reinterpret_cast<const T*>(x), agg,
-                                                                   reinterpret_cast<T*>(out), N, Tn, C, K);
-  TIK_LAUNCH_CHECK();
+  TIK_CUDA(launch_pdl(aggregate_kernel<T, V>, (unsigned)blocks, kAggThreads, (size_t)0, s, reinterpret_cast<const T*>(x), agg,
+                      reinterpret_cast<T*>(out), N, Tn, C, K));
   return TIK_OK;
 }
 

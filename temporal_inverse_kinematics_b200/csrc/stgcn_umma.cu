@@ -137,6 +137,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();                                  // the next kernel may begin its own prologue
+  pdl_wait();                                               // everything below reads what the previous kernel wrote
   if (threadIdx.x == 0) TIK_T(1);
 
   if (warp == 0) {
@@ -731,6 +733,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_ts_kernel(const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();                                               // weights are constants; activations come from the previous kernel
 
   if (warp == 0) {
     // ===================== TMA producer: activation chunks only =====================
@@ -976,8 +980,7 @@ static int launch_variant(const UmmaParams& p, int smem_bytes, unsigned grid, cu
     TIK_CUDA(cudaFuncSetAttribute(rowgemm_umma_kernel<BN, ACT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_done[dev & 63] = kSmemBudget + 2048;
   }
-  rowgemm_umma_kernel<BN, ACT><<<grid, kUmmaThreads, smem_bytes, s>>>(p);
-  TIK_LAUNCH_CHECK();
+  TIK_CUDA(launch_pdl(rowgemm_umma_kernel<BN, ACT>, grid, kUmmaThreads, (size_t)smem_bytes, s, p));
   return TIK_OK;
 }
 
@@ -1185,10 +1188,9 @@ int umma_launch(UmmaPrepared* u, const TikRowGemm* d, cudaStream_t s) {
       ts_attr[dev & 63] = 1;
     }
     TIK_CHECK_ARG(d->res_kind == TIK_RES_NONE && !d->bias_per_node, "weight-stationary kernel: residual / per-node bias changed after prepare");
-    if (d->act == TIK_ACT_RELU) rowgemm_ts_kernel<TIK_ACT_RELU><<<grid, kUmmaThreads, u->smem_bytes, s>>>(p);
-    else if (d->act == TIK_ACT_LEAKY) rowgemm_ts_kernel<TIK_ACT_LEAKY><<<grid, kUmmaThreads, u->smem_bytes, s>>>(p);
-    else rowgemm_ts_kernel<TIK_ACT_NONE><<<grid, kUmmaThreads, u->smem_bytes, s>>>(p);
-    TIK_LAUNCH_CHECK();
+    if (d->act == TIK_ACT_RELU) TIK_CUDA(launch_pdl(rowgemm_ts_kernel<TIK_ACT_RELU>, grid, kUmmaThreads, (size_t)u->smem_bytes, s, p));
+    else if (d->act == TIK_ACT_LEAKY) TIK_CUDA(launch_pdl(rowgemm_ts_kernel<TIK_ACT_LEAKY>, grid, kUmmaThreads, (size_t)u->smem_bytes, s, p));
+    else TIK_CUDA(launch_pdl(rowgemm_ts_kernel<TIK_ACT_NONE>, grid, kUmmaThreads, (size_t)u->smem_bytes, s, p));
     return TIK_OK;
   }
   if (u->bn == 64) TIK_LAUNCH_BN(64);

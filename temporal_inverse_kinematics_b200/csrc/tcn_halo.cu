@@ -103,6 +103,8 @@ __global__ void __launch_bounds__(kThThreads, 1) tcn_halo_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();                                               // weights are constants; H and X come from the previous kernels
 
   if (warp == 0) {
     // ===================== TMA producer: one stage = one tile =====================
@@ -337,8 +339,7 @@ int tcn_halo_launch(TcnHaloPrepared* g, int64_t nv, cudaStream_t s) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)std::min<int64_t>(p.n_tiles, sms);
-  tcn_halo_kernel<<<grid, kThThreads, g->smem_bytes, s>>>(p);
-  TIK_LAUNCH_CHECK();
+  TIK_CUDA(launch_pdl(tcn_halo_kernel, grid, kThThreads, (size_t)g->smem_bytes, s, p));
   return TIK_OK;
 }
 

@@ -42,6 +42,30 @@ void set_error(const char* fmt, ...);
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch: a kernel launched this way may start (and run its prologue: barrier init, tensor-
+// memory allocation, constant operands to TMEM / shared memory) while its predecessor in the stream is still draining;
+// it must execute pdl_wait() before it touches anything the predecessor wrote.  Captured as a programmatic edge in
+// CUDA graphs.  TIK_NO_PDL=1 falls back to ordinary stream order.
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // internal entry points shared between translation units
 int rowgemm_f32(const TikRowGemm* d, cudaStream_t s);
 int rowgemm_bf16(const TikRowGemm* d, cudaStream_t s);
