@@ -241,3 +241,17 @@ def test_bf16_kernel_variants_agree(monkeypatch, switch):
     assert float((fast - want).abs().max()) < TOL_BF16_ABS
     assert float((slow - want).abs().max()) < TOL_BF16_ABS
     assert float((fast - slow).abs().max()) < 0.06
+
+
+@pytest.mark.parametrize("n,t", [(1, 1), (1, 2), (2, 11), (1, 12), (2, 13), (3, 25), (7, 33), (2, 61), (1, 65), (2, 95),
+                                 (1, 100), (2, 126), (1, 127), (1, 129), (1, 190), (1, 200), (33, 16)])
+def test_bf16_edge_shapes(n, t):
+    """Tile-boundary cases of the specialised kernels: 12 output frames per tile in the fused first block, G row groups
+    of T+2 rows per tile in the halo temporal conv (unsupported above 126 / 190 frames -> per-tap kernels), odd tile
+    counts in the paired 64-channel graph conv, single clips and single frames (tools/shape_sweep.py has the long list)."""
+    m, sd = _model(dtype="bf16")
+    x = synth.make_clips(n, t, seed=1000 * n + t)
+    want = sp.regressor_forward(sd, x)["poses"]
+    got = m(x.cuda())["poses"].cpu()
+    assert got.shape == want.shape and torch.isfinite(got).all()
+    assert float((got - want).abs().max()) < TOL_BF16_ABS
