@@ -937,8 +937,11 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return TIK_ERR_CUDA;
   TIK_CHECK_ARG(((uintptr_t)base & 15) == 0, "TMA base address must be 16-byte aligned");
+  // A strided (stride-2) box over 128-byte rows skips every other row: do not let L2 promotion fetch the skipped rows
+  const bool skip_rows = rank > 1 && estr[1] > 1 && strides_bytes[0] <= 128;
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  skip_rows ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu,%llu box %u,%u,%u)", (int)r, rank,
