@@ -603,7 +603,9 @@ bool gcn_fused_supported(int cin, int cout, int V, int K) {
 }
 
 int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float* bias, void* out, int64_t n_clips, int T, int V,
-                      int cin, int cout, int relu, GcnFusedPrepared** outp) {
+                      int cin, int cout, int relu, GcnFusedPrepared** outp, int x_row, int out_row) {
+  if (x_row <= 0) x_row = cin;                             // channels per row of the tensors in memory: a launch may work on a
+  if (out_row <= 0) out_row = cout;                        // channel slice of wider activations
   TIK_CHECK_ARG(gcn_fused_supported(cin, cout, V, 1), "fused gcn: unsupported shape cin=%d cout=%d V=%d", cin, cout, V);
   TIK_CHECK_ARG(x && abd && w && bias && out && n_clips > 0 && T > 0, "fused gcn: bad arguments");
   GcnFusedPrepared* g = new GcnFusedPrepared();
@@ -617,13 +619,13 @@ int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float
   int rc = TIK_OK;
   {
     uint64_t dims[4] = {(uint64_t)cin, (uint64_t)T, (uint64_t)V, (uint64_t)n_clips};
-    uint64_t strides[3] = {(uint64_t)cin * 2, (uint64_t)cin * 2 * T, (uint64_t)cin * 2 * T * V};
+    uint64_t strides[3] = {(uint64_t)x_row * 2, (uint64_t)x_row * 2 * T, (uint64_t)x_row * 2 * T * V};
     uint32_t box[4] = {64, (uint32_t)p.ttg, (uint32_t)V, 1};
     rc = encode_bf16_map(&p.map_x, x, 4, dims, strides, box);
   }
   if (rc == TIK_OK) {
     uint64_t dims[4] = {(uint64_t)cout, (uint64_t)T, (uint64_t)V, (uint64_t)n_clips};
-    uint64_t strides[3] = {(uint64_t)cout * 2, (uint64_t)cout * 2 * T, (uint64_t)cout * 2 * T * V};
+    uint64_t strides[3] = {(uint64_t)out_row * 2, (uint64_t)out_row * 2 * T, (uint64_t)out_row * 2 * T * V};
     uint32_t box[4] = {64, (uint32_t)p.ttg, (uint32_t)V, 1};
     rc = encode_bf16_map(&p.map_out, out, 4, dims, strides, box);
   }
@@ -723,7 +725,7 @@ extern "C" int tik_gcn_fused(const void* x_dev, const void* abd_dev, const void*
                              int64_t N, int T, int V, int Cin, int Cout, int relu, void* stream) {
   using namespace tik;
   GcnFusedPrepared* g = nullptr;
-  int rc = gcn_fused_prepare(x_dev, abd_dev, w_dev, bias_dev, out_dev, N, T, V, Cin, Cout, relu, &g);
+  int rc = gcn_fused_prepare(x_dev, abd_dev, w_dev, bias_dev, out_dev, N, T, V, Cin, Cout, relu, &g, 0, 0);
   if (rc != TIK_OK) return rc;
   rc = gcn_fused_launch(g, N, (cudaStream_t)stream);
   gcn_fused_free(g);
