@@ -225,7 +225,7 @@ def test_bf16_forward_windows_equals_materialised_windows(win, offset, stride):
     assert float((got.cpu() - ref).abs().max()) < TOL_BF16_ABS
 
 
-@pytest.mark.parametrize("switch", ["TIK_NO_STEM_BLOCK", "TIK_NO_TS", "TIK_NO_FUSED_GCN", "TIK_NO_TCN_HALO", "TIK_2CTA"])
+@pytest.mark.parametrize("switch", ["TIK_NO_STEM_BLOCK", "TIK_NO_TS", "TIK_NO_FUSED_GCN", "TIK_NO_TC_AGG", "TIK_NO_TCN_HALO", "TIK_2CTA"])
 def test_bf16_kernel_variants_agree(monkeypatch, switch):
     """Every specialised tensor-core kernel has a more general one behind it (first block: stem + temporal conv;
     halo / weight-stationary temporal conv: per-tap TS kernel, then the SS-mode kernel; fused graph conv: aggregate +
