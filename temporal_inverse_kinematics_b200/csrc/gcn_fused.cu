@@ -5,8 +5,8 @@
 // Replaces the aggregate kernel + channel GEMM pair (gconv_origin.py:56-65 with the einsum moved in front of the
 // conv, st_gcn_aaai18.py:178-179), i.e. two full activation passes through HBM per block.
 //
-// A tile is 7 frames x 17 nodes of one clip = 119 rows (row r = v*7 + t_local), fetched as ONE 4-D TMA box
-// (64 channels, 7 frames, 17 nodes, 1 clip) per 64-channel slab of the node-major activations.
+// A tile is f <= 7 frames x 17 nodes of one clip (<= 119 rows, row r = v*f + t_local; f = gcn_fused_frames(T)), fetched
+// as ONE 4-D TMA box (64 channels, f frames, 17 nodes, 1 clip) per 64-channel slab of the node-major activations.
 //   MMA 1 (aggregation as a dense block-structured GEMM):   D1[128 x Cin] = Abd[128 x 128] . Xtile[128 x Cin]
 //          Abd[(w,t),(v,t')] = A^[v,w] * delta(t,t'), bf16, K-major, resident in shared memory;
 //          the X tile is used in place as the MN-major B operand (rows = K, channels contiguous).
@@ -17,6 +17,7 @@
 // aggregated tensor through HBM.  Warp roles: warp 0 TMA producer, warp 1 MMA issuer, 8 mid-pass warps and 8
 // final-pass warps (TMEM lane group x column half each), so tile i+1's mid pass overlaps tile i's final pass; D1 is
 // double buffered in tensor memory, D2 too when 2*(Cin+Cout) <= 512 columns.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -34,7 +35,7 @@ constexpr int kGfMaxBufs = 8;                      // input tiles in flight: the
 
 struct GcnFusedParams {
   CUtensorMap map_x, map_out, map_w;
-  int32_t n_clips, T, V, ttg, tiles_t;   // ttg = frames per tile (min(T, 7))
+  int32_t n_clips, T, V, ttg, tiles_t;   // ttg = frames per tile (gcn_fused_frames(T) <= 7)
   int32_t xbufs;                          // input tiles in flight
   int32_t sbufs;                          // staging tiles (2: the store of tile i-1 may still be reading while tile i is staged)
   int32_t off_w, off_x, off_stage, off_bias, off_bar;
@@ -597,6 +598,13 @@ struct GcnFusedPrepared {
   bool pair;                               // Cin = 64: two tiles per aggregation pass (gcn_fused_pair_kernel)
 };
 
+// Frames per tile: at most 7 (7 x 17 nodes = 119 of the 128 MMA rows), balanced over the ceil(T/7) tiles of a clip so
+// that the last tile re-does as few frames as possible (T=16: 3 tiles of 6, not 7+7+shifted 7; T=8: 2 tiles of 4).
+int gcn_fused_frames(int T) {
+  const int tiles = (T + 6) / 7;
+  return (T + tiles - 1) / tiles;
+}
+
 bool gcn_fused_supported(int cin, int cout, int V, int K) {
   if (K != 1 || V * 7 > 128 || V < 1) return false;
   return (cin == 64 && (cout == 64 || cout == 128)) || (cin == 128 && (cout == 128 || cout == 256));
@@ -613,7 +621,7 @@ int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float
   memset(&p, 0, sizeof(p));
   g->cin = cin; g->cout = cout;
   p.n_clips = (int32_t)n_clips; p.T = T; p.V = V;
-  p.ttg = T < 7 ? T : 7;
+  p.ttg = gcn_fused_frames(T);
   p.tiles_t = (T + p.ttg - 1) / p.ttg;
   p.bias = bias; p.relu = relu; p.abd = reinterpret_cast<const __nv_bfloat16*>(abd);
   int rc = TIK_OK;

@@ -307,7 +307,7 @@ int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int64_t
       P->chunk_steps.push_back(s);
     } else if (dtype == TIK_BF16 && gcn_fused_supported(b.c_in, b.c_out, V, K) && !getenv("TIK_NO_FUSED_GCN")) {
       // aggregation + channel GEMM in one kernel: build the block-structured bf16 operand Abd in the workspace
-      const int f = t < 7 ? t : 7;
+      const int f = gcn_fused_frames(t);
       std::vector<float> a_host((size_t)V * V);
       cudaError_t ce = cudaMemcpy(a_host.data(), b.agg_dev, a_host.size() * sizeof(float), cudaMemcpyDeviceToHost);
       std::vector<__nv_bfloat16> abd_host(128 * 128, __float2bfloat16_rn(0.f));
@@ -329,7 +329,7 @@ int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int64_t
         // wide layers (256 channels): the fused kernel does not fit, but its aggregation half does -- run it per
         // 128-channel slice with identity weights and a zero bias (Abd . X on the tensor pipe, bf16 out), then the
         // channel GEMM below.  Replaces the SIMT aggregate kernel (172 -> ~100 us at B=4096).
-        const int f = t < 7 ? t : 7;
+        const int f = gcn_fused_frames(t);
         std::vector<float> a_host((size_t)V * V);
         cudaError_t ce = cudaMemcpy(a_host.data(), b.agg_dev, a_host.size() * sizeof(float), cudaMemcpyDeviceToHost);
         std::vector<__nv_bfloat16> abd_host(128 * 128, __float2bfloat16_rn(0.f)), eye_host(128 * 128, __float2bfloat16_rn(0.f));

@@ -15,6 +15,7 @@ int umma_launch(UmmaPrepared* u, const TikRowGemm* d, cudaStream_t s);
 void umma_free(UmmaPrepared* u);
 struct GcnFusedPrepared;
 bool gcn_fused_supported(int cin, int cout, int V, int K);
+int gcn_fused_frames(int T);          // frames per tile = the block size of the Abd operand
 int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float* bias, void* out, int64_t n_clips, int T, int V,
                       int cin, int cout, int relu, GcnFusedPrepared** outp, int x_row = 0, int out_row = 0);
 int gcn_fused_launch(GcnFusedPrepared* g, int64_t n_clips, cudaStream_t s);

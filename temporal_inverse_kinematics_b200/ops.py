@@ -63,9 +63,10 @@ def stem_gcn(x, in_scale, in_shift, A_hat, w, bias, out_dtype, relu=True, res_w=
 
 def build_abd(A_hat, T):
     """(128,128) bf16 block-structured aggregation operand of the fused graph conv: rows (w, t), columns (v, t'),
-    entry A_hat[v, w] * (t == t'), f = min(T, 7) frames per tile, zero padding."""
+    entry A_hat[v, w] * (t == t'), f = ceil(T / ceil(T/7)) frames per tile (tik.h), zero padding."""
     V = A_hat.shape[-1]
-    f = min(int(T), 7)
+    tiles = (int(T) + 6) // 7
+    f = (int(T) + tiles - 1) // tiles
     a = A_hat.reshape(V, V).float()
     abd = torch.zeros(128, 128, dtype=torch.float32, device=A_hat.device)
     abd[: V * f, : V * f] = torch.kron(a.t().contiguous(), torch.eye(f, device=A_hat.device))
