@@ -66,7 +66,10 @@ int tik_rotmat_to_aa(const float* R_dev, float* aa_dev, int64_t M, int kornia_qu
  *   rest_host    (J,3) rest joints, HOST memory (copied into kernel arguments)
  *   parents_host (J) parent index, -1 for the root, parents[i] < i, HOST memory
  *   transl_dev   (F,3) or NULL
- *   joints_dev   (F,J,3) out; local_R_dev / global_R_dev (F,J,3,3) out, each may be NULL. */
+ *   joints_dev   (F,J,3) out; local_R_dev / global_R_dev (F,J,3,3) out, each may be NULL.
+ * J <= TIK_MAX_JOINTS (64): the 22-joint SMPL-X body tree and the 60-joint full skeleton (55 joints + 5 face landmarks
+ * as rigid children of the head, data_amass.py:176-218) have thread-per-frame specialisations; any other tree runs on
+ * a warp-per-frame kernel (J <= 32: pointer jumping over shuffles; J <= 64: level order through shared memory). */
 int tik_fk_body(const float* pose_dev, int pose_is_rotmat, const float* rest_host, const int32_t* parents_host,
                 int J, const float* transl_dev, float* joints_dev, float* local_R_dev, float* global_R_dev,
                 int64_t F, void* stream);
