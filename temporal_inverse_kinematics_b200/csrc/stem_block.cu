@@ -52,7 +52,7 @@ constexpr int kSbBiasLd = kSbCout + 4;               // padded pitch: rows of di
 constexpr int kSbOffBias2 = kSbOffBias1 + kSbMaxV * kSbBiasLd * 4;
 constexpr int kSbOffAs = kSbOffBias2 + kSbMaxV * kSbBiasLd * 4;           // As[u][v][c] = A^[u,v] * s0[u,c]   (V*V*Cin fp32)
 constexpr int kSbNbrLd = 20;                        // neighbour list pitch (ints): lists are read 4 entries at a time
-constexpr int kSbAsLd = 20 * 4;                     // weight row pitch (floats) for CIN <= 4, 16-byte aligned per node
+constexpr int kSbAsLd = 20 * 4 + 4;                 // weight row pitch (floats) for CIN <= 4: 16-byte aligned, odd multiple of 4 banks
 constexpr int kSbOffNbr = kSbOffAs + kSbMaxV * kSbAsLd * 4;             // per node: source-node offsets of the non-zero A^[u,v], zero padded
 constexpr int kSbOffCnt = kSbOffNbr + kSbMaxV * kSbNbrLd * 4;           // per node: number of 4-entry groups
 constexpr int kSbOffCst = kSbOffCnt + kSbMaxV * 4 + 8;         // cst[v][c] = sum_u A^[u,v] o0[u,c]; sum[v][c] = sum_u As; scale[v][c]
