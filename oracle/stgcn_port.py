@@ -169,6 +169,27 @@ def regressor_forward(sd, x, layers=POSE_REGRESSOR_LAYERS):
         return {"poses": h.view(n, t, -1)}
 
 
+def iterative_regressor_forward(sd, x, n_iter=3, layers=POSE_REGRESSOR_LAYERS):
+    """The HMR-style iterative 6-D head that pose_trainer.py keeps commented out (:53-64 definition, :108-126 forward):
+    pred = init_pose; repeat n_iter times: xc = fc2(fc1(cat[x, pred])) (dropouts are identities in eval, there is no
+    activation between the layers in the reference text), pred = decpose(xc) + pred; rot6d -> rotmat -> axis-angle.
+    **parity unpinned**: the code is commented out in the reference, so there is nothing to run for goldens."""
+    from . import geometry_port as gp
+    with torch.no_grad():
+        f = backbone_forward(sd, x, layers)
+        n, t, c = f.shape
+        feats = f.reshape(n * t, c)
+        pred = sd["init_pose"].expand(n * t, -1)
+        for _ in range(n_iter):
+            xc = torch.cat([feats, pred], 1)
+            xc = F.linear(xc, sd["fc1.weight"], sd["fc1.bias"])
+            xc = F.linear(xc, sd["fc2.weight"], sd["fc2.bias"])
+            pred = F.linear(xc, sd["decpose.weight"], sd["decpose.bias"]) + pred
+        rot = torch.from_numpy(gp.rot6d_to_rotmat(pred.numpy().reshape(-1, 6))).view(n * t, 22, 3, 3)
+        aa = torch.from_numpy(gp.rotation_matrix_to_angle_axis(rot.numpy().reshape(-1, 3, 3))).view(n, t, 66)
+        return {"poses": aa, "rotmats": rot, "rot6d": pred}
+
+
 # --------------------------------------------------------------------------- callers (SURVEY.md section 8f rows 1-2)
 def sample_window(arr, idx, half):
     """Edge-padded window of 2*half+1 frames centred on idx -- data_amass.py:18-42."""

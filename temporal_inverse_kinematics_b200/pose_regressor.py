@@ -84,6 +84,89 @@ class PoseRegressor(nn.Module, _ComputeDtypeMixin):
         return {"poses": plan.run_windows(seq, n_windows, offset, stride, root)}
 
 
+class IterativePoseRegressor(nn.Module, _ComputeDtypeMixin):
+    """The HMR-style iterative 6-D head the reference keeps commented out (pose_trainer.py:53-64 definition, :108-126
+    forward), as a first-class model on the same backbone:
+
+        pred = init_pose;  n_iter times:  xc = fc2(fc1(cat[features, pred]));  pred = decpose(xc) + pred
+        rotmats = rot6d_to_rotmat(pred);  poses = rotation_matrix_to_angle_axis(rotmats)
+
+    (dropouts are identities in eval; the reference text has no activation between fc1 and fc2).  Everything runs in
+    libtik.so: the backbone plan, the three Linear layers as tensor-core / fp32 implicit GEMMs (`tik_rowgemm`; the
+    concatenation is two K slabs, the 132 pose columns zero-padded to 192) and the conversion kernels.  The reference
+    loads SPIN's mean pose for `init_pose`; here it defaults to the 6-D identity and can be passed in."""
+
+    NPOSE = 22 * 6
+    NPAD = 192                      # pose columns / decpose rows padded to the 64-wide MMA granule
+
+    def __init__(self, hparams, init_pose=None, channel=512):
+        super().__init__()
+        self.graph_cfg = dict(layout=hparams.graph_layout, strategy="uniform", max_hop=hparams.max_hop,
+                              dilation=hparams.dilation)
+        layers = [StgLayerConfig(in_channels=hparams.kps_channel if ci is None else ci, out_channels=co,
+                                 temporal_stride=s, is_residual=True) for ci, co, s in _BLOCKS]
+        self.backbone = StgGcn18(config=StgConfig(layers=layers, temporal_kernel_size=3), graph_cfg=self.graph_cfg)
+        self.fc1 = nn.Linear(17 * 256 + self.NPOSE, channel)
+        self.drop1 = nn.Dropout()
+        self.fc2 = nn.Linear(channel, channel)
+        self.drop2 = nn.Dropout()
+        self.decpose = nn.Linear(channel, self.NPOSE)
+        nn.init.xavier_uniform_(self.decpose.weight, gain=0.01)
+        if init_pose is None:
+            init_pose = torch.tensor([1.0, 0.0, 0.0, 1.0, 0.0, 0.0]).repeat(22)
+        self.register_buffer("init_pose", torch.as_tensor(init_pose, dtype=torch.float32).reshape(1, self.NPOSE))
+        self.compute_dtype = _default_dtype()
+        self.chunk_clips = None
+        self._engine = None
+        self._packed = None
+
+    def _head_weights(self):
+        """fc1 / fc2 / decpose in the compute dtype, padded as the GEMM kernels want them; cached per parameter version."""
+        ps = [self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, self.decpose.weight, self.decpose.bias]
+        stamp = (self.compute_dtype,) + tuple((t.data_ptr(), t._version) for t in ps)
+        if self._packed is None or self._packed[0] != stamp:
+            _, tdt = engine.resolve_dtype(self.compute_dtype)
+            feat = 17 * 256
+            w1 = self.fc1.weight.detach()
+            w1 = torch.cat([w1, w1.new_zeros(w1.shape[0], self.NPAD - self.NPOSE)], dim=1)          # (512, 4352 + 192)
+            assert w1.shape[1] == feat + self.NPAD
+            w3 = self.decpose.weight.detach()
+            w3 = torch.cat([w3, w3.new_zeros(self.NPAD - self.NPOSE, w3.shape[1])], dim=0)          # (192, 512)
+            b3 = torch.cat([self.decpose.bias.detach(), self.decpose.bias.new_zeros(self.NPAD - self.NPOSE)])
+            self._packed = (stamp, w1.to(tdt).contiguous(), self.fc1.bias.detach().float().reshape(1, -1).contiguous(),
+                            self.fc2.weight.detach().to(tdt).contiguous(), self.fc2.bias.detach().float().reshape(1, -1).contiguous(),
+                            w3.to(tdt).contiguous(), b3.float().reshape(1, -1).contiguous())
+        return self._packed[1:]
+
+    def forward(self, x, init_pose=None, n_iter=3):
+        """x (N, T, V, C) -> {'poses': (N, T', 66) axis-angle, 'rotmats': (N*T', 22, 3, 3)}."""
+        from . import geometry, ops
+        engine.require_cuda_eval(self, x, "IterativePoseRegressor")
+        x = self.backbone._check_input(x)
+        N, T = x.shape[0], x.shape[1]
+        Tp = self.backbone.out_frames(T)
+        if N == 0:
+            return {"poses": x.new_zeros((0, Tp, 66)), "rotmats": x.new_zeros((0, 22, 3, 3))}
+        if self._engine is None:
+            self._engine = engine.Engine(self.backbone)
+        plan = self._engine.plan(self.compute_dtype, N, T, self.chunk_clips)
+        _, feat = plan.run(x, want_feat=True)                               # (N, T', 17*256) in the compute dtype
+        M = N * Tp
+        feat = feat.view(1, M, -1)
+        w1, b1, w2, b2, w3, b3 = self._head_weights()
+        pred = (self.init_pose if init_pose is None else init_pose.to(x.device).float().reshape(-1, self.NPOSE)).expand(M, -1)
+        pose_slab = torch.zeros((1, M, self.NPAD), dtype=feat.dtype, device=x.device)
+        for _ in range(int(n_iter)):
+            pose_slab[0, :, : self.NPOSE] = pred
+            h = ops.rowgemm([(feat, 1, 0), (pose_slab, 1, 0)], w1, b1, 1, 1, M)
+            h = ops.rowgemm([(h, 1, 0)], w2, b2, 1, 1, M)
+            d = ops.rowgemm([(h, 1, 0)], w3, b3, 1, 1, M, out_layout="rows_f32", c_out_valid=self.NPOSE)
+            pred = d + pred
+        rotmats = geometry.rot6d_to_rotmat(pred.reshape(-1, 6)).view(M, 22, 3, 3)
+        poses = geometry.rotation_matrix_to_angle_axis(rotmats.reshape(-1, 3, 3)).reshape(N, Tp, 66)
+        return {"poses": poses, "rotmats": rotmats}
+
+
 class IKPoseTrainer(nn.Module, _ComputeDtypeMixin):
     """Inference-side stand-in for the reference LightningModule (pose_trainer.py:136-144): same attribute
     names (``hparams``, ``regressor``, ``device``), same forward, loads Lightning checkpoints."""

@@ -72,6 +72,24 @@ def make_regressor_state(A, layers=POSE_REGRESSOR_LAYERS, kt=3, seed=0, hidden=5
     return sd
 
 
+def make_iterative_state(A, layers=POSE_REGRESSOR_LAYERS, kt=3, seed=0, hidden=512, njoints=22):
+    """State dict of IterativePoseRegressor (the reference's commented-out 6-D head, pose_trainer.py:53-64): backbone,
+    fc1 (17*256 + 132 -> 512), fc2 (512 -> 512), decpose (512 -> 132, small init as xavier gain 0.01) and init_pose =
+    the 6-D encoding of the identity rotation for every joint (the reference loads SPIN's mean pose from a file)."""
+    sd = make_backbone_state(A, layers, kt, seed)
+    rs = np.random.RandomState(seed + 2000003)
+    feat = A.shape[1] * layers[-1][1]
+    npose = njoints * 6
+    sd["fc1.weight"] = _t(rs.standard_normal((hidden, feat + npose)) * np.sqrt(1.0 / (feat + npose)))
+    sd["fc1.bias"] = _t(rs.standard_normal(hidden) * 0.1)
+    sd["fc2.weight"] = _t(rs.standard_normal((hidden, hidden)) * np.sqrt(1.0 / hidden))
+    sd["fc2.bias"] = _t(rs.standard_normal(hidden) * 0.1)
+    sd["decpose.weight"] = _t(rs.standard_normal((npose, hidden)) * 0.3 * np.sqrt(1.0 / hidden))
+    sd["decpose.bias"] = _t(rs.standard_normal(npose) * 0.05)
+    sd["init_pose"] = _t(np.tile(np.array([1.0, 0.0, 0.0, 1.0, 0.0, 0.0]), njoints)[None, :])
+    return sd
+
+
 def make_clips(n, t, v=17, c=3, seed=1234, scale=0.3):
     """Root-relative COCO-17 clips (N,T,V,C): mid-hip = 0.5*(kp11+kp12) subtracted
     (mmskeleton/datasets/data_amass.py:232-235)."""
