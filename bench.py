@@ -307,7 +307,8 @@ def run_ours(args):
                 "e2e": {"value": world * B * T / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": world * x_host.numel() * 4,
                         "d2h_bytes_per_step": world * (out_p.numel() + out_j.numel()) * 4},
-                "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline}
+                "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline,
+                "clips_per_s": world * B / (ms * 1e-3), "output_poses_per_s": world * B * T_out / (ms * 1e-3)}
         if world == 1 and not args.no_cpu:
             torch.set_num_threads(os.cpu_count() or 1)
             fps, sec, threads = time_cpu(CPU_SAMPLE_CLIPS, 3)
