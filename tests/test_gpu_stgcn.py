@@ -248,7 +248,7 @@ def test_bf16_kernel_variants_agree(monkeypatch, switch):
 def test_bf16_edge_shapes(n, t):
     """Tile-boundary cases of the specialised kernels: 12 output frames per tile in the fused first block, G row groups
     of T+2 rows per tile in the halo temporal conv (unsupported above 126 / 190 frames -> per-tap kernels), odd tile
-    counts in the paired 64-channel graph conv, single clips and single frames (tools/shape_sweep.py has the long list)."""
+    counts in the paired 64-channel graph conv, single clips and single frames (tests/tools/shape_sweep.py has the long list)."""
     m, sd = _model(dtype="bf16")
     x = synth.make_clips(n, t, seed=1000 * n + t)
     want = sp.regressor_forward(sd, x)["poses"]

@@ -1,6 +1,6 @@
-"""Step-by-step GPU diagnostics (run on the B200 box; each stage in its own process via tools/gpu_check.sh).
+"""Step-by-step GPU diagnostics (run on the B200 box; each stage in its own process via tests/tools/gpu_check.sh).
 
-    python tools/gpu_check.py simt | umma | net
+    python tests/tools/gpu_check.py simt | umma | net
 """
 import os
 import sys
@@ -9,7 +9,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
