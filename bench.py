@@ -295,6 +295,10 @@ def run_ours(args):
                     "peak_source": (peak_src + " bf16_tflops_sustained (kernel timed inside a long step)") if args.dtype == "bf16" else "nominal fp32 SIMT 148 SM x 128 FMA x 2 x 1.965 GHz",
                     "launches": g_n, "avg_launch_us": g_ms * 1e3 / max(g_n, 1), "flops_per_step": gemm_flops,
                     "kernel_ms_per_step": {k: v[0] for k, v in kinds.items()}, "traffic": _ncu_traffic_per_launch()}
+        if roofline["traffic"] and g_ms > 0:
+            # context: the same launches against the HBM roofline (DRAM bytes from the committed ncu capture / live time)
+            gbs = roofline["traffic"] / (roofline["avg_launch_us"] * 1e-6) / 1e9
+            roofline["dram"] = {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]}
         line = {"metric": METRIC, "value": world * B * T / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.dtype, "data": "synthetic",
