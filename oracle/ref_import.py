@@ -15,11 +15,27 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("TIK_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    """The reference checkout (dev container), else the snapshot oracle/build_ref.py made of its hot-path files
+    (``oracle/_ref``, which travels to the GPU box)."""
+    for cand in (os.environ.get("TIK_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "mmskeleton")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, "mmskeleton"))
+
+
+def is_snapshot() -> bool:
+    return os.path.abspath(REF_ROOT) == os.path.join(_HERE, "_ref")
 
 
 def _namespace(name, path):

@@ -5,8 +5,22 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtik.so")
 
-TIK_F32, TIK_BF16 = 0, 1
-MAX_BLOCKS, MAX_SLABS, MAX_JOINTS = 16, 6, 32
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "tik.h")
+
+
+def _header_defines():
+    """Integer #defines of include/tik.h: the header is the single source of the ABI's limits and codes."""
+    import re
+    out = {}
+    with open(HEADER_PATH) as f:
+        for m in re.finditer(r"^#define\s+(TIK_\w+)\s+\(?(-?\d+)\)?", f.read(), re.M):
+            out[m.group(1)] = int(m.group(2))
+    return out
+
+
+_H = _header_defines()
+TIK_F32, TIK_BF16 = _H["TIK_F32"], _H["TIK_BF16"]
+MAX_BLOCKS, MAX_SLABS, MAX_JOINTS = _H["TIK_MAX_BLOCKS"], _H["TIK_MAX_SLABS"], _H["TIK_MAX_JOINTS"]
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 RES_NONE, RES_IDENTITY, RES_STEM, RES_CONV = 0, 1, 2, 3
 OUT_NODE_MAJOR, OUT_TIME_MAJOR, OUT_ROWS_F32 = 0, 1, 2
@@ -105,3 +119,11 @@ def ptr(t):
 def stream_ptr(device=None):
     import torch
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def on_device(t):
+    """Context manager making the tensor's (or torch.device's) GPU the current CUDA device for the enclosed libtik
+    calls: kernels, function attributes, cudaGetDevice and the plan's setup copies all act on the *current* device,
+    which need not be the one the caller's tensors live on (a model on cuda:1 while cuda:0 is current)."""
+    import torch
+    return torch.cuda.device(t.device if torch.is_tensor(t) else t)

@@ -12,6 +12,7 @@ BN folded as s = gamma / sqrt(var + eps), o = beta - mean * s:
 There is no CPU or eager-PyTorch fallback: anything but eval-mode CUDA tensors raises.
 """
 import ctypes as C
+import os
 import weakref
 
 import torch
@@ -174,6 +175,9 @@ class PackedNet:
 
 
 class Plan:
+    """One launch plan = kernels + tensor maps over ONE workspace.  A plan belongs to the (device, stream) it was
+    made for (Engine keys on both): its workspace is reused by every run, so runs must be stream-ordered."""
+
     def __init__(self, packed, n_chunk, n_max, T):
         lib = L.lib()
         self.packed = packed
@@ -183,8 +187,9 @@ class Plan:
         self.workspace = torch.empty(nbytes.value + 1024, dtype=torch.uint8, device=packed.device)
         base = (self.workspace.data_ptr() + 1023) // 1024 * 1024
         handle = L.vp()
-        L.check(lib.tik_stgcn_plan_create(C.byref(packed.net), packed.code, n_chunk, n_max, T, C.c_void_p(base),
-                                          nbytes.value, C.byref(handle)))
+        with L.on_device(packed.device):      # plan_create issues cudaMemcpy / cudaFuncSetAttribute on the current device
+            L.check(lib.tik_stgcn_plan_create(C.byref(packed.net), packed.code, n_chunk, n_max, T, C.c_void_p(base),
+                                              nbytes.value, C.byref(handle)))
         self.handle = handle
         self.T_out = lib.tik_stgcn_out_frames(C.byref(packed.net), T)
         self.workspace_bytes = nbytes.value
@@ -202,8 +207,9 @@ class Plan:
         ms = (C.c_double * 3)()
         cnt = (L.i64 * 3)()
         fl = C.c_double(0)
-        L.check(L.lib().tik_stgcn_plan_profile(self.handle, L.ptr(x), N, L.ptr(poses), L.stream_ptr(x.device), ms, cnt,
-                                               C.byref(fl)))
+        with L.on_device(x):
+            L.check(L.lib().tik_stgcn_plan_profile(self.handle, L.ptr(x), N, L.ptr(poses), L.stream_ptr(x.device), ms, cnt,
+                                                   C.byref(fl)))
         return {k: (ms[i], int(cnt[i])) for i, k in enumerate(("stem", "aggregate", "gemm"))}, fl.value
 
     def run_graphed(self, x):
@@ -219,18 +225,20 @@ class Plan:
 
             def enqueue():
                 L.check(L.lib().tik_stgcn_plan_run(self.handle, L.ptr(xbuf), N, L.ptr(poses), None, L.stream_ptr(x.device)))
-            xbuf.copy_(x)
-            enqueue()                                                 # eager warm-up (function attributes, lazy init)
-            torch.cuda.current_stream(x.device).synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                enqueue()
+            with L.on_device(x):
+                xbuf.copy_(x)
+                enqueue()                                             # eager warm-up (function attributes, lazy init)
+                torch.cuda.current_stream(x.device).synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    enqueue()
             if len(self._graphs) >= 4:
                 self._graphs.pop(next(iter(self._graphs)))
             entry = self._graphs[N] = (graph, poses, xbuf)
-        entry[2].copy_(x)
-        entry[0].replay()
-        return entry[1].clone()
+        with L.on_device(x):
+            entry[2].copy_(x)
+            entry[0].replay()
+            return entry[1].clone()
 
     def run_windows(self, seq, n_windows, offset, stride, root):
         """Sliding windows of one resident sequence (F,V,C): window n, frame t = seq[clamp(n*stride + t + offset)],
@@ -238,8 +246,9 @@ class Plan:
         p = self.packed
         win = L.TikWindowing(seq.shape[0], offset, stride, root[0] if root else -1, root[1] if root else -1)
         poses = torch.empty((n_windows, self.T_out, p.head_out), dtype=torch.float32, device=seq.device)
-        L.check(L.lib().tik_stgcn_plan_run_windows(self.handle, L.ptr(seq), C.byref(win), n_windows, L.ptr(poses), None,
-                                                   L.stream_ptr(seq.device)))
+        with L.on_device(seq):
+            L.check(L.lib().tik_stgcn_plan_run_windows(self.handle, L.ptr(seq), C.byref(win), n_windows, L.ptr(poses), None,
+                                                       L.stream_ptr(seq.device)))
         return poses
 
     def run(self, x, want_feat=False):
@@ -247,7 +256,8 @@ class Plan:
         N = x.shape[0]
         poses = torch.empty((N, self.T_out, p.head_out), dtype=torch.float32, device=x.device) if p.head_out else None
         feat = torch.empty((N, self.T_out, p.V * p.c_last), dtype=p.tdtype, device=x.device) if want_feat else None
-        L.check(L.lib().tik_stgcn_plan_run(self.handle, L.ptr(x), N, L.ptr(poses), L.ptr(feat), L.stream_ptr(x.device)))
+        with L.on_device(x):
+            L.check(L.lib().tik_stgcn_plan_run(self.handle, L.ptr(x), N, L.ptr(poses), L.ptr(feat), L.stream_ptr(x.device)))
         return poses, feat
 
 
@@ -262,7 +272,15 @@ def default_chunk(T):
 
 
 class Engine:
-    """Per-model cache of packed weights and plans, invalidated when any parameter/buffer changes."""
+    """Per-model cache of packed (BN / bias / edge-importance folded) weights and launch plans.
+
+    Invalidation.  The cache is stamped with every parameter's and buffer's (data_ptr, _version, device) plus the
+    scalars that enter the folding (BatchNorm eps, LeakyReLU slope), so optimizer steps, `load_state_dict`, `.to()`
+    and any autograd-visible in-place update re-fold automatically.  Writes through ``param.data`` (old-style EMA,
+    manual loaders) do NOT bump `_version`; after such a write either call ``invalidate()`` (also exposed as
+    ``model.invalidate_packed()`` on the modules), or set ``weight_check = "content"``, which additionally compares a
+    strided-sample checksum of every tensor on each call (one small device->host read per forward: safe, but it
+    serialises the host with the stream, so it is off by default for the latency path)."""
 
     def __init__(self, backbone, head_fn=None):
         self._backbone = weakref.ref(backbone)
@@ -270,16 +288,37 @@ class Engine:
         self._packed = {}
         self._plans = {}
         self._stamp = None
+        self.weight_check = os.environ.get("TIK_WEIGHT_CHECK", "version")
 
-    def _stamp_now(self, backbone, extra):
-        ts = list(backbone.parameters()) + list(backbone.buffers()) + extra
-        return tuple((t.data_ptr(), t._version, t.device.index) for t in ts)
+    def invalidate(self):
+        """Drop the folded weights and every plan; the next forward re-folds from the module's current tensors."""
+        self._packed.clear()
+        self._plans.clear()
+        self._stamp = None
+
+    def _tensors(self, backbone, head):
+        extra = [] if head is None else [head[0].weight, head[0].bias, head[2].weight, head[2].bias]
+        return list(backbone.parameters()) + list(backbone.buffers()) + extra
+
+    def _stamp_now(self, backbone, head):
+        ts = self._tensors(backbone, head)
+        scalars = tuple(m.eps for m in backbone.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm))
+        scalars += (None if head is None else float(head[1]),)
+        stamp = tuple((t.data_ptr(), t._version, t.device.index) for t in ts) + scalars
+        if self.weight_check == "content":
+            # <= 64 strided samples + the sum of each tensor, reduced on the device, one read-back
+            with torch.no_grad():
+                sums = torch.stack([t.detach().reshape(-1)[:: max(1, t.numel() // 64)].double().sum() + t.detach().double().sum()
+                                    for t in ts if t.numel()])
+            stamp += (tuple(sums.tolist()),)
+        elif self.weight_check != "version":
+            raise ValueError("weight_check must be 'version' or 'content'")
+        return stamp
 
     def plan(self, dtype_name, N, T, chunk=None):
         backbone = self._backbone()
         head = self._head_fn() if self._head_fn else None
-        extra = [] if head is None else [head[0].weight, head[0].bias, head[2].weight, head[2].bias]
-        stamp = self._stamp_now(backbone, extra)
+        stamp = self._stamp_now(backbone, head)
         if stamp != self._stamp:
             self._packed.clear()
             self._plans.clear()
@@ -289,12 +328,40 @@ class Engine:
         n_chunk = int(chunk) if chunk else default_chunk(T)
         n_chunk = max(1, min(n_chunk, N))
         n_max = max(n_chunk, min(N, MAX_HEAD_CLIPS))
-        key = (dtype_name, n_chunk, n_max, T)
+        dev = self._packed[dtype_name].device
+        # a plan's workspace is reused by every run: runs on different streams would race on it, so each stream
+        # (and device) gets its own plan
+        key = (dtype_name, n_chunk, n_max, T, dev.index, torch.cuda.current_stream(dev).cuda_stream)
         if key not in self._plans:
             if len(self._plans) >= 8:                                    # bound the workspaces kept alive
                 self._plans.pop(next(iter(self._plans)))
             self._plans[key] = Plan(self._packed[dtype_name], n_chunk, n_max, T)
         return self._plans[key]
+
+
+class EngineHolder:
+    """Mixin for the modules that own an Engine: the engine (weak reference, ctypes handles, device workspaces) is a
+    cache, not state -- it is dropped by pickling / ``torch.save(model)`` / ``copy.deepcopy`` and rebuilt lazily, as
+    the reference's plain nn.Modules would allow."""
+
+    _CACHE_ATTRS = ("_engine", "_packed")
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for k in self._CACHE_ATTRS:
+            if k in state:
+                state[k] = None
+        return state
+
+    def invalidate_packed(self):
+        """Forget folded weights / plans (call after writing parameters through ``.data``)."""
+        for m in self.modules():
+            if isinstance(m, EngineHolder):
+                if getattr(m, "_engine", None) is not None:
+                    m._engine.invalidate()
+                if "_packed" in m.__dict__:
+                    m._packed = None
+        return self
 
 
 def require_cuda_eval(module, x, what):
@@ -305,4 +372,5 @@ def require_cuda_eval(module, x, what):
         raise TypeError(f"{what}: expected a torch.Tensor, got {type(x)}")
     if not x.is_cuda:
         raise RuntimeError(f"{what}: input must be a CUDA tensor -- there is no CPU fallback")
-    L.check(L.lib().tik_check_device())
+    with L.on_device(x):
+        L.check(L.lib().tik_check_device())

@@ -15,12 +15,16 @@ def _prep(x, last, what):
         raise RuntimeError(f"{what}: input must be a CUDA tensor -- there is no CPU fallback")
     if x.numel() % last:
         raise ValueError(f"{what}: input with {x.numel()} elements is not a multiple of {last}")
-    return x.detach().to(torch.float32).contiguous().view(-1, last)
+    x = x.detach().to(torch.float32).contiguous().view(-1, last)
+    if x.data_ptr() % 16:            # a contiguous slice (aa[1:]) keeps its storage offset; the kernels use 16-byte vectors
+        x = x.clone()
+    return x
 
 
 def _run(fn, x, out_shape, *extra):
     out = torch.empty((x.shape[0],) + out_shape, dtype=torch.float32, device=x.device)
-    L.check(fn(L.ptr(x), L.ptr(out), x.shape[0], *extra, L.stream_ptr(x.device)))
+    with L.on_device(x):
+        L.check(fn(L.ptr(x), L.ptr(out), x.shape[0], *extra, L.stream_ptr(x.device)))
     return out
 
 

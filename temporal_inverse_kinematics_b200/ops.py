@@ -42,7 +42,8 @@ def aggregate(x, A_hat):
     N, V, T, Cc = x.shape
     K = A_hat.shape[0]
     out = torch.empty((K, N, V, T, Cc), dtype=x.dtype, device=x.device)
-    L.check(L.lib().tik_aggregate(_code(x), L.ptr(x), L.ptr(A_hat), L.ptr(out), N, T, V, Cc, K, L.stream_ptr(x.device)))
+    with L.on_device(x):
+        L.check(L.lib().tik_aggregate(_code(x), L.ptr(x), L.ptr(A_hat), L.ptr(out), N, T, V, Cc, K, L.stream_ptr(x.device)))
     return out
 
 
@@ -55,9 +56,10 @@ def stem_gcn(x, in_scale, in_shift, A_hat, w, bias, out_dtype, relu=True, res_w=
     Cout = w.shape[0]
     out = torch.empty((N, V, T, Cout), dtype=out_dtype, device=x.device)
     res = None if res_w is None else torch.empty((N, V, (T - 1) // res_stride + 1, Cout), dtype=out_dtype, device=x.device)
-    L.check(L.lib().tik_stem_gcn(_code(out), L.ptr(x), L.ptr(in_scale), L.ptr(in_shift), L.ptr(A_hat), L.ptr(w), L.ptr(bias),
-                                 L.ptr(out), L.ptr(res_w), L.ptr(res), res_stride, N, T, V, Cin, K, Cout, int(relu),
-                                 L.stream_ptr(x.device)))
+    with L.on_device(x):
+        L.check(L.lib().tik_stem_gcn(_code(out), L.ptr(x), L.ptr(in_scale), L.ptr(in_shift), L.ptr(A_hat), L.ptr(w), L.ptr(bias),
+                                     L.ptr(out), L.ptr(res_w), L.ptr(res), res_stride, N, T, V, Cin, K, Cout, int(relu),
+                                     L.stream_ptr(x.device)))
     return out if res_w is None else (out, res)
 
 
@@ -79,8 +81,9 @@ def gcn_fused(x, abd, w, bias, relu=True):
     N, V, T, Cin = x.shape
     Cout = w.shape[0]
     out = torch.empty((N, V, T, Cout), dtype=torch.bfloat16, device=x.device)
-    L.check(L.lib().tik_gcn_fused(L.ptr(x), L.ptr(abd), L.ptr(w), L.ptr(bias), L.ptr(out), N, T, V, Cin, Cout, int(relu),
-                                  L.stream_ptr(x.device)))
+    with L.on_device(x):
+        L.check(L.lib().tik_gcn_fused(L.ptr(x), L.ptr(abd), L.ptr(w), L.ptr(bias), L.ptr(out), N, T, V, Cin, Cout, int(relu),
+                                      L.stream_ptr(x.device)))
     return out
 
 
@@ -137,5 +140,6 @@ def rowgemm(slabs, w, bias, nv, v, t_out, act="none", slope=0.01, residual=None,
     else:
         raise ValueError(out_layout)
     g.out_dev = out.data_ptr()
-    L.check(L.lib().tik_rowgemm(code, C.byref(g), L.stream_ptr(a0.device)))
+    with L.on_device(a0):
+        L.check(L.lib().tik_rowgemm(code, C.byref(g), L.stream_ptr(a0.device)))
     return out

@@ -26,7 +26,7 @@ def default_hparams(**over):
     return argparse.Namespace(**hp)
 
 
-class PoseRegressor(nn.Module, _ComputeDtypeMixin):
+class PoseRegressor(engine.EngineHolder, nn.Module, _ComputeDtypeMixin):
     def __init__(self, hparams):
         super().__init__()
         self.graph_cfg = dict(layout=hparams.graph_layout, strategy="uniform", max_hop=hparams.max_hop,
@@ -40,6 +40,7 @@ class PoseRegressor(nn.Module, _ComputeDtypeMixin):
         self.compute_dtype = _default_dtype()
         self.chunk_clips = None
         self.use_cuda_graph = os.environ.get("TIK_CUDA_GRAPH", "0") == "1"   # replay the launch sequence as one graph
+        self.weight_check = None           # None = engine default ('version'); 'content': see engine.Engine
         self._engine = None
 
     def _head(self):
@@ -48,6 +49,7 @@ class PoseRegressor(nn.Module, _ComputeDtypeMixin):
     def plan_for(self, N, T):
         if self._engine is None:
             self._engine = engine.Engine(self.backbone, self._head)
+        self._engine.weight_check = self.weight_check or self._engine.weight_check
         return self._engine.plan(self.compute_dtype, N, T, self.chunk_clips)
 
     def forward(self, x, init_pose=None, n_iter=3):
@@ -76,6 +78,11 @@ class PoseRegressor(nn.Module, _ComputeDtypeMixin):
             raise ValueError(f"expected a (F, {self.backbone.A.size(1)}, C) sequence, got {tuple(seq.shape)}")
         seq = seq.detach().float().contiguous()
         F = seq.shape[0]
+        V = seq.shape[1]
+        if root is not None and (len(root) != 2 or not all(0 <= int(r) < V for r in root)):
+            raise ValueError(f"root must be a pair of keypoint indices in [0, {V}), got {root!r}")
+        if F < 1 or int(stride) < 1 or int(win_frames) < 1:
+            raise ValueError("forward_windows needs a non-empty sequence, stride >= 1 and win_frames >= 1")
         if n_windows is None:
             n_windows = F if offset < 0 else max(0, (F - win_frames - offset) // stride + 1)
         if n_windows == 0:
@@ -84,7 +91,7 @@ class PoseRegressor(nn.Module, _ComputeDtypeMixin):
         return {"poses": plan.run_windows(seq, n_windows, offset, stride, root)}
 
 
-class IterativePoseRegressor(nn.Module, _ComputeDtypeMixin):
+class IterativePoseRegressor(engine.EngineHolder, nn.Module, _ComputeDtypeMixin):
     """The HMR-style iterative 6-D head the reference keeps commented out (pose_trainer.py:53-64 definition, :108-126
     forward), as a first-class model on the same backbone:
 
@@ -117,6 +124,7 @@ class IterativePoseRegressor(nn.Module, _ComputeDtypeMixin):
         self.register_buffer("init_pose", torch.as_tensor(init_pose, dtype=torch.float32).reshape(1, self.NPOSE))
         self.compute_dtype = _default_dtype()
         self.chunk_clips = None
+        self.weight_check = None
         self._engine = None
         self._packed = None
 
@@ -149,6 +157,7 @@ class IterativePoseRegressor(nn.Module, _ComputeDtypeMixin):
             return {"poses": x.new_zeros((0, Tp, 66)), "rotmats": x.new_zeros((0, 22, 3, 3))}
         if self._engine is None:
             self._engine = engine.Engine(self.backbone)
+        self._engine.weight_check = self.weight_check or self._engine.weight_check
         plan = self._engine.plan(self.compute_dtype, N, T, self.chunk_clips)
         _, feat = plan.run(x, want_feat=True)                               # (N, T', 17*256) in the compute dtype
         M = N * Tp
@@ -167,7 +176,7 @@ class IterativePoseRegressor(nn.Module, _ComputeDtypeMixin):
         return {"poses": poses, "rotmats": rotmats}
 
 
-class IKPoseTrainer(nn.Module, _ComputeDtypeMixin):
+class IKPoseTrainer(engine.EngineHolder, nn.Module, _ComputeDtypeMixin):
     """Inference-side stand-in for the reference LightningModule (pose_trainer.py:136-144): same attribute
     names (``hparams``, ``regressor``, ``device``), same forward, loads Lightning checkpoints."""
 

@@ -43,7 +43,11 @@ def fk_body(pose, rest_joints, parents, transl=None, want_local=False, want_glob
         raise RuntimeError("fk_body: pose must be a CUDA tensor -- there is no CPU fallback")
     is_rot = pose.dim() == 4
     pose = pose.detach().float().contiguous()
+    if pose.data_ptr() % 16:
+        pose = pose.clone()
     F, J = pose.shape[0], pose.shape[1]
+    if J > L.MAX_JOINTS:
+        raise ValueError(f"fk_body supports at most {L.MAX_JOINTS} joints, got {J}")
     rest = np.ascontiguousarray(np.asarray(rest_joints, dtype=np.float32).reshape(J, 3))
     par = np.ascontiguousarray(np.asarray(parents, dtype=np.int32).reshape(J))
     joints = torch.empty((F, J, 3), dtype=torch.float32, device=pose.device)
@@ -51,9 +55,10 @@ def fk_body(pose, rest_joints, parents, transl=None, want_local=False, want_glob
     glo = torch.empty((F, J, 3, 3), dtype=torch.float32, device=pose.device) if want_global else None
     if transl is not None:
         transl = transl.detach().float().contiguous()
-    L.check(L.lib().tik_fk_body(L.ptr(pose), int(is_rot), rest.ctypes.data_as(C.POINTER(C.c_float)),
-                                par.ctypes.data_as(C.POINTER(C.c_int32)), J, L.ptr(transl), L.ptr(joints), L.ptr(loc),
-                                L.ptr(glo), F, L.stream_ptr(pose.device)))
+    with L.on_device(pose):
+        L.check(L.lib().tik_fk_body(L.ptr(pose), int(is_rot), rest.ctypes.data_as(C.POINTER(C.c_float)),
+                                    par.ctypes.data_as(C.POINTER(C.c_int32)), J, L.ptr(transl), L.ptr(joints), L.ptr(loc),
+                                    L.ptr(glo), F, L.stream_ptr(pose.device)))
     out = (joints,) + ((loc,) if want_local else ()) + ((glo,) if want_global else ())
     return out[0] if len(out) == 1 else out
 

@@ -37,6 +37,11 @@ class _ComputeDtypeMixin:
         return self
 
 
+def _identity(x):
+    """data_bn=False stand-in (module level so the model pickles; the reference uses a lambda there)."""
+    return x
+
+
 def _pad_channels(t, mult):
     c = t.shape[-1]
     pad = (-c) % mult
@@ -156,7 +161,7 @@ class StgConfig:
     temporal_kernel_size: int
 
 
-class StgGcn18(nn.Module, _ComputeDtypeMixin):
+class StgGcn18(engine.EngineHolder, nn.Module, _ComputeDtypeMixin):
     """ST-GCN backbone: (N, T, V, C) keypoint windows -> (N, T', V * C_last) features."""
 
     def __init__(self, config: StgConfig, graph_cfg, edge_importance_weighting=True, data_bn=True, **kwargs):
@@ -166,7 +171,7 @@ class StgGcn18(nn.Module, _ComputeDtypeMixin):
         self.n_in_keypoints = self.A.size(1)
         kernel_size = (config.temporal_kernel_size, self.A.size(0))
         c0 = config.layers[0].in_channels
-        self.data_bn = nn.BatchNorm1d(c0 * self.A.size(1)) if data_bn else (lambda x: x)
+        self.data_bn = nn.BatchNorm1d(c0 * self.A.size(1)) if data_bn else _identity
         block_kw = {k: v for k, v in kwargs.items() if k != "dropout"}
         self.st_gcn_networks = nn.ModuleList([
             StGcnBlock(l.in_channels, l.out_channels, kernel_size, stride=l.temporal_stride, residual=l.is_residual,
@@ -178,6 +183,7 @@ class StgGcn18(nn.Module, _ComputeDtypeMixin):
             self.edge_importance = [1] * len(self.st_gcn_networks)
         self.compute_dtype = _default_dtype()
         self.chunk_clips = None            # None = engine.default_chunk(T)
+        self.weight_check = None           # None = engine default ('version'); 'content' also checksums the tensors
         self._engine = None
 
     def out_frames(self, T):
@@ -196,6 +202,7 @@ class StgGcn18(nn.Module, _ComputeDtypeMixin):
         x = self._check_input(x)
         if self._engine is None:
             self._engine = engine.Engine(self)
+        self._engine.weight_check = self.weight_check or self._engine.weight_check
         N, T = x.shape[0], x.shape[1]
         if N == 0:
             return x.new_zeros((0, self.out_frames(T), self.A.size(1) * self.st_gcn_networks[-1].out_channels))
