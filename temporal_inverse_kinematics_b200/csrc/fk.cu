@@ -11,7 +11,12 @@
 // joints + local rotmats out).
 #include <string.h>
 
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "tik_common.cuh"
+#include "umma_ptx.cuh"
 
 namespace tik {
 
@@ -401,6 +406,205 @@ fk_full60_kernel(const float* __restrict__ pose, const float* __restrict__ trans
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Bulk-async pipelined thread-per-frame FK (axis-angle in, joints out) for the compile-time trees: the 22-joint
+// SMPL-X body (the tree on the IK path) and the 60-joint full skeleton.
+//
+// The thread-per-frame kernels above are instruction-bound on their own staging: every float goes global -> register
+// -> shared, shared -> register -> global with index arithmetic (~1200 of ~3600 thread-instructions per frame), and
+// load / compute / store are serial phases per CTA.  Here a tile of kFrames frames is ONE contiguous block of global
+// memory (kFrames * J * 12 bytes), so a producer thread moves it with a single cp.async.bulk (1-D TMA) into one of
+// kStages shared-memory buffers, the compute threads overwrite their pose row in place with the joint positions
+// (joint j's output occupies exactly the floats of joint j's input), and the producer sends the buffer back with a
+// single bulk store.  Load of tile i+1, compute of tile i and store of tile i-1 overlap; the compute threads issue
+// no global-memory instructions at all.  Rows are read / written as 8-byte (J = 22: row pitch 264 B) or 16-byte
+// (J = 60: 720 B) vectors, both bank-conflict free at those pitches.  sin / cos / rsqrt use the SFU intrinsics
+// (abs error ~5e-7 on |x| < pi, far inside the 1e-4 parity bar): precise sincosf costs ~40 instructions and a
+// local-memory slow path per joint.
+struct TreeBody22 {
+  static constexpr int J = 22, VEC = 2;
+  __host__ __device__ static constexpr int parent(int j) {
+    constexpr int P[22] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19};
+    return P[j];
+  }
+};
+struct TreeFull60 {
+  static constexpr int J = 60, VEC = 4;
+  __host__ __device__ static constexpr int parent(int j) { return f60_parent(j); }
+};
+template <int J> struct RestParams { float rest[J * 3]; };   // offset to parent (root: rest position)
+
+__device__ __forceinline__ void bulk_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void rodrigues_q_fast(float ax, float ay, float az, float* R) {
+  // common/geometry.py:22-65 with SFU sin / cos / rsqrt
+  float ex = ax + 1e-8f, ey = ay + 1e-8f, ez = az + 1e-8f;
+  float n2 = ex * ex + ey * ey + ez * ez;
+  float ia = rsqrtf(n2);
+  float ang = n2 * ia;
+  float nx = ax * ia, ny = ay * ia, nz = az * ia;
+  float s, c;
+  __sincosf(ang * 0.5f, &s, &c);
+  float w = c, x = s * nx, y = s * ny, z = s * nz;
+  float iq = rsqrtf(w * w + x * x + y * y + z * z);   // quaternion re-normalisation (quat2mat, geometry.py:49)
+  w *= iq; x *= iq; y *= iq; z *= iq;
+  float w2 = w * w, x2 = x * x, y2 = y * y, z2 = z * z;
+  float wx = w * x, wy = w * y, wz = w * z, xy = x * y, xz = x * z, yz = y * z;
+  R[0] = w2 + x2 - y2 - z2; R[1] = 2.f * (xy - wz);       R[2] = 2.f * (wy + xz);
+  R[3] = 2.f * (wz + xy);   R[4] = w2 - x2 + y2 - z2;     R[5] = 2.f * (yz - wx);
+  R[6] = 2.f * (xz - wy);   R[7] = 2.f * (wx + yz);       R[8] = w2 - x2 - y2 + z2;
+}
+
+template <int VEC> struct VecT;
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<4> { using type = float4; };
+
+template <class Tree, int kFrames, int kStages>
+__global__ void __launch_bounds__(kFrames + 32)
+fk_bulk_kernel(const float* __restrict__ pose, const float* __restrict__ transl, float* __restrict__ joints, int64_t n_tiles,
+               const __grid_constant__ RestParams<Tree::J> p) {
+  constexpr int J = Tree::J, ROW = J * 3, VEC = Tree::VEC, G = VEC;       // G joints = 3 vectors of VEC floats
+  static_assert(J % G == 0 && (ROW * 4) % (VEC * 4) == 0, "row must split into whole vector groups");
+  constexpr uint32_t kTileBytes = (uint32_t)kFrames * ROW * 4;
+  static_assert(kTileBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+  using V = typename VecT<VEC>::type;
+  extern __shared__ __align__(128) uint8_t fk_bulk_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(fk_bulk_smem + (size_t)kStages * kTileBytes);
+  uint64_t* done = full + kStages;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int b = 0; b < kStages; ++b) { mbar_init(&full[b], 1); mbar_init(&done[b], kFrames); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int64_t n_my = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+
+  if (tid >= kFrames) {
+    // ---- producer: one thread issues every bulk load and bulk store of this CTA
+    if (tid == kFrames) {
+      for (int64_t i = 0; i < n_my; ++i) {
+        const int b = (int)(i % kStages);
+        uint8_t* buf = fk_bulk_smem + (size_t)b * kTileBytes;
+        if (i >= kStages) {                                  // the buffer's previous tile has been computed: send it out
+          mbar_wait(&done[b], (uint32_t)((i / kStages) - 1) & 1u);
+          bulk_store_1d(joints + (first + (i - kStages) * stride) * (int64_t)(kFrames * ROW), buf, kTileBytes);
+          tma_store_commit();
+          tma_store_wait_read0();                            // shared memory has been read: the buffer may be refilled
+        }
+        mbar_expect_tx(&full[b], kTileBytes);
+        bulk_load_1d(buf, pose + (first + i * stride) * (int64_t)(kFrames * ROW), kTileBytes, &full[b]);
+      }
+      for (int64_t i = n_my > kStages ? n_my - kStages : 0; i < n_my; ++i) {
+        const int b = (int)(i % kStages);
+        mbar_wait(&done[b], (uint32_t)(i / kStages) & 1u);
+        bulk_store_1d(joints + (first + i * stride) * (int64_t)(kFrames * ROW), fk_bulk_smem + (size_t)b * kTileBytes, kTileBytes);
+        tma_store_commit();
+      }
+      tma_store_wait0();
+    }
+    return;
+  }
+
+  // ---- compute: thread tid owns frame tid of every tile
+  for (int64_t i = 0; i < n_my; ++i) {
+    const int b = (int)(i % kStages);
+    mbar_wait(&full[b], (uint32_t)(i / kStages) & 1u);
+    V* row = reinterpret_cast<V*>(fk_bulk_smem + (size_t)b * kTileBytes + (size_t)tid * ROW * 4);
+    float tx = 0.f, ty = 0.f, tz = 0.f;
+    if (transl != nullptr) {
+      const int64_t f = (first + i * stride) * kFrames + tid;
+      tx = __ldg(transl + f * 3); ty = __ldg(transl + f * 3 + 1); tz = __ldg(transl + f * 3 + 2);
+    }
+    float GR[J][9];
+    float Gt[J][3];
+#pragma unroll
+    for (int g = 0; g < J / G; ++g) {
+      float a[3 * G];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const V v = row[g * 3 + q];
+        const float* vf = reinterpret_cast<const float*>(&v);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) a[q * VEC + e] = vf[e];
+      }
+#pragma unroll
+      for (int q = 0; q < G; ++q) {
+        const int j = g * G + q;
+        float R[9];
+        rodrigues_q_fast(a[q * 3], a[q * 3 + 1], a[q * 3 + 2], R);
+        const float dx = p.rest[j * 3], dy = p.rest[j * 3 + 1], dz = p.rest[j * 3 + 2];
+        const int par = Tree::parent(j);
+        if (par < 0) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) GR[j][k] = R[k];
+          Gt[j][0] = dx; Gt[j][1] = dy; Gt[j][2] = dz;
+        } else {
+          const float* A = GR[par];
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) GR[j][r * 3 + c] = A[r * 3] * R[c] + A[r * 3 + 1] * R[3 + c] + A[r * 3 + 2] * R[6 + c];
+          Gt[j][0] = A[0] * dx + A[1] * dy + A[2] * dz + Gt[par][0];
+          Gt[j][1] = A[3] * dx + A[4] * dy + A[5] * dz + Gt[par][1];
+          Gt[j][2] = A[6] * dx + A[7] * dy + A[8] * dz + Gt[par][2];
+        }
+        a[q * 3] = Gt[j][0] + tx; a[q * 3 + 1] = Gt[j][1] + ty; a[q * 3 + 2] = Gt[j][2] + tz;
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        V v;
+        float* vf = reinterpret_cast<float*>(&v);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) vf[e] = a[q * VEC + e];
+        row[g * 3 + q] = v;
+      }
+    }
+    fence_proxy_async_smem();          // this thread's st.shared -> visible to the bulk store (async proxy)
+    mbar_arrive(&done[b]);
+  }
+}
+
+// Launches the bulk kernel on the whole tiles of the batch; returns the number of frames it covered.
+template <class Tree, int kFrames, int kStages>
+static int launch_fk_bulk(const float* pose, const float* transl, float* joints, int64_t F, const float* rest_off,
+                          cudaStream_t s, int64_t* covered) {
+  constexpr size_t smem = (size_t)kStages * kFrames * Tree::J * 12 + 2 * kStages * sizeof(uint64_t);
+  auto kern = fk_bulk_kernel<Tree, kFrames, kStages>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  TIK_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    TIK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TIK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_set[dev & 63] = true;
+  }
+  const int64_t n_tiles = F / kFrames;
+  *covered = n_tiles * kFrames;
+  if (n_tiles == 0) return TIK_OK;
+  RestParams<Tree::J> p;
+  for (int i = 0; i < Tree::J * 3; ++i) p.rest[i] = rest_off[i];
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (227 * 1024) / (smem + 1024)));
+  int64_t blocks = std::min<int64_t>(n_tiles, (int64_t)148 * per_sm);
+  kern<<<(unsigned)blocks, kFrames + 32, smem, s>>>(pose, transl, joints, n_tiles, p);
+  TIK_LAUNCH_CHECK();
+  return TIK_OK;
+}
+
+static int fk_bulk_cfg() {
+  static int v = -2;
+  if (v == -2) { const char* e = getenv("TIK_FK_BULK"); v = e ? atoi(e) : 0; }
+  return v;      // -1: off (staged kernels above); 0: default; 1..3: alternative tile / stage shapes (tools/hbm_bench.py)
+}
+
 template <bool kRotIn, bool kLocalOut>
 static int launch_body22(const float* pose, const float* transl, float* joints, float* localR, int64_t F,
                          const Fk22Params& p, cudaStream_t s) {
@@ -452,19 +656,44 @@ extern "C" int tik_fk_body(const float* pose_dev, int pose_is_rotmat, const floa
     for (int i = 0; i < kB22 * 3; ++i) q.rest[i] = p.rest[i];
     if (pose_is_rotmat) return launch_body22<true, false>(pose_dev, transl_dev, joints_dev, nullptr, F, q, s);
     if (local_R_dev) {
-      // local rotations are an element-wise conversion: the streaming Rodrigues kernel (81 % of HBM peak) writes
-      // them, the joints-only FK kernel keeps its small shared-memory footprint (measured: 3.4 ms vs 8.0 ms fused
-      // at 8.4 M frames, profiles/r1_notes.md)
+      // local rotations are an element-wise conversion: the streaming Rodrigues kernel (81 % of the HBM peak) writes
+      // them; the joints come from the joints-only kernel below (a fused variant needs 792 more bytes of shared
+      // memory per frame and measured 2.3x slower, profiles/r1_notes.md)
       int rc = launch_batch_rodrigues(pose_dev, local_R_dev, F * kB22, s);
       if (rc != TIK_OK) return rc;
-      return launch_body22<false, false>(pose_dev, transl_dev, joints_dev, nullptr, F, q, s);
     }
-    return launch_body22<false, false>(pose_dev, transl_dev, joints_dev, nullptr, F, q, s);
+    // joints from axis-angle: bulk-async pipelined kernel on the whole tiles, staged kernel on the remainder
+    int64_t done_frames = 0;
+    const int cfg = fk_bulk_cfg();
+    if (cfg >= 0) {
+      int rc = cfg == 1   ? launch_fk_bulk<TreeBody22, 64, 3>(pose_dev, transl_dev, joints_dev, F, p.rest, s, &done_frames)
+               : cfg == 2 ? launch_fk_bulk<TreeBody22, 128, 2>(pose_dev, transl_dev, joints_dev, F, p.rest, s, &done_frames)
+               : cfg == 3 ? launch_fk_bulk<TreeBody22, 64, 2>(pose_dev, transl_dev, joints_dev, F, p.rest, s, &done_frames)
+                          : launch_fk_bulk<TreeBody22, 128, 3>(pose_dev, transl_dev, joints_dev, F, p.rest, s, &done_frames);
+      if (rc != TIK_OK) return rc;
+      if (done_frames == F) return TIK_OK;
+    }
+    return launch_body22<false, false>(pose_dev + done_frames * (kB22 * 3), transl_dev ? transl_dev + done_frames * 3 : nullptr,
+                                       joints_dev + done_frames * (kB22 * 3), nullptr, F - done_frames, q, s);
   }
   if (J == kF60 && !pose_is_rotmat && local_R_dev == nullptr && global_R_dev == nullptr) {
     bool full60 = true;
     for (int i = 0; full60 && i < J; ++i) full60 = parents_host[i] == kF60ParentHost[i];
     if (full60) {
+      int64_t done_frames = 0;
+      const int cfg = fk_bulk_cfg();
+      if (cfg >= 0 && (((uintptr_t)pose_dev | (uintptr_t)joints_dev) & 15) == 0) {
+        int rc = cfg == 1   ? launch_fk_bulk<TreeFull60, 32, 3>(pose_dev, transl_dev, joints_dev, F, p.rest, s, &done_frames)
+                 : cfg == 2 ? launch_fk_bulk<TreeFull60, 64, 3>(pose_dev, transl_dev, joints_dev, F, p.rest, s, &done_frames)
+                 : cfg == 3 ? launch_fk_bulk<TreeFull60, 32, 2>(pose_dev, transl_dev, joints_dev, F, p.rest, s, &done_frames)
+                            : launch_fk_bulk<TreeFull60, 64, 2>(pose_dev, transl_dev, joints_dev, F, p.rest, s, &done_frames);
+        if (rc != TIK_OK) return rc;
+        if (done_frames == F) return TIK_OK;
+        pose_dev += done_frames * (kF60 * 3);
+        joints_dev += done_frames * (kF60 * 3);
+        if (transl_dev) transl_dev += done_frames * 3;
+        F -= done_frames;
+      }
       Fk60Params q;
       for (int i = 0; i < kF60 * 3; ++i) q.rest[i] = p.rest[i];
       const size_t smem = sizeof(float) * (size_t)kF60Threads * (kF60 * 3 + 1);

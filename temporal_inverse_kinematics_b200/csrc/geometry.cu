@@ -49,12 +49,13 @@ __device__ __forceinline__ void staged_map(const float* __restrict__ in, float* 
 // common/geometry.py:330-344 -- a1 = (x0,x2,x4), a2 = (x1,x3,x5); R columns = b1,b2,b3.
 __device__ __forceinline__ void rot6d_one(const float* x, float* R) {
   float a1x = x[0], a1y = x[2], a1z = x[4], a2x = x[1], a2y = x[3], a2z = x[5];
-  float n1 = fmaxf(sqrtf(a1x * a1x + a1y * a1y + a1z * a1z), 1e-6f);
-  float b1x = a1x / n1, b1y = a1y / n1, b1z = a1z / n1;
+  // one reciprocal per normalisation instead of three divisions (the kernels were issue-bound, profiles/r2_hbm_kernels.md)
+  float i1 = 1.0f / fmaxf(sqrtf(a1x * a1x + a1y * a1y + a1z * a1z), 1e-6f);
+  float b1x = a1x * i1, b1y = a1y * i1, b1z = a1z * i1;
   float d = b1x * a2x + b1y * a2y + b1z * a2z;
   float ux = a2x - d * b1x, uy = a2y - d * b1y, uz = a2z - d * b1z;
-  float n2 = fmaxf(sqrtf(ux * ux + uy * uy + uz * uz), 1e-6f);
-  float b2x = ux / n2, b2y = uy / n2, b2z = uz / n2;
+  float i2 = 1.0f / fmaxf(sqrtf(ux * ux + uy * uy + uz * uz), 1e-6f);
+  float b2x = ux * i2, b2y = uy * i2, b2z = uz * i2;
   float b3x = b1y * b2z - b1z * b2y, b3y = b1z * b2x - b1x * b2z, b3z = b1x * b2y - b1y * b2x;
   R[0] = b1x; R[1] = b2x; R[2] = b3x;
   R[3] = b1y; R[4] = b2y; R[5] = b3y;
@@ -67,8 +68,8 @@ __device__ __forceinline__ void aa_kornia_one(const float* a, float* R) {
   float t2 = rx * rx + ry * ry + rz * rz;
   if (t2 > 1e-6f) {
     float th = sqrtf(t2);
-    float inv = th + 1e-6f;
-    float wx = rx / inv, wy = ry / inv, wz = rz / inv;
+    float inv = 1.0f / (th + 1e-6f);
+    float wx = rx * inv, wy = ry * inv, wz = rz * inv;
     float s, c;
     sincosf(th, &s, &c);
     float k = 1.0f - c;
@@ -86,12 +87,13 @@ __device__ __forceinline__ void aa_kornia_one(const float* a, float* R) {
 __device__ __forceinline__ void rodrigues_one(const float* a, float* R) {
   float ex = a[0] + 1e-8f, ey = a[1] + 1e-8f, ez = a[2] + 1e-8f;
   float ang = sqrtf(ex * ex + ey * ey + ez * ez);
-  float nx = a[0] / ang, ny = a[1] / ang, nz = a[2] / ang;
+  float ia = 1.0f / ang;
+  float nx = a[0] * ia, ny = a[1] * ia, nz = a[2] * ia;
   float s, c;
   sincosf(ang * 0.5f, &s, &c);
   float w = c, x = s * nx, y = s * ny, z = s * nz;
-  float qn = sqrtf(w * w + x * x + y * y + z * z);
-  w /= qn; x /= qn; y /= qn; z /= qn;
+  float iq = rsqrtf(w * w + x * x + y * y + z * z);
+  w *= iq; x *= iq; y *= iq; z *= iq;
   float w2 = w * w, x2 = x * x, y2 = y * y, z2 = z * z;
   float wx = w * x, wy = w * y, wz = w * z, xy = x * y, xz = x * z, yz = y * z;
   R[0] = w2 + x2 - y2 - z2; R[1] = 2.f * xy - 2.f * wz;   R[2] = 2.f * wy + 2.f * xz;
@@ -99,34 +101,61 @@ __device__ __forceinline__ void rodrigues_one(const float* a, float* R) {
   R[6] = 2.f * xz - 2.f * wy; R[7] = 2.f * wx + 2.f * yz; R[8] = w2 - x2 - y2 + z2;
 }
 
-// common/geometry.py:100-150 (w,x,y,z)
+// atan2(y, x) for x >= 0 (or NaN): |error| <= 1.1e-7 rad (degree-8 minimax-style fit of atan(z)/z in z^2 on [0,1],
+// checked against float64 on 200,001 points in fp32 arithmetic; tools/fit_atan.py).  libm's atan2f costs ~60
+// instructions with divergent paths; this is ~20, branch-free.
+__device__ __forceinline__ float atan2_xpos(float y, float x) {
+  const float ay = fabsf(y);
+  const float mx = fmaxf(ay, x), mn = fminf(ay, x);
+  const float z = mx > 0.0f ? __fdividef(mn, mx) : (mx == 0.0f ? 0.0f : mx);     // NaN propagates
+  const float u = z * z;
+  float p = 0.0028340641874819994f;
+  p = fmaf(p, u, -0.016005029901862144f);
+  p = fmaf(p, u, 0.042587608098983765f);
+  p = fmaf(p, u, -0.07495445758104324f);
+  p = fmaf(p, u, 0.10636754333972931f);
+  p = fmaf(p, u, -0.14202570915222168f);
+  p = fmaf(p, u, 0.19992484152317047f);
+  p = fmaf(p, u, -0.3333306610584259f);
+  p = fmaf(p, u, 1.0f);
+  float r = z * p;
+  r = ay > x ? 1.5707963267948966f - r : r;
+  r = (x != x || y != y) ? x + y : r;                   // fmaxf / fminf drop NaNs: put them back as atan2f would
+  return copysignf(r, y);
+}
+
+// common/geometry.py:100-150 (w,x,y,z).  The reference picks atan2(-s, -q0) when q0 < 0 and atan2(s, q0) otherwise:
+// one atan2 of sign-flipped arguments, whose second argument is never negative.
 __device__ __forceinline__ void quat_to_aa(float q0, float q1, float q2, float q3, float* aa) {
-  float s2 = q1 * q1 + q2 * q2 + q3 * q3;
-  float s = sqrtf(s2);
-  float two_theta = 2.0f * (q0 < 0.0f ? atan2f(-s, -q0) : atan2f(s, q0));
-  float k = s2 > 0.0f ? two_theta / s : 2.0f;
+  const float s2 = q1 * q1 + q2 * q2 + q3 * q3;
+  const float rs = rsqrtf(s2);
+  const float s = s2 * rs;                              // sqrt(s2) for s2 > 0 (s2 == 0 takes the k = 2 branch below)
+  const bool neg = q0 < 0.0f;
+  const float two_theta = 2.0f * atan2_xpos(neg ? -s : s, neg ? -q0 : q0);
+  const float k = s2 > 0.0f ? two_theta * rs : 2.0f;
   aa[0] = q1 * k; aa[1] = q2 * k; aa[2] = q3 * k;
 }
 
-// common/geometry.py:68-97,153-233: four-case selection on the transposed matrix, NaN -> 0
+// common/geometry.py:68-97,153-233: four-case selection on the transposed matrix, NaN -> 0.
+// The ncu capture of round 2 (profiles/r2_hbm_kernels.md) showed the first version issue-bound (306 instructions per
+// rotation: four divergent cases, two atan2f, five precise divisions): the cases are now selects over shared sums, the
+// common factor 0.5 / sqrt(t) is one rsqrt (same inf / NaN behaviour as q / sqrt(t) * 0.5 for t <= 0).
 __device__ __forceinline__ void rotmat_to_aa_one(const float* R, float* aa) {
   // m = R^T
-  float m00 = R[0], m01 = R[3], m02 = R[6];
-  float m10 = R[1], m11 = R[4], m12 = R[7];
-  float m20 = R[2], m21 = R[5], m22 = R[8];
-  bool d2 = m22 < 1e-6f, d01 = m00 > m11, d0n1 = m00 < -m11;
-  float q0, q1, q2, q3, t;
-  if (d2 && d01) {
-    t = 1.f + m00 - m11 - m22; q0 = m12 - m21; q1 = t; q2 = m01 + m10; q3 = m20 + m02;
-  } else if (d2) {
-    t = 1.f - m00 + m11 - m22; q0 = m20 - m02; q1 = m01 + m10; q2 = t; q3 = m12 + m21;
-  } else if (d0n1) {
-    t = 1.f - m00 - m11 + m22; q0 = m01 - m10; q1 = m20 + m02; q2 = m12 + m21; q3 = t;
-  } else {
-    t = 1.f + m00 + m11 + m22; q0 = t; q1 = m12 - m21; q2 = m20 - m02; q3 = m01 - m10;
-  }
-  float st = sqrtf(t);
-  q0 = q0 / st * 0.5f; q1 = q1 / st * 0.5f; q2 = q2 / st * 0.5f; q3 = q3 / st * 0.5f;
+  const float m00 = R[0], m01 = R[3], m02 = R[6];
+  const float m10 = R[1], m11 = R[4], m12 = R[7];
+  const float m20 = R[2], m21 = R[5], m22 = R[8];
+  const bool d2 = m22 < 1e-6f, d01 = m00 > m11, d0n1 = m00 < -m11;
+  const bool c0 = d2 && d01, c1 = d2 && !d01, c2 = !d2 && d0n1;           // else: c3
+  const float s01 = m01 + m10, s20 = m20 + m02, s12 = m12 + m21;
+  const float a12 = m12 - m21, a20 = m20 - m02, a01 = m01 - m10;
+  const float t = c0 ? 1.f + m00 - m11 - m22 : c1 ? 1.f - m00 + m11 - m22 : c2 ? 1.f - m00 - m11 + m22 : 1.f + m00 + m11 + m22;
+  float q0 = c0 ? a12 : c1 ? a20 : c2 ? a01 : t;
+  float q1 = c0 ? t : c1 ? s01 : c2 ? s20 : a12;
+  float q2 = c0 ? s01 : c1 ? t : c2 ? s12 : a20;
+  float q3 = c0 ? s20 : c1 ? s12 : c2 ? t : a01;
+  const float h = 0.5f * rsqrtf(t);
+  q0 *= h; q1 *= h; q2 *= h; q3 *= h;
   quat_to_aa(q0, q1, q2, q3, aa);
 #pragma unroll
   for (int k = 0; k < 3; ++k)

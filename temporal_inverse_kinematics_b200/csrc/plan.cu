@@ -454,8 +454,6 @@ int tik_stgcn_plan_run_windows(TikPlan* P, const float* seq, const TikWindowing*
   TIK_CHECK_ARG((win->root_a < 0) == (win->root_b < 0), "windowing: root_a and root_b must both be set or both be negative");
   TIK_CHECK_ARG(win->root_a < P->net.V && win->root_b < P->net.V, "windowing: root keypoints (%d, %d) must be < V = %d",
                 win->root_a, win->root_b, P->net.V);
-  TIK_CHECK_ARG(n_windows == 0 || (int64_t)(n_windows - 1) * win->stride + win->offset < win->frames + (int64_t)P->T,
-                "windowing: the last window starts past the end of the sequence");
   TIK_CHECK_ARG(P->net.blocks[0].res_kind != TIK_RES_STEM || P->net.blocks[0].c_in <= 8, "window mode needs the stem path");
   TIK_CHECK_ARG(P->net.head_hidden == 0 || poses, "poses pointer required");
   return run_impl(P, seq, n_windows, poses, feat_out, (cudaStream_t)stream, nullptr, nullptr, win);

@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,driver_version,clocks.sm,clocks.max.sm --format=csv 
 for what in "$@"; do
   case $what in
     tests)
-      timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/pytest.log 2>&1; echo "pytest exit $?" | tee -a gpurun_out/summary.txt
+      timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/pytest.log 2>&1; echo "pytest exit $?" | tee -a gpurun_out/summary.txt
       tail -5 gpurun_out/pytest.log ;;
     smoke)
       timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" | tee -a gpurun_out/summary.txt; tail -2 gpurun_out/smoke.log ;;
@@ -25,10 +25,15 @@ for what in "$@"; do
       TIK_PLAN_TRACE=1 timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu --no-hbm > gpurun_out/trace.json 2> gpurun_out/trace.err; grep "tik trace" gpurun_out/trace.err | tail -24 ;;
     hbm)
       timeout 600 python tools/hbm_bench.py > gpurun_out/hbm_bench.log 2>&1; echo "hbm exit $?" | tee -a gpurun_out/summary.txt; cat gpurun_out/hbm_bench.log ;;
+    hbm_fk_sweep)
+      for c in -1 1 2 3; do
+        echo "TIK_FK_BULK=$c" | tee -a gpurun_out/hbm_fk_sweep.log
+        TIK_FK_BULK=$c timeout 600 python tools/hbm_bench.py 2>&1 | grep fk_body | tee -a gpurun_out/hbm_fk_sweep.log
+      done ;;
     ncu_hbm)
-      timeout 300 python tools/hbm_bench.py 2097152 > gpurun_out/hbm_plain.log 2>&1 &&
+      timeout 300 python tools/hbm_bench.py 2097152 --once > gpurun_out/hbm_plain.log 2>&1 &&
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:'rot6d_kernel|aa_kornia_kernel|rodrigues_kernel|rotmat_to_aa_kernel|fk_' \
-          -s 40 -c 14 -f -o gpurun_out/prof_hbm python tools/hbm_bench.py 2097152 > gpurun_out/ncu_hbm.log 2>&1
+          -c 16 -f -o gpurun_out/prof_hbm python tools/hbm_bench.py 2097152 --once > gpurun_out/ncu_hbm.log 2>&1
       echo "ncu_hbm exit $?" | tee -a gpurun_out/summary.txt ;;
     ncu_net)
       timeout 300 python bench.py --steps 1 --warmup 3 --no-cpu --no-hbm > gpurun_out/net_plain.log 2>&1 &&
