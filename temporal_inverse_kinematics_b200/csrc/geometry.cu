@@ -4,7 +4,10 @@
 // global traffic is fully coalesced 128-bit loads/stores even though a rotation is 3, 6 or 9
 // floats.  Precise libm (no fast-math): parity target is 1e-4 max-abs against the reference
 // formulas, cited per function.
+#include <algorithm>
+
 #include "tik_common.cuh"
+#include "umma_ptx.cuh"
 
 namespace tik {
 
@@ -43,6 +46,88 @@ __device__ __forceinline__ void staged_map(const float* __restrict__ in, float* 
     for (int i = threadIdx.x; i < kConvThreads * OUT / 4; i += kConvThreads) g4[i] = s4[i];
   } else {
     for (int i = threadIdx.x; i < n * OUT; i += kConvThreads) gout[i] = s_out[i];
+  }
+}
+
+// Bulk-async pipelined variant of staged_map for the whole 256-rotation tiles of a batch (the staged kernel above
+// keeps the remainder).  A tile's input and output are contiguous blocks of global memory, so ONE producer thread
+// moves them with cp.async.bulk (1-D TMA) through a ring of kStages shared-memory buffer pairs and the 256 compute
+// threads issue no global-memory instructions: the staged version spent about a quarter of its instructions on
+// staging and ran load / compute / store as serial phases per CTA (ncu: issue-bound at 55-73 % issue utilisation
+// with DRAM at 50-65 %, profiles/r2_hbm_kernels.md).
+constexpr int kConvStages = 4;
+
+__device__ __forceinline__ void conv_bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void conv_bulk_store(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+
+template <int IN, int OUT, class F>
+__device__ __forceinline__ void bulk_map(const float* __restrict__ in, float* __restrict__ out, int64_t n_tiles, F f) {
+  constexpr uint32_t kInBytes = kConvThreads * IN * 4, kOutBytes = kConvThreads * OUT * 4;
+  extern __shared__ __align__(128) uint8_t conv_smem[];
+  uint8_t* in_bufs = conv_smem;
+  uint8_t* out_bufs = conv_smem + (size_t)kConvStages * kInBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(out_bufs + (size_t)kConvStages * kOutBytes);
+  uint64_t* done = full + kConvStages;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int b = 0; b < kConvStages; ++b) { mbar_init(&full[b], 1); mbar_init(&done[b], kConvThreads); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int64_t n_my = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+  if (tid >= kConvThreads) {
+    if (tid == kConvThreads) {
+      auto load = [&](int64_t t) {
+        const int b = (int)(t % kConvStages);
+        mbar_expect_tx(&full[b], kInBytes);
+        conv_bulk_load(in_bufs + (size_t)b * kInBytes, in + (first + t * stride) * (int64_t)(kConvThreads * IN), kInBytes, &full[b]);
+      };
+      for (int64_t t = 0; t < n_my && t < kConvStages; ++t) load(t);
+      for (int64_t j = 0; j < n_my; ++j) {
+        const int b = (int)(j % kConvStages);
+        mbar_wait(&done[b], (uint32_t)(j / kConvStages) & 1u);                 // tile j computed: its output buffer is complete
+        conv_bulk_store(out + (first + j * stride) * (int64_t)(kConvThreads * OUT), out_bufs + (size_t)b * kOutBytes, kOutBytes);
+        tma_store_commit();
+        if (j >= 1) {
+          // the PREVIOUS tile's store has read its shared-memory buffer (one tile of slack for the producer): that
+          // buffer pair may take the tile kStages ahead of it
+          tma_store_wait_read1();
+          if (j - 1 + kConvStages < n_my) load(j - 1 + kConvStages);
+        }
+      }
+      tma_store_wait0();
+    }
+    return;
+  }
+  for (int64_t i = 0; i < n_my; ++i) {
+    const int b = (int)(i % kConvStages);
+    mbar_wait(&full[b], (uint32_t)(i / kConvStages) & 1u);
+    const float* si = reinterpret_cast<const float*>(in_bufs + (size_t)b * kInBytes) + tid * IN;
+    float* so = reinterpret_cast<float*>(out_bufs + (size_t)b * kOutBytes) + tid * OUT;
+    float a[IN], r[OUT];
+    if constexpr (IN % 2 == 0) {       // even row pitch: 8-byte loads are bank-conflict free where 4-byte ones are 2-way
+#pragma unroll
+      for (int k = 0; k < IN / 2; ++k) {
+        const float2 v = reinterpret_cast<const float2*>(si)[k];
+        a[2 * k] = v.x; a[2 * k + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < IN; ++k) a[k] = si[k];
+    }
+    f(a, r);
+#pragma unroll
+    for (int k = 0; k < OUT; ++k) so[k] = r[k];
+    fence_proxy_async_smem();          // st.shared -> visible to the bulk store (async proxy)
+    mbar_arrive(&done[b]);
   }
 }
 
@@ -200,36 +285,88 @@ __global__ void __launch_bounds__(kConvThreads) rotmat_to_aa_kernel(const float*
     staged_map<9, 3>(in, out, M, [](const float* a, float* r) { rotmat_to_aa_one(a, r); });
 }
 
-template <class K, class... Args>
-static int launch_conv(K kernel, const void* in, void* out, int64_t M, cudaStream_t s, Args... extra) {
+__global__ void __launch_bounds__(kConvThreads + 32) rot6d_bulk_kernel(const float* in, float* out, int64_t n_tiles) {
+  bulk_map<6, 9>(in, out, n_tiles, [](const float* a, float* r) { rot6d_one(a, r); });
+}
+__global__ void __launch_bounds__(kConvThreads + 32) aa_kornia_bulk_kernel(const float* in, float* out, int64_t n_tiles) {
+  bulk_map<3, 9>(in, out, n_tiles, [](const float* a, float* r) { aa_kornia_one(a, r); });
+}
+__global__ void __launch_bounds__(kConvThreads + 32) rodrigues_bulk_kernel(const float* in, float* out, int64_t n_tiles) {
+  bulk_map<3, 9>(in, out, n_tiles, [](const float* a, float* r) { rodrigues_one(a, r); });
+}
+__global__ void __launch_bounds__(kConvThreads + 32) rotmat_to_aa_bulk_kernel(const float* in, float* out, int64_t n_tiles, int quirk) {
+  if (quirk)
+    bulk_map<9, 3>(in, out, n_tiles, [](const float* a, float* r) { rotmat_to_aa_kornia_quirk_one(a, r); });
+  else
+    bulk_map<9, 3>(in, out, n_tiles, [](const float* a, float* r) { rotmat_to_aa_one(a, r); });
+}
+
+static bool conv_bulk_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("TIK_NO_CONV_BULK") ? 0 : 1;
+  return v != 0;
+}
+
+// whole 256-rotation tiles -> the bulk-pipelined kernel (persistent CTAs); the remainder (and small batches) -> the
+// staged kernel
+template <int IN, int OUT, class KB, class K, class... Args>
+static int launch_conv(KB bulk_kernel, K kernel, const void* in, void* out, int64_t M, cudaStream_t s, Args... extra) {
   TIK_CHECK_ARG(M >= 0, "negative count");
   if (M == 0) return TIK_OK;
   TIK_CHECK_ARG(in && out, "null pointer");
   TIK_CHECK_ARG((((uintptr_t)in | (uintptr_t)out) & 15) == 0, "pointers must be 16-byte aligned");
+  const float* fin = (const float*)in;
+  float* fout = (float*)out;
+  const int64_t n_tiles = M / kConvThreads;
+  if (conv_bulk_enabled() && n_tiles >= 148) {
+    constexpr size_t smem = (size_t)kConvStages * kConvThreads * (IN + OUT) * 4 + 2 * kConvStages * sizeof(uint64_t);
+    // function attributes are per (kernel, device); several kernels share this template instantiation
+    static const void* attr_kernel[16] = {};
+    static uint64_t attr_devs[16] = {};
+    int dev = 0;
+    TIK_CUDA(cudaGetDevice(&dev));
+    int slot = 0;
+    while (slot < 15 && attr_kernel[slot] && attr_kernel[slot] != (const void*)bulk_kernel) ++slot;
+    if (attr_kernel[slot] != (const void*)bulk_kernel || !(attr_devs[slot] >> (dev & 63) & 1)) {
+      TIK_CUDA(cudaFuncSetAttribute(bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TIK_CUDA(cudaFuncSetAttribute(bulk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      if (attr_kernel[slot] != (const void*)bulk_kernel) { attr_kernel[slot] = (const void*)bulk_kernel; attr_devs[slot] = 0; }
+      attr_devs[slot] |= 1ull << (dev & 63);
+    }
+    const int per_sm = (int)std::min<size_t>(7, (227 * 1024) / (smem + 1024));     // 288 threads per CTA, 2048 per SM
+    const int64_t blocks = std::min<int64_t>(n_tiles, (int64_t)148 * per_sm);
+    bulk_kernel<<<(unsigned)blocks, kConvThreads + 32, smem, s>>>(fin, fout, n_tiles, extra...);
+    TIK_LAUNCH_CHECK();
+    const int64_t covered = n_tiles * kConvThreads;
+    fin += covered * IN;
+    fout += covered * OUT;
+    M -= covered;
+    if (M == 0) return TIK_OK;
+  }
   int64_t blocks = ceil_div(M, kConvThreads);
   TIK_CHECK_ARG(blocks < (1ll << 31), "too many rotations for one launch");
-  kernel<<<(unsigned)blocks, kConvThreads, 0, s>>>((const float*)in, (float*)out, M, extra...);
+  kernel<<<(unsigned)blocks, kConvThreads, 0, s>>>(fin, fout, M, extra...);
   TIK_LAUNCH_CHECK();
   return TIK_OK;
 }
 
 int launch_batch_rodrigues(const float* aa, float* R9, int64_t M, cudaStream_t s) {
-  return launch_conv(rodrigues_kernel, aa, R9, M, s);
+  return launch_conv<3, 9>(rodrigues_bulk_kernel, rodrigues_kernel, aa, R9, M, s);
 }
 
 }  // namespace tik
 
 extern "C" {
 int tik_rot6d_to_rotmat(const float* x6, float* R, int64_t M, void* stream) {
-  return tik::launch_conv(tik::rot6d_kernel, x6, R, M, (cudaStream_t)stream);
+  return tik::launch_conv<6, 9>(tik::rot6d_bulk_kernel, tik::rot6d_kernel, x6, R, M, (cudaStream_t)stream);
 }
 int tik_aa_to_rotmat(const float* aa, float* R, int64_t M, void* stream) {
-  return tik::launch_conv(tik::aa_kornia_kernel, aa, R, M, (cudaStream_t)stream);
+  return tik::launch_conv<3, 9>(tik::aa_kornia_bulk_kernel, tik::aa_kornia_kernel, aa, R, M, (cudaStream_t)stream);
 }
 int tik_batch_rodrigues(const float* aa, float* R9, int64_t M, void* stream) {
-  return tik::launch_conv(tik::rodrigues_kernel, aa, R9, M, (cudaStream_t)stream);
+  return tik::launch_conv<3, 9>(tik::rodrigues_bulk_kernel, tik::rodrigues_kernel, aa, R9, M, (cudaStream_t)stream);
 }
 int tik_rotmat_to_aa(const float* R, float* aa, int64_t M, int kornia_quirk, void* stream) {
-  return tik::launch_conv(tik::rotmat_to_aa_kernel, R, aa, M, (cudaStream_t)stream, kornia_quirk);
+  return tik::launch_conv<9, 3>(tik::rotmat_to_aa_bulk_kernel, tik::rotmat_to_aa_kernel, R, aa, M, (cudaStream_t)stream, kornia_quirk);
 }
 }
