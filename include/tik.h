@@ -221,6 +221,29 @@ int tik_stgcn_plan_profile(TikPlan* plan, const float* x_dev, int64_t N, float* 
 int64_t tik_stgcn_plan_launches(const TikPlan* plan, int64_t N);
 void tik_stgcn_plan_destroy(TikPlan* plan);
 
+/* ------------------------------------------------------------------ latency plan (BASELINE.json configs[4])
+ * The same PoseRegressor.forward for a handful of clips (N * T' <= 32 head rows; e.g. one 64-frame window) as ONE
+ * persistent cooperative kernel: every layer is a phase, the 148 resident CTAs meet at a grid-wide barrier between
+ * phases, activations stay in L2.  Replaces the 19-25 dependent launches of the throughput plan, which are launch-bound
+ * at batch 1 (inference.py:43-52 with DataLoader(batch_size=1); streaming windows).  fp32 arithmetic on the TIK_F32
+ * packing of the network (same algebra as the 1e-4 parity path), K = 1 adjacency partition only. */
+typedef struct TikLatencyPlan TikLatencyPlan;
+int tik_stgcn_latency_workspace_bytes(const TikNet* net, int64_t n_max, int T, int64_t* bytes);
+/* Host-only work (+ one small cudaMemcpy of the phase table into the workspace, 256-byte aligned). */
+int tik_stgcn_latency_create(const TikNet* net, int64_t n_max, int T, void* workspace_dev, int64_t workspace_bytes,
+                             TikLatencyPlan** plan);
+/* x (N,T,V,c_in) fp32 -> poses (N,T',head_out) fp32, N <= n_max.  One cooperative launch on `stream`. */
+int tik_stgcn_latency_run(TikLatencyPlan* plan, const float* x_dev, int64_t N, float* poses_dev, void* stream);
+/* Same over sliding windows of one resident sequence (see TikWindowing / tik_stgcn_plan_run_windows). */
+int tik_stgcn_latency_run_windows(TikLatencyPlan* plan, const float* seq_dev, const TikWindowing* win, int64_t n_windows,
+                                  float* poses_dev, void* stream);
+/* number of phases (= grid barriers + 1) of the plan */
+int tik_stgcn_latency_phases(const TikLatencyPlan* plan);
+void tik_stgcn_latency_destroy(TikLatencyPlan* plan);
+/* Probe hook: device buffer of [CTAs = SM count (x TIK_LAT_CTAS_PER_SM)][2 * phases] uint64 receiving %globaltimer (ns)
+ * at the start and at the end of every phase's work in every CTA (NULL switches it off).  tools/latency_phases.py. */
+int tik_debug_latency_times(TikLatencyPlan* plan, void* dev_buf);
+
 /* Experiment hook, not used by the product path: makes the tensor-core kernel read its A operand `rows`
  * rows below the tile start (mode 1 also sets the descriptor's base-offset field).  See DESIGN.md. */
 int tik_debug_set_umma_shift(int rows, int mode);

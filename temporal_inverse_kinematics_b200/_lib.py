@@ -78,6 +78,13 @@ _PROTOS = {
     "tik_stgcn_plan_profile": (C.c_int, [vp, vp, i64, vp, vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]),
     "tik_stgcn_plan_launches": (i64, [vp, i64]),
     "tik_stgcn_plan_destroy": (None, [vp]),
+    "tik_stgcn_latency_workspace_bytes": (C.c_int, [C.POINTER(TikNet), i64, C.c_int, C.POINTER(i64)]),
+    "tik_stgcn_latency_create": (C.c_int, [C.POINTER(TikNet), i64, C.c_int, vp, i64, C.POINTER(vp)]),
+    "tik_stgcn_latency_run": (C.c_int, [vp, vp, i64, vp, vp]),
+    "tik_stgcn_latency_run_windows": (C.c_int, [vp, vp, C.POINTER(TikWindowing), i64, vp, vp]),
+    "tik_stgcn_latency_phases": (C.c_int, [vp]),
+    "tik_stgcn_latency_destroy": (None, [vp]),
+    "tik_debug_latency_times": (C.c_int, [vp, vp]),
     "tik_debug_set_umma_shift": (C.c_int, [C.c_int, C.c_int]),
     "tik_debug_set_umma_times": (C.c_int, [vp]),
 }

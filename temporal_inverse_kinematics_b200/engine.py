@@ -261,6 +261,50 @@ class Plan:
         return poses, feat
 
 
+class LatencyPlan:
+    """The whole forward for a handful of clips as ONE persistent cooperative kernel (csrc/latency.cu): fp32 arithmetic on
+    the fp32 packing, every layer a phase between grid-wide barriers.  Batch-1 windows are launch-bound on the
+    throughput plan (19-25 dependent launches); this is one launch."""
+
+    LIMIT_ROWS = 32                     # N * T' head rows
+
+    def __init__(self, packed, n_max, T):
+        if packed.code != L.TIK_F32:
+            raise ValueError("the latency plan takes the fp32 packing")
+        lib = L.lib()
+        self.packed, self.n_max, self.T = packed, n_max, T
+        nbytes = L.i64(0)
+        L.check(lib.tik_stgcn_latency_workspace_bytes(C.byref(packed.net), n_max, T, C.byref(nbytes)))
+        self.workspace = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=packed.device)
+        base = (self.workspace.data_ptr() + 255) // 256 * 256
+        handle = L.vp()
+        with L.on_device(packed.device):
+            L.check(lib.tik_stgcn_latency_create(C.byref(packed.net), n_max, T, C.c_void_p(base), nbytes.value, C.byref(handle)))
+        self.handle = handle
+        self.T_out = lib.tik_stgcn_out_frames(C.byref(packed.net), T)
+        self.phases = int(lib.tik_stgcn_latency_phases(handle))
+        self._fin = weakref.finalize(self, lib.tik_stgcn_latency_destroy, handle)
+
+    def launches(self, N):
+        return 1
+
+    def run(self, x):
+        p = self.packed
+        poses = torch.empty((x.shape[0], self.T_out, p.head_out), dtype=torch.float32, device=x.device)
+        with L.on_device(x):
+            L.check(L.lib().tik_stgcn_latency_run(self.handle, L.ptr(x), x.shape[0], L.ptr(poses), L.stream_ptr(x.device)))
+        return poses
+
+    def run_windows(self, seq, n_windows, offset, stride, root):
+        p = self.packed
+        win = L.TikWindowing(seq.shape[0], offset, stride, root[0] if root else -1, root[1] if root else -1)
+        poses = torch.empty((n_windows, self.T_out, p.head_out), dtype=torch.float32, device=seq.device)
+        with L.on_device(seq):
+            L.check(L.lib().tik_stgcn_latency_run_windows(self.handle, L.ptr(seq), C.byref(win), n_windows, L.ptr(poses),
+                                                          L.stream_ptr(seq.device)))
+        return poses
+
+
 MAX_HEAD_CLIPS = 16384   # clips whose features are kept for one head launch (143 MB in bf16 at T=64)
 
 
@@ -288,6 +332,7 @@ class Engine:
         self._packed = {}
         self._plans = {}
         self._stamp = None
+        self._watch = None
         self.weight_check = os.environ.get("TIK_WEIGHT_CHECK", "version")
 
     def invalidate(self):
@@ -295,16 +340,26 @@ class Engine:
         self._packed.clear()
         self._plans.clear()
         self._stamp = None
+        self._watch = None
+
+    def _collect(self, backbone, head):
+        """The tensors and scalars the folding reads.  Walking the module tree costs ~0.3-0.7 ms of host time, far more
+        than a batch-1 forward, so the lists are cached and re-walked only when the cheap stamp below changes (or after
+        invalidate() / _apply() / load_state_dict(), which EngineHolder hooks).  Not covered: re-ASSIGNING a Parameter
+        or buffer object of an already-run model (`bn.running_mean = t`): call invalidate_packed() after that."""
+        extra = [] if head is None else [head[0].weight, head[0].bias, head[2].weight, head[2].bias]
+        ts = list(backbone.parameters()) + list(backbone.buffers()) + extra
+        bns = [m for m in backbone.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
+        self._watch = (ts, bns)
+        return self._watch
 
     def _tensors(self, backbone, head):
-        extra = [] if head is None else [head[0].weight, head[0].bias, head[2].weight, head[2].bias]
-        return list(backbone.parameters()) + list(backbone.buffers()) + extra
+        return (self._watch or self._collect(backbone, head))[0]
 
-    def _stamp_now(self, backbone, head):
-        ts = self._tensors(backbone, head)
-        scalars = tuple(m.eps for m in backbone.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm))
-        scalars += (None if head is None else float(head[1]),)
-        stamp = tuple((t.data_ptr(), t._version, t.device.index) for t in ts) + scalars
+    def _stamp_now(self, backbone, head, fresh=False):
+        ts, bns = self._collect(backbone, head) if (fresh or self._watch is None) else self._watch
+        stamp = (tuple([t._version for t in ts]), tuple([t.data_ptr() for t in ts]), ts[0].device,
+                 tuple([m.eps for m in bns]), None if head is None else float(head[1]))
         if self.weight_check == "content":
             # <= 64 strided samples + the sum of each tensor, reduced on the device, one read-back
             with torch.no_grad():
@@ -315,14 +370,19 @@ class Engine:
             raise ValueError("weight_check must be 'version' or 'content'")
         return stamp
 
-    def plan(self, dtype_name, N, T, chunk=None):
-        backbone = self._backbone()
-        head = self._head_fn() if self._head_fn else None
+    def _refresh(self, backbone, head):
+        """Re-fold if anything the folding reads has changed."""
         stamp = self._stamp_now(backbone, head)
         if stamp != self._stamp:
+            stamp = self._stamp_now(backbone, head, fresh=True)      # objects may have been replaced: walk the tree again
             self._packed.clear()
             self._plans.clear()
             self._stamp = stamp
+
+    def plan(self, dtype_name, N, T, chunk=None):
+        backbone = self._backbone()
+        head = self._head_fn() if self._head_fn else None
+        self._refresh(backbone, head)
         if dtype_name not in self._packed:
             self._packed[dtype_name] = PackedNet(backbone, head, dtype_name)
         n_chunk = int(chunk) if chunk else default_chunk(T)
@@ -339,6 +399,25 @@ class Engine:
         return self._plans[key]
 
 
+def _latency_plan(self, N, T):
+    """Engine.latency_plan: cached LatencyPlan for up to N clips of T frames (fp32 packing, one per device / stream)."""
+    backbone = self._backbone()
+    head = self._head_fn() if self._head_fn else None
+    self._refresh(backbone, head)
+    if "fp32" not in self._packed:
+        self._packed["fp32"] = PackedNet(backbone, head, "fp32")
+    dev = self._packed["fp32"].device
+    key = ("latency", int(N), T, dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    if key not in self._plans:
+        if len(self._plans) >= 8:
+            self._plans.pop(next(iter(self._plans)))
+        self._plans[key] = LatencyPlan(self._packed["fp32"], int(N), T)
+    return self._plans[key]
+
+
+Engine.latency_plan = _latency_plan
+
+
 class EngineHolder:
     """Mixin for the modules that own an Engine: the engine (weak reference, ctypes handles, device workspaces) is a
     cache, not state -- it is dropped by pickling / ``torch.save(model)`` / ``copy.deepcopy`` and rebuilt lazily, as
@@ -353,8 +432,19 @@ class EngineHolder:
                 state[k] = None
         return state
 
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float(): buffers are REPLACED by new tensor objects, so the engine's cached lists go stale
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate_packed()
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_packed()
+        return out
+
     def invalidate_packed(self):
-        """Forget folded weights / plans (call after writing parameters through ``.data``)."""
+        """Forget folded weights / plans (call after writing parameters through ``.data`` or re-assigning them)."""
         for m in self.modules():
             if isinstance(m, EngineHolder):
                 if getattr(m, "_engine", None) is not None:

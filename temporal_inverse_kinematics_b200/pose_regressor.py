@@ -41,6 +41,9 @@ class PoseRegressor(engine.EngineHolder, nn.Module, _ComputeDtypeMixin):
         self.chunk_clips = None
         self.use_cuda_graph = os.environ.get("TIK_CUDA_GRAPH", "0") == "1"   # replay the launch sequence as one graph
         self.weight_check = None           # None = engine default ('version'); 'content': see engine.Engine
+        # low_latency: batches of a few clips (N * T' <= 32, e.g. one streaming window) run as ONE persistent cooperative
+        # kernel in fp32 (engine.LatencyPlan) instead of the launch-bound 19-25 kernel throughput plan
+        self.low_latency = os.environ.get("TIK_LOW_LATENCY", "0") == "1"
         self._engine = None
 
     def _head(self):
@@ -50,7 +53,28 @@ class PoseRegressor(engine.EngineHolder, nn.Module, _ComputeDtypeMixin):
         if self._engine is None:
             self._engine = engine.Engine(self.backbone, self._head)
         self._engine.weight_check = self.weight_check or self._engine.weight_check
+        if self._use_latency_plan(N, T):
+            return self._engine.latency_plan(N, T)
         return self._engine.plan(self.compute_dtype, N, T, self.chunk_clips)
+
+    def session(self, N, T):
+        """A bound forward for a serving loop: resolves the plan for (N, T) ONCE (weights are folded as they are now) and
+        returns ``run(x) -> poses`` that only launches -- none of ``forward``'s per-call checks (eval / device / shape
+        checks, the cache stamp over ~160 tensors: ~50 us of Python, as much as the kernel at batch 1).  ``x`` must be a
+        contiguous fp32 CUDA tensor of exactly (N, T, V, C) on the model's device and current stream; make a new session
+        after changing weights.  Uses the latency plan when ``low_latency`` is set and the batch fits it."""
+        if self.training:
+            raise NotImplementedError("PoseRegressor.session: eval-mode inference only")
+        plan = self.plan_for(N, T)
+        if isinstance(plan, engine.LatencyPlan):
+            return plan.run
+        if self.use_cuda_graph:
+            return plan.run_graphed
+        return lambda x: plan.run(x)[0]
+
+    def _use_latency_plan(self, N, T):
+        return (self.low_latency and self.backbone.A.size(0) == 1 and len(self.backbone.st_gcn_networks) >= 2
+                and N * self.backbone.out_frames(T) <= engine.LatencyPlan.LIMIT_ROWS)
 
     def forward(self, x, init_pose=None, n_iter=3):
         """x (N, T, V, C) -> {'poses': (N, T', 66)} axis-angle, joint-major (reference pose_trainer.py:94-133).
@@ -62,6 +86,8 @@ class PoseRegressor(engine.EngineHolder, nn.Module, _ComputeDtypeMixin):
         if N == 0:
             return {"poses": x.new_zeros((0, self.backbone.out_frames(T), self.pose_dim))}
         plan = self.plan_for(N, T)
+        if isinstance(plan, engine.LatencyPlan):
+            return {"poses": plan.run(x)}
         poses = plan.run_graphed(x) if self.use_cuda_graph else plan.run(x)[0]
         return {"poses": poses}
 

@@ -255,3 +255,55 @@ def test_bf16_edge_shapes(n, t):
     got = m(x.cuda())["poses"].cpu()
     assert got.shape == want.shape and torch.isfinite(got).all()
     assert float((got - want).abs().max()) < TOL_BF16_ABS
+
+
+@pytest.mark.parametrize("n,t", [(1, 64), (2, 64), (1, 9), (7, 9), (32, 9), (1, 13), (3, 33), (4, 128), (1, 1), (2, 200)])
+def test_latency_plan_matches_reference_path(n, t):
+    """One persistent cooperative kernel for a handful of clips (csrc/latency.cu): fp32, so the 1e-4 parity bar of the
+    fp32 path applies, and it must agree with the multi-launch fp32 plan to rounding."""
+    m, sd = _model()
+    x = synth.make_clips(n, t, seed=7000 + 10 * n + t)
+    want = sp.regressor_forward(sd, x)["poses"]
+    multi = m(x.cuda())["poses"].cpu()
+    m.low_latency = True
+    plan = m.plan_for(n, t)
+    from temporal_inverse_kinematics_b200 import engine
+    assert isinstance(plan, engine.LatencyPlan) and plan.launches(n) == 1
+    got = m(x.cuda())["poses"].cpu()
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) < TOL_F32
+    assert float((got - multi).abs().max()) < 2e-5
+    # batches above the head's 32-row limit fall back to the throughput plan
+    big = synth.make_clips(40, t, seed=1)
+    assert not isinstance(m.plan_for(40, t), engine.LatencyPlan) or 40 * m.backbone.out_frames(t) <= 32
+    assert m(big.cuda())["poses"].shape[0] == 40
+
+
+def test_latency_plan_dance_batch1_and_windows(golden):
+    """configs[0] through the latency plan (231 windows of 9 frames, batch 1) and window mode of configs[4]."""
+    g = golden("dance.npz")
+    m, sd = _model()
+    m.low_latency = True
+    names = [str(s) for s in g["joint_3d_names"]]
+    wins = sp.inference_windows(sp.moveai_to_coco(g["joints_3d"], names), 9).astype(np.float32)
+    y1 = torch.cat([m(torch.from_numpy(wins[i:i + 1]).cuda())["poses"] for i in range(0, 231, 11)]).cpu().numpy()
+    assert np.abs(y1 - g["poses"][::11]).max() < TOL_F32
+    F = 150
+    seq = synth.make_clips(1, F, seed=33)[0]
+    idx = (torch.arange(4)[:, None] * 3 + torch.arange(64)[None, :] - 32).clamp(0, F - 1)
+    w = seq[idx]
+    w = w - 0.5 * (w[:, :, 11] + w[:, :, 12])[:, :, None, :]
+    want = sp.regressor_forward(sd, w)["poses"]
+    got = m.forward_windows(seq.cuda(), 64, offset=-32, stride=3, root=(11, 12), n_windows=4)["poses"].cpu()
+    assert float((got - want).abs().max()) < TOL_F32
+
+
+def test_session_is_the_same_forward():
+    """model.session(N, T): the bound forward of a serving loop returns exactly what model(x) returns, on every plan."""
+    x = synth.make_clips(1, 64, seed=77).cuda()
+    for dtype, low, graph in (("bf16", False, False), ("bf16", False, True), ("fp32", True, False)):
+        m, _ = _model(dtype=dtype)
+        m.low_latency, m.use_cuda_graph = low, graph
+        want = m(x)["poses"]
+        run = m.session(1, 64)
+        assert torch.equal(run(x), want) and torch.equal(run(x), want)

@@ -22,7 +22,7 @@ for what in "$@"; do
         cat gpurun_out/bench_c$c.json; tail -3 gpurun_out/bench_c$c.err
       done ;;
     trace)
-      TIK_PLAN_TRACE=1 timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu --no-hbm > gpurun_out/trace.json 2> gpurun_out/trace.err; grep "tik trace" gpurun_out/trace.err | tail -24 ;;
+      TIK_PLAN_TRACE=1 timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu --no-hbm --no-c3 > gpurun_out/trace.json 2> gpurun_out/trace.err; grep "tik trace" gpurun_out/trace.err | tail -24 ;;
     hbm)
       timeout 600 python tools/hbm_bench.py > gpurun_out/hbm_bench.log 2>&1; echo "hbm exit $?" | tee -a gpurun_out/summary.txt; cat gpurun_out/hbm_bench.log ;;
     hbm_fk_sweep)
@@ -36,15 +36,15 @@ for what in "$@"; do
           -c 16 -f -o gpurun_out/prof_hbm python tools/hbm_bench.py 2097152 --once > gpurun_out/ncu_hbm.log 2>&1
       echo "ncu_hbm exit $?" | tee -a gpurun_out/summary.txt ;;
     ncu_net)
-      timeout 300 python bench.py --steps 1 --warmup 3 --no-cpu --no-hbm > gpurun_out/net_plain.log 2>&1 &&
+      timeout 300 python bench.py --steps 1 --warmup 3 --no-cpu --no-hbm --no-c3 > gpurun_out/net_plain.log 2>&1 &&
       timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum \
           --clock-control none -k regex:'rowgemm|tcn_halo|gcn_fused|stem_|block_fused|fk_|aggregate' -c 120 --csv --log-file gpurun_out/launches.csv \
-          python bench.py --steps 1 --warmup 3 --no-cpu --no-hbm --no-graph > gpurun_out/ncu_net.log 2>&1
+          python bench.py --steps 1 --warmup 3 --no-cpu --no-hbm --no-c3 --no-graph > gpurun_out/ncu_net.log 2>&1
       echo "ncu_net exit $?" | tee -a gpurun_out/summary.txt ;;
     ncu_full)
-      timeout 300 python bench.py --steps 1 --warmup 3 --no-cpu --no-hbm --no-graph > gpurun_out/full_plain.log 2>&1 &&
+      timeout 300 python bench.py --steps 1 --warmup 3 --no-cpu --no-hbm --no-c3 --no-graph > gpurun_out/full_plain.log 2>&1 &&
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'rowgemm|tcn_halo|gcn_fused|stem_|block_fused' -s 60 -c 20 -f -o gpurun_out/prof_net \
-          python bench.py --steps 1 --warmup 3 --no-cpu --no-hbm --no-graph > gpurun_out/ncu_full.log 2>&1
+          python bench.py --steps 1 --warmup 3 --no-cpu --no-hbm --no-c3 --no-graph > gpurun_out/ncu_full.log 2>&1
       echo "ncu_full exit $?" | tee -a gpurun_out/summary.txt ;;
   esac
 done
