@@ -12,11 +12,16 @@
 // with the BN-folded weights (and the identity block that carries the residual) written once per CTA into tensor
 // memory, N = the tile's rows rounded up to 16; output column n = j*(T+2) + t is valid for t < T.
 // One ring stage = one tile (all of its 64-channel chunks): one barrier hand-off per tile.
+// Long clips are cut into SEGMENTS of L frames: a tile is then G row groups x (L + 2) frames starting at frame t0 - 1;
+// the halo rows of an interior segment are the neighbouring segment's real frames (same TMA box, other start
+// coordinate), only the clip ends are out-of-bounds zero fill.  T = 64 at 128 channels thereby runs with the T = 32
+// tile shape (3 x 34 rows, N = 112) instead of one 66-row group per tile (N = 80): 370 -> ~295 us per launch.
 //
 // Measured (B=4096): b1 (64 ch, T=64) 410 us (SS, per-tap boxes) -> 324 (TS, per-tap boxes) -> 297 us here; b3/b4
 // (128 ch, T=32) 397 -> 338 -> 288 us = 5.8 TB/s of DRAM traffic, 89 % of the copy peak.  The channel-major accumulator
 // is transposed by the epilogue with tcgen05.ld.16x256b fragments + stmatrix.trans; a first version with 2-byte
 // shared-memory stores was instruction-bound and 2x slower than the kernels it replaces.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -37,7 +42,8 @@ struct TcnHaloParams {
   const __nv_bfloat16* w;        // (c_out, ktot) row-major: [tap 0 | tap 1 | tap 2 | identity]
   const float* bias;             // (c_out)
   int32_t ktot, c, c_out;        // c = channels of H and X (= c_out)
-  int32_t T, R, G, N;            // R = T + 2 rows per row group, G row groups per tile, N = MMA columns (multiple of 16)
+  int32_t T, R, G, N;            // T frames per clip, R = L + 2 rows per row group and tile, G row groups per tile, N = MMA columns (multiple of 16)
+  int32_t L, segs;               // segment length (frames of a row group per tile) and segments per row group
   int32_t acc_stride;            // TMEM columns between the two accumulators
   int32_t kc;                    // 64-channel chunks of H (= of X)
   int32_t chunk_bytes, stage_bytes, stages;
@@ -112,12 +118,13 @@ __global__ void __launch_bounds__(kThThreads, 1) tcn_halo_kernel(const __grid_co
       const uint32_t box_bytes = (uint32_t)(p.G * p.R * 128);
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int nv0 = tile * p.G;
+        const int nv0 = (tile / p.segs) * p.G;
+        const int t0 = (tile % p.segs) * p.L;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_expect_tx(&full_bar[stage], box_bytes * (uint32_t)chunks);
         uint8_t* dst = ring + (size_t)stage * p.stage_bytes;
-        for (int c = 0; c < p.kc; ++c) tma_load_3d(dst + (size_t)c * p.chunk_bytes, &p.map_h, &full_bar[stage], c * 64, -1, nv0);
-        for (int c = 0; c < p.kc; ++c) tma_load_3d(dst + (size_t)(p.kc + c) * p.chunk_bytes, &p.map_x, &full_bar[stage], c * 64, -1, nv0);
+        for (int c = 0; c < p.kc; ++c) tma_load_3d(dst + (size_t)c * p.chunk_bytes, &p.map_h, &full_bar[stage], c * 64, t0 - 1, nv0);
+        for (int c = 0; c < p.kc; ++c) tma_load_3d(dst + (size_t)(p.kc + c) * p.chunk_bytes, &p.map_x, &full_bar[stage], c * 64, t0 - 1, nv0);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(kThThreads, 1) tcn_halo_kernel(const __grid_co
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         mbar_wait(&stage_full[sbuf], sphase);
         for (int c = 0; c < regions; ++c)
-          tma_store_3d(&p.map_out, s_stage + ((size_t)sbuf * regions + c) * p.region_bytes, c * 64, 0, tile * p.G);
+          tma_store_3d(&p.map_out, s_stage + ((size_t)sbuf * regions + c) * p.region_bytes, c * 64, (tile % p.segs) * p.L, (tile / p.segs) * p.G);
         tma_store_commit();
         if (p.stage_bufs == 2) {
           tma_store_wait_read1();
@@ -233,8 +240,8 @@ __global__ void __launch_bounds__(kThThreads, 1) tcn_halo_kernel(const __grid_co
           if (ch < n_chunks16) {
             const int n = ch * 16 + a_col;                  // column n = j*R + t  ->  row group j, frame t
             const int j = n / p.R, t = n - j * p.R;
-            const bool ok = j < p.G && t < p.T;
-            const int r = j * p.T + t;                      // staging row
+            const bool ok = j < p.G && t < p.L;
+            const int r = j * p.L + t;                      // staging row
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int co0 = lane_grp * 32 + 16 * h;
@@ -275,10 +282,28 @@ struct TcnHaloPrepared {
 
 bool tcn_halo_supported(int c, int c_out, int kt, int stride, int T, bool identity_slab) {
   if (!(identity_slab && kt == 3 && stride == 1 && c == c_out && (c_out == 64 || c_out == 128))) return false;
-  const int R = T + 2;
-  const int ktot = 4 * c;
-  const int n_max = ((512 - ktot / 2) / 2) / 32 * 32;        // two accumulators beside the weights, 32-column pitch
-  return R <= n_max && R <= 256;
+  (void)T;                                                   // any T: long clips are cut into segments
+  return true;
+}
+
+// Segment length.  The whole clip (the tuned shapes: T = 32 at 128 channels, T = 64 at 64 channels) unless cutting it
+// fills the MMA columns clearly better or the clip does not fit a tile at all.  Candidates are the divisors of T (no
+// ragged last segment); score = valid rows per MMA column minus a charge for the two halo rows every segment re-loads.
+static int tcn_halo_segment(int T, int n_max) {
+  auto score = [&](int L) {
+    const int G = n_max / (L + 2);
+    if (G < 1) return -1.0;
+    const int N = (G * (L + 2) + 15) / 16 * 16;
+    return (double)G * L / N - 0.5 * (2.0 / L - 2.0 / T);
+  };
+  int best = T + 2 <= n_max ? T : 0;
+  double best_s = best ? score(T) + 0.03 : -1.0;             // hysteresis: leave the whole-clip shape only for a clear win
+  for (int L = std::min(T - 1, n_max - 2); L >= 8; --L) {
+    if (T % L) continue;
+    const double sc = score(L);
+    if (sc > best_s + 1e-9) { best_s = sc; best = L; }
+  }
+  return best ? best : std::min(T, n_max - 2);               // no divisor fits: ragged last segment (TMA clips it)
 }
 
 int tcn_halo_prepare(const void* h, const void* x, const void* w, const float* bias, void* out, int64_t nv_cap, int T, int c,
@@ -289,8 +314,12 @@ int tcn_halo_prepare(const void* h, const void* x, const void* w, const float* b
   memset(&p, 0, sizeof(p));
   p.w = reinterpret_cast<const __nv_bfloat16*>(w); p.bias = bias;
   p.c = c; p.c_out = c; p.ktot = 4 * c; p.kc = c / 64;
-  p.T = T; p.R = T + 2;
-  const int n_max = ((512 - p.ktot / 2) / 2) / 32 * 32;
+  const int n_max = ((512 - p.ktot / 2) / 2) / 32 * 32;   // two accumulators beside the weights, 32-column pitch
+  p.T = T;
+  p.L = tcn_halo_segment(T, std::min(n_max, 256));
+  if (const char* e = getenv("TIK_HALO_SEG")) { const int l = atoi(e); if (l >= 1 && l <= T && l + 2 <= n_max) p.L = l; }
+  p.segs = (T + p.L - 1) / p.L;
+  p.R = p.L + 2;
   p.G = n_max / p.R;
   if ((int64_t)p.G > nv_cap) p.G = (int)nv_cap;
   p.N = (p.G * p.R + 15) / 16 * 16;
@@ -298,7 +327,7 @@ int tcn_halo_prepare(const void* h, const void* x, const void* w, const float* b
   p.chunk_bytes = p.N * 128;
   if (p.chunk_bytes % 1024) p.chunk_bytes = (p.chunk_bytes / 1024 + 1) * 1024;
   p.stage_bytes = 2 * p.kc * p.chunk_bytes;
-  p.region_bytes = (p.G * T * 128 + 1023) / 1024 * 1024;
+  p.region_bytes = (p.G * p.L * 128 + 1023) / 1024 * 1024;
   const int regions = c / 64;
   p.stage_bufs = 2;
   p.stages = (kThSmemBudget - 768 - p.stage_bufs * regions * p.region_bytes) / p.stage_bytes;
@@ -315,7 +344,7 @@ int tcn_halo_prepare(const void* h, const void* x, const void* w, const float* b
     uint32_t box[3] = {64, (uint32_t)p.R, (uint32_t)p.G};
     rc = encode_bf16_map(&p.map_h, h, 3, dims, strides, box);
     if (rc == TIK_OK) rc = encode_bf16_map(&p.map_x, x, 3, dims, strides, box);
-    uint32_t obox[3] = {64, (uint32_t)T, (uint32_t)p.G};
+    uint32_t obox[3] = {64, (uint32_t)p.L, (uint32_t)p.G};
     if (rc == TIK_OK) rc = encode_bf16_map(&p.map_out, out, 3, dims, strides, obox);
   }
   if (rc != TIK_OK) { delete g; return rc; }
@@ -328,7 +357,7 @@ int tcn_halo_launch(TcnHaloPrepared* g, int64_t nv, cudaStream_t s) {
   if (nv <= 0) return TIK_OK;
   TcnHaloParams p = g->p;
   p.nv = nv;
-  p.n_tiles = (int32_t)((nv + p.G - 1) / p.G);
+  p.n_tiles = (int32_t)((nv + p.G - 1) / p.G) * p.segs;
   static bool attr_done[64] = {};
   int dev = 0;
   TIK_CUDA(cudaGetDevice(&dev));

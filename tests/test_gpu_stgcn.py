@@ -244,7 +244,7 @@ def test_bf16_kernel_variants_agree(monkeypatch, switch):
 
 
 @pytest.mark.parametrize("n,t", [(1, 1), (1, 2), (2, 11), (1, 12), (2, 13), (3, 25), (7, 33), (2, 61), (1, 65), (2, 95),
-                                 (1, 100), (2, 126), (1, 127), (1, 129), (1, 190), (1, 200), (33, 16)])
+                                 (1, 100), (2, 126), (1, 127), (1, 129), (1, 190), (1, 191), (1, 200), (1, 256), (33, 16)])
 def test_bf16_edge_shapes(n, t):
     """Tile-boundary cases of the specialised kernels: 12 output frames per tile in the fused first block, G row groups
     of T+2 rows per tile in the halo temporal conv (unsupported above 126 / 190 frames -> per-tap kernels), odd tile
