@@ -512,29 +512,6 @@ def measure(args, dev, world, rank, local):
         step(x_dev, i)
     barrier()
 
-    # ---- parity of what was just computed, against the CPU arm on the same clips (rank 0)
-    parity = cpu = None
-    if rank == 0 and not args.no_cpu:
-        torch.set_num_threads(os.cpu_count() or 1)
-        arm = CpuArm(want_port=args.port)
-        xs = x_host[:n_sample].clone()
-        fps, sec, threads, (w_poses, w_R, w_joints) = arm.time(xs, 3)
-        pg = poses_local[:n_sample]
-        jg, Rg = smpl_util.fk_body(pg.reshape(-1, J, 3), rest, parents, want_local=True)
-        # joints: what the timed step itself produced (joints-only FK kernel); rotmats: the local rotations of the
-        # same poses from the FK kernel's want_local variant
-        got = {"poses": pg.cpu().numpy(), "rotmats": Rg.cpu().numpy(), "joints": joints_local[:n_sample * T_out].cpu().numpy()}
-        del jg
-        parity = _parity(dtype, got, {"poses": w_poses, "rotmats": w_R, "joints": w_joints})
-        parity["clips"] = n_sample
-        parity["against"] = arm.kind
-        n1 = max(8, n_sample // 8)
-        fps1, sec1, _, _ = arm.time(xs[:n1], 1, warm=0, threads=1)
-        cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": arm.kind,
-               "sample": f"{n_sample} of the {n_local} clips (T={T}), 3 iterations, {arm.describe()}; {sec:.2f} s/iteration",
-               "one_thread": {"value": fps1, "clips": n1, "s_per_iteration": sec1}, "host_cpus": os.cpu_count()}
-    barrier()
-
     # ---- device-resident timing: CUDA events per step on the launching stream, L2 flushed between steps
     sampler.mark()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -548,7 +525,7 @@ def measure(args, dev, world, rank, local):
     main_stream.wait_stream(side)                                # the last overlapped gather belongs to the timed region
     t_end.record()
     barrier()
-    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    ms_steps = sorted(a.elapsed_time(b) for a, b in ev)
     ms = (sum(ms_steps) + max(0.0, ev[-1][1].elapsed_time(t_end))) / args.steps
     g_ms = sum(a.elapsed_time(b) for a, b in gather_ms) / len(gather_ms) if gather_ms else 0.0
 
@@ -608,6 +585,29 @@ def measure(args, dev, world, rank, local):
     ms_e2e = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- parity of what the last step computed, against the CPU arm on the same clips (rank 0).  After the timed
+    # regions: seconds of CPU-only work just before them would let the GPU fall into an idle power state.
+    parity = cpu = None
+    if rank == 0 and not args.no_cpu:
+        torch.set_num_threads(os.cpu_count() or 1)
+        arm = CpuArm(want_port=args.port)
+        xs = x_host[:n_sample].clone()
+        fps, sec, threads, (w_poses, w_R, w_joints) = arm.time(xs, 3)
+        pg = poses_local[:n_sample]
+        jg, Rg = smpl_util.fk_body(pg.reshape(-1, J, 3), rest, parents, want_local=True)
+        # joints: what the timed step itself produced (joints-only FK kernel); rotmats: the local rotations of the
+        # same poses from the FK kernel's want_local variant
+        got = {"poses": pg.cpu().numpy(), "rotmats": Rg.cpu().numpy(), "joints": joints_local[:n_sample * T_out].cpu().numpy()}
+        del jg
+        parity = _parity(dtype, got, {"poses": w_poses, "rotmats": w_R, "joints": w_joints})
+        parity["clips"] = n_sample
+        parity["against"] = arm.kind
+        n1 = max(8, n_sample // 8)
+        fps1, sec1, _, _ = arm.time(xs[:n1], 1, warm=0, threads=1)
+        cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": arm.kind,
+               "sample": f"{n_sample} of the {n_local} clips (T={T}), 3 iterations, {arm.describe()}; {sec:.2f} s/iteration",
+               "one_thread": {"value": fps1, "clips": n1, "s_per_iteration": sec1}, "host_cpus": os.cpu_count()}
+
     t = torch.tensor([ms, ms_e2e, g_ms], device=dev, dtype=torch.float64)
     t_min = t.clone()
     if world > 1:
@@ -646,7 +646,8 @@ def measure(args, dev, world, rank, local):
                 roofline["dram"] = {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                                     "note": "DRAM bytes per launch from the committed ncu capture / live launch time"}
         line = {"metric": METRIC, "value": frames / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms, "ms_per_step_min_median_max_rank0": [ms_steps[0], ms_steps[len(ms_steps) // 2], ms_steps[-1]],
+                "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
                 "dtype": dtype, "data": "synthetic",
                 "config": {"workload": workload_name(args.config, world), "global_batch": total, "clips_per_gpu": n_local,
                            "frames_per_step": frames, "micro_batch_clips": micro, "chunk_clips": plan.n_chunk,
@@ -682,7 +683,7 @@ def _config1_rot6d(dev, IterativePoseRegressor, default_hparams, synth, A, x_dev
     m = IterativePoseRegressor(default_hparams()).eval()
     m.load_state_dict(synth.make_iterative_state(A, seed=0))
     m = m.to(dev).set_compute_dtype("fp32")
-    for _ in range(3):
+    for _ in range(12):                                          # also brings the clocks back up after the CPU arm
         m(x_dev)
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
