@@ -34,14 +34,14 @@
 
 namespace tik {
 
-constexpr int kSbL = 14;                            // frames per tile incl. halo
-constexpr int kSbLoMax = 12;                        // output frames per tile
+constexpr int kSbL = 15;                            // frames per tile incl. halo (V * kSbL <= 256 rows = two 128-row MMA tiles)
+constexpr int kSbLoMax = kSbL - 2;                 // output frames per tile (T = 64: 5 tiles of 13 instead of 6 of 12)
 constexpr int kSbCout = 64;
 constexpr int kSbEpiWarps = 16, kSbBuildWarps = 8;
 constexpr int kSbThreads = 64 + 32 * kSbEpiWarps + 32 * kSbBuildWarps;   // 832
 constexpr int kSbTile = 16384;                      // 128 rows x 128 B
 constexpr int kSbHBytes = 1024 + 2 * kSbTile + 1024;   // 8 guard rows + 256 rows + 8 guard rows
-constexpr int kSbMaxV = 18;                         // V * 14 <= 256
+constexpr int kSbMaxV = 256 / kSbL;                // V * kSbL <= 256
 // shared-memory map (bytes from the 1024-aligned base)
 constexpr int kSbOffW16 = 0;                        // stacked [Wg' ; Wr'] : 128 rows x 64 K
 constexpr int kSbOffWt = kSbOffW16 + kSbTile;       // 3 taps x (64 rows x 64 K)
