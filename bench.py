@@ -460,13 +460,18 @@ def measure(args, dev, world, rank, local):
     mbs = [(m0, min(n_local, m0 + micro)) for m0 in range(0, n_local, micro)]
     sizes = [shard_bounds(total, r, world)[1] - shard_bounds(total, r, world)[0] for r in range(world)] if args.config == 3 else [n_local] * world
     assert len(set(sizes)) == 1 or world == 1, "bench shards are equal-sized (65,536 and 4096*N divide by 1/2/4/8)"
-    gathered = [torch.empty((world * n_local, T_out, 66), device=dev) for _ in range(2)] if world > 1 else None
+    RING = 4                                                     # configs[2] at N>1: steps a rank may run ahead of its gathers
+    n_gath = 2 if args.config == 3 else RING
+    gathered = [torch.empty((world * n_local, T_out, 66), device=dev) for _ in range(n_gath)] if world > 1 else None
+    snaps = [torch.empty_like(poses_local) for _ in range(RING)] if (world > 1 and args.config != 3) else None
+    snap_ready = [torch.cuda.Event() for _ in range(RING)]
+    snap_free = [torch.cuda.Event() for _ in range(RING)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     main_stream = torch.cuda.current_stream(dev)
     side = torch.cuda.Stream(device=dev)
     gather_ms = []
-    cloned = torch.cuda.Event()
-    cloned.record(main_stream)
+    for e in snap_free:
+        e.record(main_stream)
 
     def solve(xm, m0, m1):
         poses = model(xm)["poses"]                               # (n, T', 66) axis-angle
@@ -487,14 +492,19 @@ def measure(args, dev, world, rank, local):
             if timed:
                 e1.record(main_stream)
         else:
-            side.wait_stream(main_stream)
+            # The step's poses are snapshotted on the compute stream (4 MB device copy) into a ring of RING buffers; the
+            # side stream gathers them.  A rank only waits for its own gather of RING steps ago, so the ranks are not
+            # locked to the slowest GPU of every single step (power-cap jitter), only to the slowest GPU over the run.
+            k = i % RING
+            main_stream.wait_event(snap_free[k])
+            snaps[k].copy_(poses_local)
+            snap_ready[k].record(main_stream)
             with torch.cuda.stream(side):
-                src = poses_local.clone()                        # poses_local is overwritten by the next step
-                cloned.record(side)
-                dist.all_gather_into_tensor(gathered[i % 2], src)
+                side.wait_event(snap_ready[k])
+                dist.all_gather_into_tensor(gathered[k], snaps[k])
+                snap_free[k].record(side)
 
     def step(x, i=0, timed=False):
-        main_stream.wait_event(cloned)                           # the previous step's poses have been snapshotted
         for m0, m1 in mbs:
             solve(x[m0:m1], m0, m1)
         gather(i, timed)
@@ -654,7 +664,7 @@ def measure(args, dev, world, rank, local):
                            "cuda_graph": bool(model.use_cuda_graph), "l2": "flushed between timed steps (256 MiB memset)",
                            "parallelism": f"dp{world}",
                            "gather": ("none" if world == 1 else "ONE NCCL all_gather of the poses at the end of the step, on the compute stream"
-                                      if args.config == 3 else "NCCL all_gather of the poses per step on a side stream (overlaps the next step)"),
+                                      if args.config == 3 else "NCCL all_gather of the poses per step on a side stream from a 4-deep snapshot ring (overlaps the next steps)"),
                            "e2e_pipeline": "pinned H2D of micro-batch k+1 and D2H of step i's results overlap compute on a copy stream"},
                 "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": world * x_host.numel() * 4,

@@ -117,3 +117,50 @@ def test_run_smpl_inference_signature():
     assert np.abs(j0[:, 0] - m.rest_joints[0]).max() < 1e-6
     with pytest.raises(NotImplementedError):
         SU.run_smpl_inference(data, models, "cuda", return_mesh=True)
+
+
+def test_bulk_kernels_write_only_their_outputs():
+    """compute-sanitizer is closed on the GPU pool, so the bulk-async (cp.async.bulk) kernels are checked with guard
+    regions: outputs are carved out of a larger sentinel-filled buffer through the raw C ABI, for sizes around the
+    bulk / remainder split (whole 256-rotation and 128- / 64-frame tiles, plus ragged tails)."""
+    import ctypes as C
+    from temporal_inverse_kinematics_b200 import _lib as L, geometry as G, smpl_util as SU
+    lib = L.lib()
+    stream = L.stream_ptr(torch.device("cuda"))
+    GUARD, SENT = 4096, 12345.0
+
+    def guarded(n_out):
+        buf = torch.full((GUARD + n_out + GUARD,), SENT, dtype=torch.float32, device="cuda")
+        return buf, buf[GUARD:GUARD + n_out]
+
+    def check(buf, n_out, what):
+        assert bool((buf[:GUARD] == SENT).all()) and bool((buf[GUARD + n_out:] == SENT).all()), what
+        assert bool(torch.isfinite(buf[GUARD:GUARD + n_out]).all()) and not bool((buf[GUARD:GUARD + n_out] == SENT).any()), what
+
+    for M in (148 * 256, 148 * 256 + 1, 148 * 256 * 3 + 255, 37):
+        x3 = torch.randn(M, 3, device="cuda") * 0.7
+        x6 = torch.randn(M, 6, device="cuda")
+        for name, fn, x, per in (("rodrigues", lib.tik_batch_rodrigues, x3, 9), ("aa_kornia", lib.tik_aa_to_rotmat, x3, 9),
+                                 ("rot6d", lib.tik_rot6d_to_rotmat, x6, 9)):
+            buf, out = guarded(M * per)
+            L.check(fn(L.ptr(x), L.ptr(out), M, stream))
+            torch.cuda.synchronize()
+            check(buf, M * per, (name, M))
+        R = G.batch_rodrigues(x3)
+        buf, out = guarded(M * 3)
+        L.check(lib.tik_rotmat_to_aa(L.ptr(R), L.ptr(out), M, 0, stream))
+        torch.cuda.synchronize()
+        check(buf, M * 3, ("rotmat_to_aa", M))
+    rest, parents = synth.make_rest_skeleton(), synth.SMPLX_BODY_PARENTS
+    full = SU.SyntheticBodyModel(skeleton="full")
+    for J, rj, par, frames in ((22, rest, parents, (128, 129, 128 * 7 + 5, 127)), (60, full.rest_joints, full.parents, (64, 65, 64 * 5 + 3, 63))):
+        rj = np.ascontiguousarray(np.asarray(rj, dtype=np.float32))
+        pa = np.ascontiguousarray(np.asarray(par, dtype=np.int32))
+        for F in frames:
+            pose = torch.randn(F, J, 3, device="cuda") * 0.5
+            buf, out = guarded(F * J * 3)
+            L.check(lib.tik_fk_body(L.ptr(pose), 0, rj.ctypes.data_as(C.POINTER(C.c_float)), pa.ctypes.data_as(C.POINTER(C.c_int32)), J,
+                                    None, L.ptr(out), None, None, F, stream))
+            torch.cuda.synchronize()
+            check(buf, F * J * 3, ("fk", J, F))
+            assert torch.equal(out.view(F, J, 3), SU.fk_body(pose, rj, par))
