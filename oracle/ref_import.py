@@ -18,12 +18,28 @@ import types
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+_snapshot = False
+
+
 def _find_root():
-    """The reference checkout (dev container), else the snapshot oracle/build_ref.py made of its hot-path files
-    (``oracle/_ref``, which travels to the GPU box)."""
-    for cand in (os.environ.get("TIK_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+    """The reference checkout (dev container), else the archive oracle/build_ref.py made of its hot-path files
+    (``oracle/_ref/hot_path.tar.gz``, which travels to the GPU box), unpacked into a temporary directory outside the
+    repository for the life of the process."""
+    global _snapshot
+    for cand in (os.environ.get("TIK_REFERENCE_ROOT"), "/root/reference"):
         if cand and os.path.isdir(os.path.join(cand, "mmskeleton")):
             return cand
+    archive = os.path.join(_HERE, "_ref", "hot_path.tar.gz")
+    if os.path.exists(archive):
+        import atexit
+        import shutil
+        import tempfile
+        from . import build_ref
+        dst = tempfile.mkdtemp(prefix="tik_ref_")
+        atexit.register(shutil.rmtree, dst, ignore_errors=True)
+        build_ref.extract(dst)
+        _snapshot = True
+        return dst
     return "/root/reference"
 
 
@@ -35,7 +51,7 @@ def available() -> bool:
 
 
 def is_snapshot() -> bool:
-    return os.path.abspath(REF_ROOT) == os.path.join(_HERE, "_ref")
+    return _snapshot
 
 
 def _namespace(name, path):

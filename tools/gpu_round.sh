@@ -32,7 +32,7 @@ for what in "$@"; do
       done ;;
     ncu_hbm)
       timeout 300 python tools/hbm_bench.py 2097152 --once > gpurun_out/hbm_plain.log 2>&1 &&
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:'rot6d_kernel|aa_kornia_kernel|rodrigues_kernel|rotmat_to_aa_kernel|fk_' \
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:'rot6d|aa_kornia|rodrigues|rotmat_to_aa|fk_' \
           -c 16 -f -o gpurun_out/prof_hbm python tools/hbm_bench.py 2097152 --once > gpurun_out/ncu_hbm.log 2>&1
       echo "ncu_hbm exit $?" | tee -a gpurun_out/summary.txt ;;
     ncu_net)
