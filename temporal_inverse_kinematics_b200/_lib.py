@@ -133,4 +133,18 @@ def on_device(t):
     calls: kernels, function attributes, cudaGetDevice and the plan's setup copies all act on the *current* device,
     which need not be the one the caller's tensors live on (a model on cuda:1 while cuda:0 is current)."""
     import torch
-    return torch.cuda.device(t.device if torch.is_tensor(t) else t)
+    dev = t.device if torch.is_tensor(t) else t
+    if dev.index is None or dev.index == torch.cuda.current_device():
+        return _NULL_CTX                       # already current: entering torch.cuda.device costs ~10 us per call
+    return torch.cuda.device(dev)
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL_CTX = _NullCtx()

@@ -12,6 +12,7 @@ BN folded as s = gamma / sqrt(var + eps), o = beta - mean * s:
 There is no CPU or eager-PyTorch fallback: anything but eval-mode CUDA tensors raises.
 """
 import ctypes as C
+import operator
 import os
 import weakref
 
@@ -20,6 +21,8 @@ import torch
 from . import _lib as L
 
 BN_EPS_DEFAULT = 1e-5
+_GET_VERSION, _GET_EPS, _GET_PTR = operator.attrgetter("_version"), operator.attrgetter("eps"), torch.Tensor.data_ptr
+_CHECKED_DEVICES = set()
 _DTYPES = {"fp32": (L.TIK_F32, torch.float32), "bf16": (L.TIK_BF16, torch.bfloat16)}
 
 
@@ -358,8 +361,8 @@ class Engine:
 
     def _stamp_now(self, backbone, head, fresh=False):
         ts, bns = self._collect(backbone, head) if (fresh or self._watch is None) else self._watch
-        stamp = (tuple([t._version for t in ts]), tuple([t.data_ptr() for t in ts]), ts[0].device,
-                 tuple([m.eps for m in bns]), None if head is None else float(head[1]))
+        stamp = (tuple(map(_GET_VERSION, ts)), tuple(map(_GET_PTR, ts)), ts[0].device,
+                 tuple(map(_GET_EPS, bns)), None if head is None else float(head[1]))
         if self.weight_check == "content":
             # <= 64 strided samples + the sum of each tensor, reduced on the device, one read-back
             with torch.no_grad():
@@ -462,5 +465,7 @@ def require_cuda_eval(module, x, what):
         raise TypeError(f"{what}: expected a torch.Tensor, got {type(x)}")
     if not x.is_cuda:
         raise RuntimeError(f"{what}: input must be a CUDA tensor -- there is no CPU fallback")
-    with L.on_device(x):
-        L.check(L.lib().tik_check_device())
+    if x.device.index not in _CHECKED_DEVICES:               # compute capability 10.x, checked once per device
+        with L.on_device(x):
+            L.check(L.lib().tik_check_device())
+        _CHECKED_DEVICES.add(x.device.index)
