@@ -47,3 +47,32 @@ def moveai_to_coco(joints_3d, joint_names):
     seq[:, :, 1] = seq[:, :, 2]
     seq[:, :, 2] = -y
     return seq
+
+
+def moveai_to_coco_device(joints_3d, joint_names):
+    """`moveai_to_coco` for a sequence that already lives on the GPU (optional part): the same
+    gather / nose = mean of the ears / eyes = ears / axis swap as inference.py:121-133, as ONE gather-and-blend on the
+    tensor's device (two index vectors and two weights per COCO keypoint), bit-identical to the numpy version.
+    joints_3d: torch tensor (F, J, 3) -> (F, 17, 3) float32 on the same device."""
+    import torch
+    j = joints_3d.to(torch.float32)
+    J = j.shape[1]
+    maps = generate_moveai3d_to_coco_mappings(list(joint_names))
+    ia, ib, wa, wb = [], [], [], []
+    for tgt, idx in enumerate(maps):
+        if tgt == 0:        # nose = 0.5 * (joint[-1] + joint[-2])
+            ia.append(J - 1); ib.append(J - 2); wa.append(0.5); wb.append(0.5)
+        elif tgt == 1:      # left eye = joint[-2]
+            ia.append(J - 2); ib.append(J - 2); wa.append(1.0); wb.append(0.0)
+        elif tgt == 2:      # right eye = joint[-1]
+            ia.append(J - 1); ib.append(J - 1); wa.append(1.0); wb.append(0.0)
+        elif idx >= 0:
+            ia.append(idx); ib.append(idx); wa.append(1.0); wb.append(0.0)
+        else:
+            ia.append(0); ib.append(0); wa.append(0.0); wb.append(0.0)
+    dev = j.device
+    ia, ib = torch.tensor(ia, device=dev), torch.tensor(ib, device=dev)
+    wa = torch.tensor(wa, dtype=torch.float32, device=dev)[None, :, None]
+    wb = torch.tensor(wb, dtype=torch.float32, device=dev)[None, :, None]
+    seq = wa * j[:, ia] + wb * j[:, ib]
+    return torch.stack([seq[:, :, 0], seq[:, :, 2], -seq[:, :, 1]], dim=2).contiguous()      # y <- z, z <- -y

@@ -156,3 +156,15 @@ def test_fk_port_agrees_with_independent_scipy_chain(skeleton):
     assert np.abs(j1[0] - (rest + transl[0])).max() < 1e-12
     Rq = gp.batch_rodrigues(aa.reshape(-1, 3)).reshape(-1, 3, 3)
     assert np.abs(fk_scipy.rodrigues_skew(aa.reshape(-1, 3)) - Rq).max() < 1e-6
+
+
+def test_device_side_moveai_remap_is_bit_identical(golden):
+    """inference.py:121-133 as one gather-and-blend on the tensor's device (here: CPU tensors) vs the numpy mirror and
+    the reference's own output stored in the golden."""
+    from temporal_inverse_kinematics_b200 import keypoints_util as ku
+    g = golden("dance.npz")
+    names = [str(s) for s in g["joint_3d_names"]]
+    want = ku.moveai_to_coco(g["joints_3d"], names)
+    got = ku.moveai_to_coco_device(torch.from_numpy(g["joints_3d"]), names)
+    assert got.dtype == torch.float32 and got.is_contiguous()
+    assert np.array_equal(got.numpy(), want) and np.array_equal(want, g["coco_seq"])

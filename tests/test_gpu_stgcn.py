@@ -307,3 +307,39 @@ def test_session_is_the_same_forward():
         want = m(x)["poses"]
         run = m.session(1, 64)
         assert torch.equal(run(x), want) and torch.equal(run(x), want)
+
+
+def test_rotation_aware_window_mean():
+    """SURVEY 8f row 2 option: rotations are averaged as rotations.  Two predictions of (almost) the same half-turn
+    written as +(pi - e) and -(pi - e) about one axis average to ~zero rotation in the reference's euclidean mean and to
+    the half-turn in rotation mode; for tightly clustered predictions both modes agree."""
+    from oracle import geometry_port as gp
+    from temporal_inverse_kinematics_b200.inference import window_mean
+    F, hw = 9, 1
+    rs = np.random.RandomState(3)
+    base = rs.standard_normal((F, 22, 3)).astype(np.float32) * 0.4
+    preds = np.repeat(base[:, None], 2 * hw + 1, axis=1) + rs.standard_normal((F, 3, 22, 3)).astype(np.float32) * 1e-3
+    # frame f receives window i = f - o at slot o + hw; make every contribution to a frame a small perturbation of base[f]
+    p = np.zeros_like(preds)
+    for i in range(F):
+        for o in range(-hw, hw + 1):
+            if 0 <= i + o < F:
+                p[i, o + hw] = base[i + o] + rs.standard_normal((22, 3)).astype(np.float32) * 1e-3
+    t = torch.from_numpy(p.reshape(F, 3, 66)).cuda()
+    e = window_mean(t, hw).cpu().numpy()
+    r = window_mean(t, hw, mode="rotation").cpu().numpy()
+    assert np.abs(e - r).max() < 5e-3 and np.abs(r.reshape(F, 22, 3) - base).max() < 5e-3
+    # half-turn about z seen from both sides
+    q = np.zeros((F, 3, 22, 3), dtype=np.float32)
+    q[:, 0, :, 2] = np.pi - 0.05
+    q[:, 1, :, 2] = -(np.pi - 0.05)
+    q[:, 2, :, 2] = np.pi - 0.05
+    t = torch.from_numpy(q.reshape(F, 3, 66)).cuda()
+    e = window_mean(t, hw).cpu().numpy().reshape(F, 22, 3)
+    r = window_mean(t, hw, mode="rotation").cpu().numpy().reshape(F, 22, 3)
+    Rr = gp.batch_rodrigues(r[2:-2].reshape(-1, 3)).reshape(-1, 3, 3)
+    half_turn = np.diag([-1.0, -1.0, 1.0])
+    assert np.abs(Rr - half_turn).max() < 0.12            # within the 0.05 rad spread of the inputs
+    assert np.abs(e[2:-2, :, 2]).max() < 1.2              # the euclidean mean collapses towards zero rotation
+    with pytest.raises(ValueError):
+        window_mean(t, hw, mode="geodesic")
