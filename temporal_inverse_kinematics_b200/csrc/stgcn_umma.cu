@@ -1026,6 +1026,10 @@ int umma_prepare(const TikRowGemm* d, int64_t nv_capacity, UmmaPrepared** out) {
     if (rc != TIK_OK) { delete u; return rc; }
   }
   u->bn = d->c_out % 256 == 0 ? 256 : (d->c_out % 128 == 0 ? 128 : 64);
+  if (const char* e = getenv("TIK_UMMA_BN")) {          // tuning hook: narrower N tiles for the 256-column layers
+    const int want = atoi(e);
+    if ((want == 128 || want == 64) && want < u->bn && d->c_out % want == 0) u->bn = want;
+  }
   p.n_tiles_n = d->c_out / u->bn;
   {
     uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d->c_out};
