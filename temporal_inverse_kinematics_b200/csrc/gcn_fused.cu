@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
   constexpr int TMEM_NEED = 64 + ND1 * CIN + ND2 * COUT;
   constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; pointer arithmetic on the shared base keeps the address space (LDS / STS, not generic LD / ST)
   uint8_t* s_w = smem + p.off_w;                      // KC1 slabs of COUT rows x 128 B
   uint8_t* s_x = smem + p.off_x;                      // xbufs x KC1 slabs
   uint8_t* s_stage = smem + p.off_stage;              // KC2 slabs
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_pair_kernel(const __g
   constexpr int TMEM_NEED = 64 + ND1 * 128 + ND2 * 2 * COUT;
   constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; pointer arithmetic on the shared base keeps the address space (LDS / STS, not generic LD / ST)
   uint8_t* s_w = smem + p.off_w;                      // COUT rows x 128 B
   uint8_t* s_x = smem + p.off_x;                      // xbufs stages x 2 slabs (tile A, tile B)
   uint8_t* s_stage = smem + p.off_stage;              // 2 staging tiles (A, B) of KC2 slabs

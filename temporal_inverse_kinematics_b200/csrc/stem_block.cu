@@ -85,7 +85,7 @@ template <int CIN>
 __global__ void __launch_bounds__(kSbThreads, 1) stem_block_kernel(const __grid_constant__ StemBlockParams p) {
   static_assert(4 * CIN <= 16, "hi/lo slices of the aggregated and the scaled input must fit one K=16 step");
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; pointer arithmetic on the shared base keeps the address space (LDS / STS, not generic LD / ST)
   uint8_t* s_w16 = smem + kSbOffW16;
   uint8_t* s_wt = smem + kSbOffWt;
   uint8_t* s_a0 = smem + kSbOffA0;

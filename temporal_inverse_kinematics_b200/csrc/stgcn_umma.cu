@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
   constexpr int kBBytes = BN * kChunkK * 2;
   if (threadIdx.x == 0) TIK_T(0);
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; pointer arithmetic on the shared base keeps the address space (LDS / STS, not generic LD / ST)
   uint8_t* w_res = smem;                                    // resident weights: total_chunks x (BN x 64) tiles
   uint8_t* ring = smem + p.off_ring;
   float* s_bias = reinterpret_cast<float*>(smem + p.off_bias);
@@ -418,7 +418,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1) row
   constexpr int BN = 256;
   constexpr int kBHalf = (BN / 2) * kChunkK * 2;            // this CTA's half of a W chunk: 16 KB
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; pointer arithmetic on the shared base keeps the address space (LDS / STS, not generic LD / ST)
   uint8_t* ring = smem + p.off_ring;
   float* s_bias = reinterpret_cast<float*>(smem + p.off_bias);
   uint8_t* s_stage = smem + p.off_stage;
@@ -675,7 +675,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1) row
 template <int ACT>
 __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_ts_kernel(const __grid_constant__ UmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; pointer arithmetic on the shared base keeps the address space (LDS / STS, not generic LD / ST)
   uint8_t* ring = smem + p.off_ring;
   uint8_t* s_stage = smem + p.off_stage;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);

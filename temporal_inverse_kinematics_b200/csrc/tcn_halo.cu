@@ -54,7 +54,7 @@ struct TcnHaloParams {
 
 __global__ void __launch_bounds__(kThThreads, 1) tcn_halo_kernel(const __grid_constant__ TcnHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; pointer arithmetic on the shared base keeps the address space (LDS / STS, not generic LD / ST)
   uint8_t* ring = smem;
   uint8_t* s_stage = smem + p.off_stage;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
