@@ -29,6 +29,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
+#include <vector>
 
 #include "tik_common.cuh"
 #include "umma_prepared.h"
@@ -1208,13 +1210,60 @@ int umma_launch(UmmaPrepared* u, const TikRowGemm* d, cudaStream_t s) {
 
 void umma_free(UmmaPrepared* u) { delete u; }
 
+// One-shot calls (tik_rowgemm: the per-module forwards and the iterative head's per-iteration layers) used to encode
+// their tensor maps and pick their shared-memory policy on EVERY call (~100-200 us of host work, more than the kernel
+// at small sizes).  Prepared launches are now kept in a small LRU keyed by the full descriptor (every pointer, shape
+// and flag) and the device: a call with the same tensors at the same addresses -- what a loop over PyTorch's caching
+// allocator produces -- re-uses its tensor maps.
 int rowgemm_bf16(const TikRowGemm* d, cudaStream_t s) {
+  struct Entry { TikRowGemm key; int dev; UmmaPrepared* u; uint64_t used; };
+  static std::mutex mu;
+  static std::vector<Entry> cache;
+  static uint64_t tick = 0;
+  constexpr size_t kCap = 32;
+  // tuning / A-B switches are read at prepare time: with any of them set (tools, the variant tests) nothing is cached
+  if (getenv("TIK_UMMA_GROUP") || getenv("TIK_UMMA_OPT") || getenv("TIK_UMMA_BN") || getenv("TIK_NO_TS") || getenv("TIK_2CTA") ||
+      getenv("TIK_NO_ROWGEMM_CACHE")) {
+    UmmaPrepared* u = nullptr;
+    int rc = umma_prepare(d, d->nv, &u);
+    if (rc != TIK_OK) return rc;
+    rc = umma_launch(u, d, s);
+    umma_free(u);
+    return rc;
+  }
+  int dev = 0;
+  TIK_CUDA(cudaGetDevice(&dev));
+  const TikRowGemm key = *d;                                // compared field-wise below (padding bytes are unspecified)
+  std::lock_guard<std::mutex> lock(mu);
+  auto same = [](const TikRowGemm& a, const TikRowGemm& b) {
+    if (a.n_slabs != b.n_slabs || a.w_dev != b.w_dev || a.bias_dev != b.bias_dev || a.bias_per_node != b.bias_per_node || a.nv != b.nv ||
+        a.v != b.v || a.t_out != b.t_out || a.c_out != b.c_out || a.c_out_valid != b.c_out_valid || a.act != b.act || a.slope != b.slope ||
+        a.res_kind != b.res_kind || a.res_dev != b.res_dev || a.res_w_dev != b.res_w_dev || a.res_cin != b.res_cin ||
+        a.res_t_mul != b.res_t_mul || a.res_t_in != b.res_t_in || a.out_dev != b.out_dev || a.out_layout != b.out_layout)
+      return false;
+    for (int i = 0; i < a.n_slabs; ++i)
+      if (a.slabs[i].a_dev != b.slabs[i].a_dev || a.slabs[i].c != b.slabs[i].c || a.slabs[i].t_in != b.slabs[i].t_in ||
+          a.slabs[i].t_mul != b.slabs[i].t_mul || a.slabs[i].t_off != b.slabs[i].t_off)
+        return false;
+    return true;
+  };
+  for (auto& e : cache)
+    if (e.dev == dev && same(e.key, key)) {
+      e.used = ++tick;
+      return umma_launch(e.u, d, s);
+    }
   UmmaPrepared* u = nullptr;
   int rc = umma_prepare(d, d->nv, &u);
   if (rc != TIK_OK) return rc;
-  rc = umma_launch(u, d, s);
-  umma_free(u);
-  return rc;
+  if (cache.size() >= kCap) {
+    size_t lru = 0;
+    for (size_t i = 1; i < cache.size(); ++i)
+      if (cache[i].used < cache[lru].used) lru = i;
+    umma_free(cache[lru].u);
+    cache.erase(cache.begin() + (long)lru);
+  }
+  cache.push_back({key, dev, u, ++tick});
+  return umma_launch(u, d, s);
 }
 
 }  // namespace tik
