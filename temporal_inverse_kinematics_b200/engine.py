@@ -426,7 +426,7 @@ class EngineHolder:
     cache, not state -- it is dropped by pickling / ``torch.save(model)`` / ``copy.deepcopy`` and rebuilt lazily, as
     the reference's plain nn.Modules would allow."""
 
-    _CACHE_ATTRS = ("_engine", "_packed")
+    _CACHE_ATTRS = ("_engine", "_packed", "_head_state")
 
     def __getstate__(self):
         state = self.__dict__.copy()
@@ -454,6 +454,8 @@ class EngineHolder:
                     m._engine.invalidate()
                 if "_packed" in m.__dict__:
                     m._packed = None
+                if "_head_state" in m.__dict__:
+                    m._head_state = None
         return self
 
 

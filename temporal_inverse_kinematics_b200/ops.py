@@ -88,13 +88,15 @@ def gcn_fused(x, abd, w, bias, relu=True):
 
 
 def rowgemm(slabs, w, bias, nv, v, t_out, act="none", slope=0.01, residual=None, out_layout="node", c_out_valid=None,
-            stem_residual=None):
+            stem_residual=None, out=None):
     """Generic implicit GEMM (TikRowGemm).
 
     slabs: list of (tensor (NV, t_in, c) node-major, t_mul, t_off); w (c_out, sum c); bias (1|V, c_out) fp32.
     residual: tensor (NV, t_out, c_out) of the activation dtype (identity residual).
     stem_residual: (x (N,T,V,cin) fp32, res_w (V,c_out,cin) fp32, t_mul).
     out_layout: 'node' (NV,t_out,c_out) | 'time' (N,t_out,V,c_out) | 'rows_f32' (NV*t_out, c_out_valid) fp32.
+    out: optional preallocated result of that shape / dtype (stable addresses let libtik re-use the prepared launch
+    and make the call CUDA-graph capturable without allocator traffic).
     """
     a0 = slabs[0][0]
     _dev(w, bias, residual, *[s[0] for s in slabs])
@@ -129,16 +131,17 @@ def rowgemm(slabs, w, bias, nv, v, t_out, act="none", slope=0.01, residual=None,
     else:
         g.res_kind = L.RES_NONE
     if out_layout == "node":
-        out = torch.empty((nv, t_out, c_out), dtype=a0.dtype, device=a0.device)
-        g.out_layout = L.OUT_NODE_MAJOR
+        shape, odt, g.out_layout = (nv, t_out, c_out), a0.dtype, L.OUT_NODE_MAJOR
     elif out_layout == "time":
-        out = torch.empty((nv // v, t_out, v, c_out), dtype=a0.dtype, device=a0.device)
-        g.out_layout = L.OUT_TIME_MAJOR
+        shape, odt, g.out_layout = (nv // v, t_out, v, c_out), a0.dtype, L.OUT_TIME_MAJOR
     elif out_layout == "rows_f32":
-        out = torch.empty((nv * t_out, c_valid), dtype=torch.float32, device=a0.device)
-        g.out_layout = L.OUT_ROWS_F32
+        shape, odt, g.out_layout = (nv * t_out, c_valid), torch.float32, L.OUT_ROWS_F32
     else:
         raise ValueError(out_layout)
+    if out is None:
+        out = torch.empty(shape, dtype=odt, device=a0.device)
+    elif tuple(out.shape) != shape or out.dtype != odt or not out.is_contiguous() or out.device != a0.device:
+        raise ValueError(f"out must be a contiguous {odt} tensor of shape {shape} on {a0.device}")
     g.out_dev = out.data_ptr()
     with L.on_device(a0):
         L.check(L.lib().tik_rowgemm(code, C.byref(g), L.stream_ptr(a0.device)))

@@ -151,8 +151,10 @@ class IterativePoseRegressor(engine.EngineHolder, nn.Module, _ComputeDtypeMixin)
         self.compute_dtype = _default_dtype()
         self.chunk_clips = None
         self.weight_check = None
+        self.use_cuda_graph = True          # the iterative head's launches are replayed as one CUDA graph
         self._engine = None
         self._packed = None
+        self._head_state = None
 
     def _head_weights(self):
         """fc1 / fc2 / decpose in the compute dtype, padded as the GEMM kernels want them; cached per parameter version."""
@@ -187,19 +189,58 @@ class IterativePoseRegressor(engine.EngineHolder, nn.Module, _ComputeDtypeMixin)
         plan = self._engine.plan(self.compute_dtype, N, T, self.chunk_clips)
         _, feat = plan.run(x, want_feat=True)                               # (N, T', 17*256) in the compute dtype
         M = N * Tp
-        feat = feat.view(1, M, -1)
-        w1, b1, w2, b2, w3, b3 = self._head_weights()
-        pred = (self.init_pose if init_pose is None else init_pose.to(x.device).float().reshape(-1, self.NPOSE)).expand(M, -1)
-        pose_slab = torch.zeros((1, M, self.NPAD), dtype=feat.dtype, device=x.device)
-        for _ in range(int(n_iter)):
-            pose_slab[0, :, : self.NPOSE] = pred
-            h = ops.rowgemm([(feat, 1, 0), (pose_slab, 1, 0)], w1, b1, 1, 1, M)
-            h = ops.rowgemm([(h, 1, 0)], w2, b2, 1, 1, M)
-            d = ops.rowgemm([(h, 1, 0)], w3, b3, 1, 1, M, out_layout="rows_f32", c_out_valid=self.NPOSE)
-            pred = d + pred
+        init = (self.init_pose if init_pose is None else init_pose.to(x.device).float().reshape(-1, self.NPOSE)).expand(M, -1)
+        pred = self._run_head(feat.view(1, M, -1), init, int(n_iter))
         rotmats = geometry.rot6d_to_rotmat(pred.reshape(-1, 6)).view(M, 22, 3, 3)
         poses = geometry.rotation_matrix_to_angle_axis(rotmats.reshape(-1, 3, 3)).reshape(N, Tp, 66)
         return {"poses": poses, "rotmats": rotmats}
+
+    def _run_head(self, feat, init, n_iter):
+        """pred = init; n_iter x { pred += decpose(fc2(fc1(cat[features, pred]))) } on preallocated buffers: the nine
+        `tik_rowgemm` launches and the small element-wise updates of one forward are captured ONCE per (rows, n_iter,
+        weights) as a CUDA graph and replayed (stable addresses: libtik re-uses its prepared launches; no allocator
+        traffic; one host call instead of ~20)."""
+        from . import ops
+        M = feat.shape[1]
+        w1, b1, w2, b2, w3, b3 = self._head_weights()
+        key = (M, n_iter, feat.dtype, feat.device, torch.cuda.current_stream(feat.device).cuda_stream, id(w1))
+        st = self._head_state
+        if st is None or st["key"] != key:
+            dev, dt = feat.device, feat.dtype
+            st = {"key": key, "feat": torch.empty_like(feat), "init": torch.empty((M, self.NPOSE), device=dev),
+                  "pred": torch.empty((M, self.NPOSE), device=dev), "slab": torch.zeros((1, M, self.NPAD), dtype=dt, device=dev),
+                  "h1": torch.empty((1, M, w1.shape[0]), dtype=dt, device=dev), "h2": torch.empty((1, M, w2.shape[0]), dtype=dt, device=dev),
+                  "d": torch.empty((M, self.NPOSE), device=dev), "graph": None, "weights": (w1, b1, w2, b2, w3, b3)}
+
+            def body():
+                st["pred"].copy_(st["init"])
+                for _ in range(n_iter):
+                    st["slab"][0, :, : self.NPOSE] = st["pred"]
+                    ops.rowgemm([(st["feat"], 1, 0), (st["slab"], 1, 0)], w1, b1, 1, 1, M, out=st["h1"])
+                    ops.rowgemm([(st["h1"], 1, 0)], w2, b2, 1, 1, M, out=st["h2"])
+                    ops.rowgemm([(st["h2"], 1, 0)], w3, b3, 1, 1, M, out_layout="rows_f32", c_out_valid=self.NPOSE, out=st["d"])
+                    st["pred"].add_(st["d"])
+
+            st["feat"].copy_(feat)
+            st["init"].copy_(init)
+            body()                                                # eager warm-up (lazy init, prepared launches)
+            if self.use_cuda_graph:
+                torch.cuda.current_stream(feat.device).synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    body()
+                st["graph"] = graph
+            st["body"] = body
+            self._head_state = st
+            if not self.use_cuda_graph:
+                return st["pred"].clone()
+        st["feat"].copy_(feat)
+        st["init"].copy_(init)
+        if st["graph"] is not None:
+            st["graph"].replay()
+        else:
+            st["body"]()
+        return st["pred"].clone()
 
 
 class IKPoseTrainer(engine.EngineHolder, nn.Module, _ComputeDtypeMixin):
