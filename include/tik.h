@@ -58,6 +58,13 @@ int tik_batch_rodrigues(const float* aa_dev, float* R9_dev, int64_t M, void* str
  * kornia_quirk != 0 reproduces common/kornia_geometry_conversion.py:204-227 instead. */
 int tik_rotmat_to_aa(const float* R_dev, float* aa_dev, int64_t M, int kornia_quirk, void* stream);
 
+/* The quaternion helpers the two conversions above are made of, as the reference exposes them (all (w,x,y,z)):
+ * common/geometry.py:37-65 quat2mat (normalises, q (M,4) -> R (M,3,3)); :153-233 rotation_matrix_to_quaternion
+ * (R (M,3,3) -> q (M,4), four-case selection on the transposed matrix); :100-150 quaternion_to_angle_axis (q -> aa). */
+int tik_quat_to_rotmat(const float* q_dev, float* R_dev, int64_t M, void* stream);
+int tik_rotmat_to_quat(const float* R_dev, float* q_dev, int64_t M, void* stream);
+int tik_quat_to_aa(const float* q_dev, float* aa_dev, int64_t M, void* stream);
+
 /* ------------------------------------------------------------------ body forward kinematics
  * Replaces the joint output of common/smpl_util.py:22-82 run_smpl_inference -> smplx forward
  * (third-party; restated from the published SMPL chain, see oracle/fk_port.py).

@@ -64,6 +64,9 @@ _PROTOS = {
     "tik_aa_to_rotmat": (C.c_int, [vp, vp, i64, vp]),
     "tik_batch_rodrigues": (C.c_int, [vp, vp, i64, vp]),
     "tik_rotmat_to_aa": (C.c_int, [vp, vp, i64, C.c_int, vp]),
+    "tik_quat_to_rotmat": (C.c_int, [vp, vp, i64, vp]),
+    "tik_rotmat_to_quat": (C.c_int, [vp, vp, i64, vp]),
+    "tik_quat_to_aa": (C.c_int, [vp, vp, i64, vp]),
     "tik_fk_body": (C.c_int, [vp, C.c_int, C.POINTER(f32), C.POINTER(i32), C.c_int, vp, vp, vp, vp, i64, vp]),
     "tik_stem_gcn": (C.c_int, [C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, i64, C.c_int, C.c_int, C.c_int,
                                C.c_int, C.c_int, C.c_int, vp]),

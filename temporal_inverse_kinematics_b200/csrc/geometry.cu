@@ -221,11 +221,33 @@ __device__ __forceinline__ void quat_to_aa(float q0, float q1, float q2, float q
   aa[0] = q1 * k; aa[1] = q2 * k; aa[2] = q3 * k;
 }
 
+// common/geometry.py:37-65 quat2mat: (w,x,y,z), normalised first
+__device__ __forceinline__ void quat2mat_one(const float* q, float* R) {
+  float w = q[0], x = q[1], y = q[2], z = q[3];
+  const float iq = rsqrtf(w * w + x * x + y * y + z * z);
+  w *= iq; x *= iq; y *= iq; z *= iq;
+  const float w2 = w * w, x2 = x * x, y2 = y * y, z2 = z * z;
+  const float wx = w * x, wy = w * y, wz = w * z, xy = x * y, xz = x * z, yz = y * z;
+  R[0] = w2 + x2 - y2 - z2; R[1] = 2.f * xy - 2.f * wz;   R[2] = 2.f * wy + 2.f * xz;
+  R[3] = 2.f * wz + 2.f * xy; R[4] = w2 - x2 + y2 - z2;   R[5] = 2.f * yz - 2.f * wx;
+  R[6] = 2.f * xz - 2.f * wy; R[7] = 2.f * wx + 2.f * yz; R[8] = w2 - x2 - y2 + z2;
+}
+
 // common/geometry.py:68-97,153-233: four-case selection on the transposed matrix, NaN -> 0.
 // The ncu capture of round 2 (profiles/r2_hbm_kernels.md) showed the first version issue-bound (306 instructions per
 // rotation: four divergent cases, two atan2f, five precise divisions): the cases are now selects over shared sums, the
 // common factor 0.5 / sqrt(t) is one rsqrt (same inf / NaN behaviour as q / sqrt(t) * 0.5 for t <= 0).
+__device__ __forceinline__ void rotmat_to_quat_one(const float* R, float* q);
 __device__ __forceinline__ void rotmat_to_aa_one(const float* R, float* aa) {
+  float q[4];
+  rotmat_to_quat_one(R, q);
+  quat_to_aa(q[0], q[1], q[2], q[3], aa);
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (isnan(aa[k])) aa[k] = 0.f;
+}
+// common/geometry.py:153-233 rotation_matrix_to_quaternion -> (w,x,y,z)
+__device__ __forceinline__ void rotmat_to_quat_one(const float* R, float* q) {
   // m = R^T
   const float m00 = R[0], m01 = R[3], m02 = R[6];
   const float m10 = R[1], m11 = R[4], m12 = R[7];
@@ -240,11 +262,7 @@ __device__ __forceinline__ void rotmat_to_aa_one(const float* R, float* aa) {
   float q2 = c0 ? s01 : c1 ? t : c2 ? s12 : a20;
   float q3 = c0 ? s20 : c1 ? s12 : c2 ? t : a01;
   const float h = 0.5f * rsqrtf(t);
-  q0 *= h; q1 *= h; q2 *= h; q3 *= h;
-  quat_to_aa(q0, q1, q2, q3, aa);
-#pragma unroll
-  for (int k = 0; k < 3; ++k)
-    if (isnan(aa[k])) aa[k] = 0.f;
+  q[0] = q0 * h; q[1] = q1 * h; q[2] = q2 * h; q[3] = q3 * h;
 }
 
 // common/kornia_geometry_conversion.py:204-307,396-439: (x,y,z,w) quaternion read as (w,x,y,z).
@@ -299,6 +317,29 @@ __global__ void __launch_bounds__(kConvThreads + 32) rotmat_to_aa_bulk_kernel(co
     bulk_map<9, 3>(in, out, n_tiles, [](const float* a, float* r) { rotmat_to_aa_kornia_quirk_one(a, r); });
   else
     bulk_map<9, 3>(in, out, n_tiles, [](const float* a, float* r) { rotmat_to_aa_one(a, r); });
+}
+
+__global__ void __launch_bounds__(kConvThreads) quat2mat_kernel(const float* in, float* out, int64_t M) {
+  staged_map<4, 9>(in, out, M, [](const float* a, float* r) { quat2mat_one(a, r); });
+}
+__global__ void __launch_bounds__(kConvThreads) rotmat_to_quat_kernel(const float* in, float* out, int64_t M) {
+  staged_map<9, 4>(in, out, M, [](const float* a, float* r) { rotmat_to_quat_one(a, r); });
+}
+__global__ void __launch_bounds__(kConvThreads) quat_to_aa_kernel(const float* in, float* out, int64_t M) {
+  staged_map<4, 3>(in, out, M, [](const float* a, float* r) { quat_to_aa(a[0], a[1], a[2], a[3], r); });
+}
+
+template <class K>
+static int launch_staged(K kernel, const void* in, void* out, int64_t M, cudaStream_t s) {
+  TIK_CHECK_ARG(M >= 0, "negative count");
+  if (M == 0) return TIK_OK;
+  TIK_CHECK_ARG(in && out, "null pointer");
+  TIK_CHECK_ARG((((uintptr_t)in | (uintptr_t)out) & 15) == 0, "pointers must be 16-byte aligned");
+  const int64_t blocks = ceil_div(M, kConvThreads);
+  TIK_CHECK_ARG(blocks < (1ll << 31), "too many rotations for one launch");
+  kernel<<<(unsigned)blocks, kConvThreads, 0, s>>>((const float*)in, (float*)out, M);
+  TIK_LAUNCH_CHECK();
+  return TIK_OK;
 }
 
 static bool conv_bulk_enabled() {
@@ -365,6 +406,15 @@ int tik_aa_to_rotmat(const float* aa, float* R, int64_t M, void* stream) {
 }
 int tik_batch_rodrigues(const float* aa, float* R9, int64_t M, void* stream) {
   return tik::launch_conv<3, 9>(tik::rodrigues_bulk_kernel, tik::rodrigues_kernel, aa, R9, M, (cudaStream_t)stream);
+}
+int tik_quat_to_rotmat(const float* q, float* R, int64_t M, void* stream) {
+  return tik::launch_staged(tik::quat2mat_kernel, q, R, M, (cudaStream_t)stream);
+}
+int tik_rotmat_to_quat(const float* R, float* q, int64_t M, void* stream) {
+  return tik::launch_staged(tik::rotmat_to_quat_kernel, R, q, M, (cudaStream_t)stream);
+}
+int tik_quat_to_aa(const float* q, float* aa, int64_t M, void* stream) {
+  return tik::launch_staged(tik::quat_to_aa_kernel, q, aa, M, (cudaStream_t)stream);
 }
 int tik_rotmat_to_aa(const float* R, float* aa, int64_t M, int kornia_quirk, void* stream) {
   return tik::launch_conv<9, 3>(tik::rotmat_to_aa_bulk_kernel, tik::rotmat_to_aa_kernel, R, aa, M, (cudaStream_t)stream, kornia_quirk);

@@ -46,3 +46,23 @@ def rotation_matrix_to_angle_axis(rotation_matrix):
     if torch.is_tensor(rotation_matrix) and rotation_matrix.dim() == 3 and rotation_matrix.shape[1:] == (3, 4):
         rotation_matrix = rotation_matrix[:, :, :3]
     return _run(L.lib().tik_rotmat_to_aa, _prep(rotation_matrix, 9, "rotation_matrix_to_angle_axis"), (3,), 0)
+
+
+def quat2mat(quat):
+    """(M, 4) quaternions (w,x,y,z), normalised first -> (M, 3, 3) (reference common/geometry.py:37-65)."""
+    return _run(L.lib().tik_quat_to_rotmat, _prep(quat, 4, "quat2mat"), (3, 3))
+
+
+def rotation_matrix_to_quaternion(rotation_matrix, eps=1e-6):
+    """(M, 3, 3) [or the reference's (M, 3, 4), last column ignored] -> (M, 4) quaternions (w,x,y,z)
+    (reference common/geometry.py:153-233; ``eps`` is the reference's 1e-6 threshold on R[2,2], fixed in the kernel)."""
+    if eps != 1e-6:
+        raise NotImplementedError("rotation_matrix_to_quaternion: only the reference's default eps=1e-6 is built")
+    if torch.is_tensor(rotation_matrix) and rotation_matrix.dim() == 3 and rotation_matrix.shape[1:] == (3, 4):
+        rotation_matrix = rotation_matrix[:, :, :3]
+    return _run(L.lib().tik_rotmat_to_quat, _prep(rotation_matrix, 9, "rotation_matrix_to_quaternion"), (4,))
+
+
+def quaternion_to_angle_axis(quaternion):
+    """(M, 4) quaternions (w,x,y,z) -> (M, 3) axis-angle (reference common/geometry.py:100-150)."""
+    return _run(L.lib().tik_quat_to_aa, _prep(quaternion, 4, "quaternion_to_angle_axis"), (3,))

@@ -164,3 +164,27 @@ def test_bulk_kernels_write_only_their_outputs():
             torch.cuda.synchronize()
             check(buf, F * J * 3, ("fk", J, F))
             assert torch.equal(out.view(F, J, 3), SU.fk_body(pose, rj, par))
+
+
+def test_quaternion_helpers_match_reference(golden):
+    """quat2mat / rotation_matrix_to_quaternion / quaternion_to_angle_axis (common/geometry.py:37-65,100-233): the
+    building blocks of batch_rodrigues and rotation_matrix_to_angle_axis, exposed as the reference exposes them."""
+    from temporal_inverse_kinematics_b200 import geometry as G
+    g = golden("geometry.npz")
+    R = g["R_in"]
+    q = G.rotation_matrix_to_quaternion(_cuda(R)).cpu().numpy()
+    np.testing.assert_allclose(q, g["R_to_quat_wxyz"], rtol=0, atol=1e-5)
+    aa = G.quaternion_to_angle_axis(_cuda(g["R_to_quat_wxyz"])).cpu().numpy()
+    want = gp.quaternion_to_angle_axis(g["R_to_quat_wxyz"])
+    ok = np.isfinite(want).all(axis=1)
+    np.testing.assert_allclose(aa[ok], want[ok], rtol=0, atol=2e-5)
+    # the composition is the R -> aa kernel (NaN rows become 0 there)
+    np.testing.assert_allclose(np.nan_to_num(aa[ok]), G.rotation_matrix_to_angle_axis(_cuda(R)).cpu().numpy()[ok], rtol=0, atol=2e-5)
+    # quat2mat: un-normalised quaternions, against the oracle's Rodrigues (which is quat2mat of (cos, sin * axis))
+    a = synth.make_axis_angles(500, 1, seed=9).reshape(-1, 3)
+    th = np.linalg.norm(a + 1e-8, axis=1, keepdims=True)
+    quat = np.concatenate([np.cos(th / 2), np.sin(th / 2) * a / th], axis=1).astype(np.float32) * 3.7
+    Rq = G.quat2mat(_cuda(quat)).cpu().numpy()
+    np.testing.assert_allclose(Rq.reshape(-1, 9), gp.batch_rodrigues(a), rtol=0, atol=1e-5)
+    q34 = np.concatenate([R, np.zeros((R.shape[0], 3, 1), dtype=np.float32)], axis=2)   # the reference's (N,3,4) input form
+    np.testing.assert_allclose(G.rotation_matrix_to_quaternion(_cuda(q34)).cpu().numpy(), q, rtol=0, atol=0)
