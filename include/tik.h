@@ -198,6 +198,57 @@ typedef struct TikNet {
   float leaky_slope;
 } TikNet;
 
+/* ------------------------------------------------------------------ weight folding (eval mode)
+ * The packing above computed ON THE DEVICE from the reference's raw parameters: BN1 / BN2 / residual-BN scale and shift,
+ * convolution biases and A * edge_importance folded into the packed weights (the algebra of
+ * st_gcn_aaai18.py:128-129,177-214 and gconv_origin.py:56-65 in eval mode).  All inputs fp32 device tensors exactly
+ * as the reference's state_dict holds them; arithmetic in fp64, rounded once to the output type (identical to the
+ * host-side packer engine.PackedNet).  Only enqueues kernels on `stream`. */
+typedef struct TikRawBN {     /* an eval-mode BatchNorm: y = (x - mean) / sqrt(var + eps) * weight + bias */
+  const float* weight_dev;    /* NULL: 1 */
+  const float* bias_dev;      /* NULL: 0 */
+  const float* mean_dev;      /* running_mean; NULL together with var_dev: no BatchNorm here (scale 1, shift 0) */
+  const float* var_dev;       /* running_var */
+  double eps;
+} TikRawBN;
+
+typedef struct TikRawBlock {  /* one st_gcn_block of the reference (st_gcn_aaai18.py:136-214) */
+  int32_t c_in, c_out, stride, kt;
+  int32_t K, V;
+  int32_t residual;             /* TIK_RES_NONE / TIK_RES_IDENTITY / TIK_RES_CONV (1x1 conv + BN) */
+  const float* A_dev;           /* (K,V,V) backbone buffer A */
+  const float* importance_dev;  /* (K,V,V) edge_importance[i], NULL: 1 */
+  const float* gcn_w_dev;       /* (K*c_out, c_in)   gcn.conv.weight (1x1) */
+  const float* gcn_b_dev;       /* (K*c_out) or NULL gcn.conv.bias */
+  TikRawBN bn1;                 /* tcn.0 */
+  const float* tcn_w_dev;       /* (c_out, c_out, kt) tcn.2.weight (kt x 1) */
+  const float* tcn_b_dev;       /* (c_out) or NULL */
+  TikRawBN bn2;                 /* tcn.3 */
+  const float* res_w_dev;       /* (c_out, c_in)      residual.0.weight, TIK_RES_CONV only */
+  const float* res_b_dev;       /* (c_out) or NULL */
+  TikRawBN bn_res;              /* residual.1 */
+} TikRawBlock;
+
+typedef struct TikPackBuffers { /* caller-allocated device outputs; sizes from tik_pack_block_bytes */
+  float* agg_dev;
+  void* w_gcn_dev;
+  float* b_gcn_dev;
+  void* w_tcn_dev;
+  float* b_tcn_dev;
+  float* w_res_stem_dev;        /* first block with a conv residual only, else NULL */
+} TikPackBuffers;
+
+/* scale / shift (n floats each) of one BatchNorm, e.g. data_bn -> TikNet.in_scale_dev / in_shift_dev (n = V*c_in). */
+int tik_pack_bn(const TikRawBN* bn, int64_t n, float* scale_dev, float* shift_dev, void* stream);
+/* bytes[6] = sizes of the TikPackBuffers members in declaration order (0 where the member is not produced).
+ * first_block != 0: the block that reads the raw input (w_gcn stays fp32, its conv residual is folded with data_bn
+ * into w_res_stem / a per-node b_tcn: TIK_RES_STEM). */
+int tik_pack_block_bytes(const TikRawBlock* raw, int dtype, int first_block, int64_t* bytes);
+/* Folds one block into `buf` and fills `out` (sizes, res_kind, res_as_slab and the pointers of `buf`).
+ * data_bn: the backbone's data_bn for the first block (NULL: none), ignored otherwise. */
+int tik_pack_block(const TikRawBlock* raw, int dtype, int first_block, const TikRawBN* data_bn,
+                   const TikPackBuffers* buf, TikBlock* out, void* stream);
+
 typedef struct TikPlan TikPlan;
 
 /* frames after the strided blocks: T -> floor((T-1)/s)+1 per block. */

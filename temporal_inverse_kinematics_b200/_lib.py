@@ -50,6 +50,22 @@ class TikBlock(C.Structure):
                 ("w_res_stem_dev", vp), ("res_as_slab", i32)]
 
 
+class TikRawBN(C.Structure):
+    _fields_ = [("weight_dev", vp), ("bias_dev", vp), ("mean_dev", vp), ("var_dev", vp), ("eps", C.c_double)]
+
+
+class TikRawBlock(C.Structure):
+    _fields_ = [("c_in", i32), ("c_out", i32), ("stride", i32), ("kt", i32), ("K", i32), ("V", i32), ("residual", i32),
+                ("A_dev", vp), ("importance_dev", vp), ("gcn_w_dev", vp), ("gcn_b_dev", vp), ("bn1", TikRawBN),
+                ("tcn_w_dev", vp), ("tcn_b_dev", vp), ("bn2", TikRawBN), ("res_w_dev", vp), ("res_b_dev", vp),
+                ("bn_res", TikRawBN)]
+
+
+class TikPackBuffers(C.Structure):
+    _fields_ = [("agg_dev", vp), ("w_gcn_dev", vp), ("b_gcn_dev", vp), ("w_tcn_dev", vp), ("b_tcn_dev", vp),
+                ("w_res_stem_dev", vp)]
+
+
 class TikNet(C.Structure):
     _fields_ = [("V", i32), ("K", i32), ("c_in", i32), ("n_blocks", i32), ("in_scale_dev", vp),
                 ("in_shift_dev", vp), ("blocks", TikBlock * MAX_BLOCKS), ("head_hidden", i32), ("head_out", i32),
@@ -73,6 +89,10 @@ _PROTOS = {
     "tik_aggregate": (C.c_int, [C.c_int, vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "tik_rowgemm": (C.c_int, [C.c_int, C.POINTER(TikRowGemm), vp]),
     "tik_gcn_fused": (C.c_int, [vp, vp, vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "tik_pack_bn": (C.c_int, [C.POINTER(TikRawBN), i64, vp, vp, vp]),
+    "tik_pack_block_bytes": (C.c_int, [C.POINTER(TikRawBlock), C.c_int, C.c_int, C.POINTER(i64)]),
+    "tik_pack_block": (C.c_int, [C.POINTER(TikRawBlock), C.c_int, C.c_int, C.POINTER(TikRawBN), C.POINTER(TikPackBuffers),
+                                 C.POINTER(TikBlock), vp]),
     "tik_stgcn_out_frames": (C.c_int, [C.POINTER(TikNet), C.c_int]),
     "tik_stgcn_workspace_bytes": (C.c_int, [C.POINTER(TikNet), C.c_int, i64, i64, C.c_int, C.POINTER(i64)]),
     "tik_stgcn_plan_create": (C.c_int, [C.POINTER(TikNet), C.c_int, i64, i64, C.c_int, vp, i64, C.POINTER(vp)]),

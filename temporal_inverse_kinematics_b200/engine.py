@@ -76,10 +76,47 @@ def fold_tcn(conv, bn, res_conv=None, res_bn=None):
     return w, b, wr
 
 
-class PackedNet:
-    """Device-resident packed weights + the TikNet descriptor that points at them."""
+def _raw_bn(bn):
+    """TikRawBN over a BatchNorm module's own tensors (None: no BatchNorm)."""
+    r = L.TikRawBN()
+    if bn is None:
+        return r
+    f = lambda t: None if t is None else t.detach().data_ptr()
+    r.weight_dev, r.bias_dev, r.mean_dev, r.var_dev, r.eps = f(bn.weight), f(bn.bias), f(bn.running_mean), f(bn.running_var), bn.eps
+    return r
 
-    def __init__(self, backbone, head, dtype_name):
+
+def raw_block(backbone, i):
+    """TikRawBlock over block i's raw fp32 parameters (pointers into the module's tensors; nothing is copied)."""
+    blk = backbone.st_gcn_networks[i]
+    A, imp = backbone.A.detach(), backbone.edge_importance[i]
+    f = lambda t: None if t is None else t.detach().data_ptr()
+    for t in (blk.gcn.conv.weight, blk.tcn[2].weight, A):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("tik_pack_block reads contiguous fp32 parameters")
+    r = L.TikRawBlock()
+    r.c_in, r.c_out, r.stride, r.kt = blk.in_channels, blk.out_channels, blk.stride, blk.temporal_kernel
+    r.K, r.V = A.shape[0], A.shape[1]
+    r.residual = {"none": L.RES_NONE, "identity": L.RES_IDENTITY, "conv": L.RES_CONV}[blk.residual_kind]
+    r.A_dev, r.importance_dev = f(A), (f(imp) if torch.is_tensor(imp) else None)
+    r.gcn_w_dev, r.gcn_b_dev, r.bn1 = f(blk.gcn.conv.weight), f(blk.gcn.conv.bias), _raw_bn(blk.tcn[0])
+    r.tcn_w_dev, r.tcn_b_dev, r.bn2 = f(blk.tcn[2].weight), f(blk.tcn[2].bias), _raw_bn(blk.tcn[3])
+    if blk.residual_kind == "conv":
+        r.res_w_dev, r.res_b_dev, r.bn_res = f(blk.residual[0].weight), f(blk.residual[0].bias), _raw_bn(blk.residual[1])
+    return r
+
+
+class PackedNet:
+    """Device-resident packed weights + the TikNet descriptor that points at them.
+
+    packer="host" folds with torch fp64 ops (fold_gcn / fold_tcn above); packer="device" calls the C ABI's
+    tik_pack_bn / tik_pack_block on the raw parameters instead (same algebra, same rounding points; the GPU tests hold
+    the two bit-identical).  Default: TIK_PACKER or "host"."""
+
+    def __init__(self, backbone, head, dtype_name, packer=None):
+        self.packer = packer or os.environ.get("TIK_PACKER", "host")
+        if self.packer not in ("host", "device"):
+            raise ValueError("packer must be 'host' or 'device'")
         self.dtype_name = dtype_name
         self.code, self.tdtype = resolve_dtype(dtype_name)
         dev = backbone.A.device
@@ -101,7 +138,14 @@ class PackedNet:
             o0 = torch.zeros(V * cin0, dtype=torch.float64, device=dev)
         net.in_scale_dev = self._f32(s0, "in_scale")
         net.in_shift_dev = self._f32(o0, "in_shift")
+        if self.packer == "device" and isinstance(backbone.data_bn, torch.nn.BatchNorm1d):
+            with L.on_device(dev):                                        # overwrite with the library's own fold
+                L.check(L.lib().tik_pack_bn(C.byref(_raw_bn(backbone.data_bn)), V * cin0, L.ptr(self.named["in_scale"]),
+                                            L.ptr(self.named["in_shift"]), L.stream_ptr(dev)))
         for i, blk in enumerate(blocks):
+            if self.packer == "device":
+                self._pack_block_device(backbone, i, net.blocks[i])
+                continue
             imp = backbone.edge_importance[i]
             A_hat = A * imp.detach() if torch.is_tensor(imp) else A * imp
             b = net.blocks[i]
@@ -163,6 +207,29 @@ class PackedNet:
             self.head_out = 0
         self.net = net
         self.V, self.K, self.c_in = V, K, cin0
+
+    def _pack_block_device(self, backbone, i, out):
+        """Block i through tik_pack_block: outputs allocated here, folded by the library on the current stream."""
+        lib = L.lib()
+        dev = self.device
+        raw = raw_block(backbone, i)
+        first = 1 if i == 0 else 0
+        nbytes = (L.i64 * 6)()
+        L.check(lib.tik_pack_block_bytes(C.byref(raw), self.code, first, nbytes))
+        names = ("agg", "w_gcn", "b_gcn", "w_tcn", "b_tcn", "w_res_stem")
+        dts = (torch.float32, torch.float32 if first else self.tdtype, torch.float32, self.tdtype, torch.float32, torch.float32)
+        buf = L.TikPackBuffers()
+        for name, dt, nb in zip(names, dts, nbytes):
+            if nb == 0:
+                continue
+            t = torch.empty(nb // dt.itemsize, dtype=dt, device=dev)
+            self.keep.append(t)
+            self.named[f"b{i}.{name}"] = t
+            setattr(buf, name + "_dev", t.data_ptr())
+        dbn = backbone.data_bn if isinstance(backbone.data_bn, torch.nn.BatchNorm1d) else None
+        with L.on_device(dev):
+            L.check(lib.tik_pack_block(C.byref(raw), self.code, first, C.byref(_raw_bn(dbn)) if dbn is not None else None,
+                                       C.byref(buf), C.byref(out), L.stream_ptr(dev)))
 
     def _f32(self, t, name):
         t = t.to(torch.float32).contiguous()

@@ -95,6 +95,26 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(dll, name), name
     assert _lib.lib().tik_version() >= 100
     assert ctypes.sizeof(_lib.TikSlab) == 24 and ctypes.sizeof(_lib.TikBlock) == 80
+    # static_assert'ed to the same numbers in csrc/pack.cu
+    assert (ctypes.sizeof(_lib.TikRawBN), ctypes.sizeof(_lib.TikRawBlock), ctypes.sizeof(_lib.TikPackBuffers)) == (40, 216, 48)
+
+
+def test_pack_block_sizes_and_argument_errors():
+    """tik_pack_block_bytes is host-only: the buffer sizes of the first block (fp32 stem weights, per-node bias, stem
+    residual) and of an inner block, and the error codes for shapes the packer rejects."""
+    lib = _lib.lib()
+    r = _lib.TikRawBlock()
+    r.c_in, r.c_out, r.stride, r.kt, r.K, r.V, r.residual = 3, 64, 1, 3, 1, 17, _lib.RES_CONV
+    nb = (_lib.i64 * 6)()
+    assert lib.tik_pack_block_bytes(ctypes.byref(r), _lib.TIK_BF16, 1, nb) == 0
+    assert list(nb) == [17 * 17 * 4, 64 * 3 * 4, 17 * 64 * 4, 64 * (3 * 64 + 64) * 2, 17 * 64 * 4, 17 * 64 * 3 * 4]
+    r.c_in = 64
+    assert lib.tik_pack_block_bytes(ctypes.byref(r), _lib.TIK_F32, 0, nb) == 0
+    assert list(nb) == [17 * 17 * 4, 64 * 64 * 4, 17 * 64 * 4, 64 * (3 * 64 + 64) * 4, 64 * 4, 0]
+    assert lib.tik_pack_block_bytes(ctypes.byref(r), _lib.TIK_F32, 1, nb) == _lib._H["TIK_ERR_UNSUPPORTED"]   # c_in > 8 on block 0
+    r.residual = 7
+    assert lib.tik_pack_block_bytes(ctypes.byref(r), _lib.TIK_F32, 0, nb) == _lib._H["TIK_ERR_INVALID"]
+    assert lib.tik_pack_block_bytes(None, _lib.TIK_F32, 0, nb) == _lib._H["TIK_ERR_INVALID"]
 
 
 def test_keypoint_preprocessing_matches_reference(golden):
