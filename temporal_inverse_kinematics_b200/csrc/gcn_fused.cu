@@ -32,12 +32,15 @@ constexpr int kGfThreads = 64 + 32 * 2 * kGfGroupWarps;
 constexpr int kGfTile = 16384;                     // one 128-row x 64-channel swizzled slab
 constexpr int kGfSmemBudget = 225 * 1024;
 constexpr int kGfMaxBufs = 8;                      // input tiles in flight: the kernel is HBM-latency bound otherwise
+constexpr int kGwMaxBufs = 12;                     // gcn_wide_kernel: 64-channel input slabs in flight
 
 struct GcnFusedParams {
   CUtensorMap map_x, map_out, map_w;
   int32_t n_clips, T, V, ttg, tiles_t;   // ttg = frames per tile (gcn_fused_frames(T) <= 7)
   int32_t xbufs;                          // input tiles in flight
   int32_t sbufs;                          // staging tiles (2: the store of tile i-1 may still be reading while tile i is staged)
+  int32_t halves;                         // gcn_wide_kernel: CTAs per tile (output-channel split)
+  int32_t xslab;                          // gcn_wide_kernel: bytes between input slabs of the ring
   int32_t off_w, off_x, off_stage, off_bias, off_bar;
   const float* bias;                      // (V, COUT)
   const __nv_bfloat16* abd;               // (128, 128) row-major block-structured adjacency, copied to tensor memory
@@ -565,6 +568,275 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_pair_kernel(const __g
   }
 }
 
+// ------------------------------------------------------------------------------------------------ wide inputs (Cin = 256): channel GEMM first
+// A 256-channel tile (64 KB) plus its 256 x 256 weights (128 KB) and a staging tile do not fit one SM, so the last block ran
+// as two aggregation-only launches + a plain channel GEMM (three activation passes, 274 us at B = 4096).  Aggregation and
+// channel mix commute (both linear: A^ acts on nodes, Wg on channels), and with Cin = Cout doing the channel GEMM FIRST
+// costs the same tensor time while its operands come straight from TMA -- no register pass between load and MMA:
+//   MMA a:  Z[128 x CO]  = Xtile[128 x 256] . Wg'[half*CO.., :]^T   SS mode, X streamed as four 64-channel slabs (16 KB ring)
+//   mid:    Z fp32 (tensor memory) -> bf16 -> shared memory, laid out like an input tile (MN-major B operand)
+//   MMA b:  D[128 x CO]  = Abd . Z                                  TS mode, over the SAME tensor-memory columns (Z is in registers / smem by then)
+//   final:  D + bias[node] -> ReLU -> bf16 -> the same shared-memory tile (Z has been consumed) -> 4-D TMA store
+// The OUTPUT channels are split over NH = Cout / CO CTAs (CTA parity = column half; adjacent CTAs work on the same tile at
+// the same time, the second reader hits L2).  Three accumulators rotate through tensor memory and two Z / staging tiles
+// through shared memory, so MMA a of tile t+1 runs under the mid pass of tile t and the final pass of tile t-1.
+// (A first version aggregated first in 64-channel quarters -- four MMA -> register pass -> MMA hand-offs per tile: 348 us.)
+// Rounding: Z is rounded to bf16 before the aggregation (the other kernels round the aggregate before the channel mix).
+template <int NQ, int CO>
+__global__ void __launch_bounds__(kGfThreads, 1) gcn_wide_kernel(const __grid_constant__ GcnFusedParams p) {
+  constexpr int KC2 = CO / 64;
+  constexpr int ND = 3;                               // accumulators in tensor memory: [Abd 64][D 3 x CO]
+  constexpr int TMEM_COLS = 512;
+  constexpr int NZ = 3;                               // Z / staging tiles in shared memory (rotate with the accumulators)
+  static_assert(NZ == ND, "one running index serves both rotations");
+  static_assert(64 + ND * CO <= 512, "tensor memory budget");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_w = smem + p.off_w;                      // NQ slabs of CO rows x 128 B
+  uint8_t* s_x = smem + p.off_x;                      // xbufs slabs (64 channels of one tile each), p.xslab bytes apart
+  uint8_t* s_zs = smem + p.off_stage;                 // NZ tiles of KC2 slabs: Z, then the staged output of the same tile
+  float* s_bias = reinterpret_cast<float*>(smem + p.off_bias);
+  uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* x_empty = x_full + kGwMaxBufs;
+  uint64_t* w_full = x_empty + kGwMaxBufs;
+  uint64_t* da_full = w_full + 1;                     // [ND] channel GEMM done -> mid group
+  uint64_t* db_full = da_full + ND;                   // [ND] aggregation done -> final group
+  uint64_t* d_empty = db_full + ND;                   // [ND] final group has read D
+  uint64_t* z_full = d_empty + ND;                    // [NZ] mid group wrote Z -> aggregation MMA
+  uint64_t* zs_free = z_full + NZ;                    // [NZ] the output store has finished reading the tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zs_free + NZ);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NH = p.halves;                            // CTAs per tile (gridDim.x is a multiple of it)
+  const int half_out = (int)blockIdx.x % NH;
+  const int first_tile = (int)blockIdx.x / NH, tile_step = (int)gridDim.x / NH;
+  const int n_tiles = p.n_clips * p.tiles_t;
+  const int my_tiles = n_tiles > first_tile ? (n_tiles - first_tile + tile_step - 1) / tile_step : 0;
+  const int rows_valid = p.ttg * p.V;
+  const int ksteps = (rows_valid + 15) >> 4;          // K-steps of the aggregation that touch valid rows
+  const uint32_t x_bytes = (uint32_t)(rows_valid * 128);
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.map_x); tma_prefetch_desc(&p.map_out); tma_prefetch_desc(&p.map_w); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kGwMaxBufs; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    mbar_init(w_full, 1);
+    for (int i = 0; i < ND; ++i) { mbar_init(&da_full[i], 1); mbar_init(&db_full[i], 1); mbar_init(&d_empty[i], kGfGroupWarps); }
+    for (int i = 0; i < NZ; ++i) { mbar_init(&z_full[i], kGfGroupWarps); mbar_init(&zs_free[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  for (int i = threadIdx.x; i < p.V * CO; i += kGfThreads)
+    s_bias[(i / CO) * (CO + 4) + (i % CO)] = __ldg(p.bias + (size_t)(i / CO) * (CO * NH) + half_out * CO + (i % CO));
+  {
+    // Input slabs are only as long as a tile has rows (rounded up to the 8-row swizzle atom), so that more of them are
+    // in flight: the kernel is bound by HBM latency x bytes in flight.  The 128-row MMA therefore reads past a slab's
+    // end into the next slab (or, for the last one, into the Z tiles): those rows become rows of Z that only meet zero
+    // columns of Abd, so they merely have to be FINITE -- bf16 activations are; the whole ring (slabs that are never
+    // filled, or not yet, hold whatever the previous kernel left) and the Z tiles are zeroed once here.
+    for (int i = threadIdx.x; i < p.xbufs * (p.xslab >> 4); i += kGfThreads) reinterpret_cast<uint4*>(s_x)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < NZ * KC2 * kGfTile / 16; i += kGfThreads) reinterpret_cast<uint4*>(s_zs)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_abd = tmem_base, tmem_d = tmem_base + 64;
+  if (warp >= 2 && warp < 6) {
+    const int r = (warp & 3) * 32 + lane;
+    const uint4* arow = reinterpret_cast<const uint4*>(p.abd + (size_t)r * 128);
+    uint4 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = __ldg(arow + u);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t w8[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w, v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
+      tmem_st8(tmem_abd + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(8 * u), w8);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();
+
+  auto tile_of = [&](int it, int& n, int& t0) {
+    const int tile = first_tile + it * tile_step;
+    n = tile / p.tiles_t;
+    t0 = min((tile - n * p.tiles_t) * p.ttg, p.T - p.ttg);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer: one 64-channel slab per step =====================
+    if (lane == 0) {
+      mbar_expect_tx(w_full, (uint32_t)(NQ * CO * 128));
+      for (int q = 0; q < NQ; ++q) tma_load_2d(s_w + (size_t)q * CO * 128, &p.map_w, w_full, q * 64, half_out * CO);
+      int b = 0; uint32_t phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        int n, t0;
+        tile_of(it, n, t0);
+        for (int q = 0; q < NQ; ++q) {
+          mbar_wait(&x_empty[b], phase ^ 1);
+          mbar_expect_tx(&x_full[b], x_bytes);
+          tma_load_4d(s_x + (size_t)b * p.xslab, &p.map_x, &x_full[b], q * 64, t0, 0, n);
+          if (++b == p.xbufs) { b = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: ONE thread, no warp-wide bookkeeping =====================
+    // A first version ran this role warp-uniformly with lane 0 elected per MMA and rebuilt every descriptor: ~540
+    // dependent scalar instructions per tile, which (not the tensor pipe, 42 % active, and not any barrier -- no wait in this
+    // role ever spun) set the tile time.  Descriptors are now one 64-bit add from three bases; indices are running counters.
+    if (lane == 0) {
+      constexpr uint32_t idesc_a = make_idesc_bf16(128, CO);
+      constexpr uint32_t idesc_b = make_idesc_bf16(128, CO) | (1u << 16);   // B operand (Z) MN-major
+      mbar_wait(w_full, 0);
+      // the start-address field (bits 0..13, 16-byte units) never overflows: shared-memory addresses are < 256 KB
+      const uint64_t dw0 = make_smem_desc_kmajor_sw128(smem_u32(s_w));
+      const uint64_t dx0 = make_smem_desc_kmajor_sw128(smem_u32(s_x));
+      const uint64_t dz0 = make_smem_desc_mnmajor_sw128(smem_u32(s_zs), (uint32_t)kGfTile);
+      int b = 0; uint32_t xphase = 0;
+      int da = 0; uint32_t da_par = 1;                 // accumulator of the next channel GEMM, parity of its d_empty wait
+      auto mma_a = [&]() {                             // Z = X . W^T into accumulator da
+        mbar_wait(&d_empty[da], da_par);
+        const uint32_t dcol = tmem_d + (uint32_t)(da * CO);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          mbar_wait(&x_full[b], xphase);
+          tc_fence_after();
+          const uint64_t dx = dx0 + (uint64_t)(b * (p.xslab >> 4));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(dcol, dx + (uint64_t)(2 * k), dw0 + (uint64_t)(q * ((CO * 128) >> 4) + 2 * k), idesc_a, (q | k) != 0 ? 1u : 0u);
+          umma_commit(&x_empty[b]);
+          if (++b == p.xbufs) { b = 0; xphase ^= 1; }
+        }
+        umma_commit(&da_full[da]);
+        if (++da == ND) { da = 0; da_par ^= 1; }
+      };
+      int db = 0; uint32_t db_par = 0;
+      if (my_tiles > 0) mma_a();
+      for (int t = 0; t < my_tiles; ++t) {
+        if (t + 1 < my_tiles) mma_a();
+        mbar_wait(&z_full[db], db_par);
+        tc_fence_after();
+        const uint64_t dz = dz0 + (uint64_t)(db * ((KC2 * kGfTile) >> 4));
+        const uint32_t dcol = tmem_d + (uint32_t)(db * CO);
+        for (int k = 0; k < ksteps; ++k)
+          umma_bf16_ts(dcol, tmem_abd + (uint32_t)(8 * k), dz + (uint64_t)(k * (2048 >> 4)), idesc_b, k != 0 ? 1u : 0u);
+        umma_commit(&db_full[db]);
+        if (++db == ND) { db = 0; db_par ^= 1; }
+      }
+    }
+  } else if (warp < 2 + kGfGroupWarps) {
+    // ===================== mid group: Z (fp32, tensor memory) -> bf16 tile in shared memory =====================
+    constexpr int CW = CO / 2;
+    const int lane_grp = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = lane_grp * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
+    const bool rows_used = lane_grp * 32 < ksteps * 16;                  // the aggregation never reads Z rows past its K-steps
+    int d = 0; uint32_t dpar = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      uint8_t* zs = s_zs + (size_t)d * (KC2 * kGfTile);
+      mbar_wait(&da_full[d], dpar);
+      tc_fence_after();
+      uint32_t a[CW];
+      if (rows_used) {
+#pragma unroll
+        for (int i = 0; i < CW / 16; ++i) tmem_ld16(tmem_d + lane_off + (uint32_t)(d * CO + half * CW + 16 * i), a + 16 * i);
+        tmem_ld_wait();
+      }
+      mbar_wait(&zs_free[d], dpar ^ 1);                                    // the store of tile t-3 has read this tile
+      if (rows_used) {
+#pragma unroll
+      for (int q = 0; q < CW / 8; ++q) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(a[8 * q + 0]), __uint_as_float(a[8 * q + 1]));
+        u.y = pack_bf16x2(__uint_as_float(a[8 * q + 2]), __uint_as_float(a[8 * q + 3]));
+        u.z = pack_bf16x2(__uint_as_float(a[8 * q + 4]), __uint_as_float(a[8 * q + 5]));
+        u.w = pack_bf16x2(__uint_as_float(a[8 * q + 6]), __uint_as_float(a[8 * q + 7]));
+        const int col = half * CW + 8 * q;
+        const int j = (col & 63) >> 3;
+        *reinterpret_cast<uint4*>(zs + (size_t)(col >> 6) * kGfTile + (size_t)r * 128 + ((j ^ (r & 7)) << 4)) = u;
+      }
+      fence_proxy_async_smem();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&z_full[d]);
+      if (++d == ND) { d = 0; dpar ^= 1; }
+    }
+  } else {
+    // ===================== final group: D + bias -> ReLU -> bf16 -> the tile's shared-memory slot -> TMA store =====================
+    constexpr int CW = CO / 2;
+    const int lane_grp = warp & 3;
+    const int half = (warp - 2 - kGfGroupWarps) >> 2;
+    const int r = lane_grp * 32 + lane;
+    const int node = r / p.ttg;
+    const float* bias = s_bias + (node < p.V ? node : 0) * (CO + 4) + half * CW;
+    const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
+    const bool issuer = threadIdx.x == 32 * (2 + kGfGroupWarps);
+    const bool rows_used = lane_grp * 32 < rows_valid;                   // warps whose 32 rows are all padding only keep the barriers
+    int d = 0, d_prev = 0; uint32_t dpar = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      int n, t0;
+      tile_of(t, n, t0);
+      uint8_t* stage = s_zs + (size_t)d * (KC2 * kGfTile);
+      mbar_wait(&db_full[d], dpar);                                        // also: the aggregation MMA has consumed Z(t)
+      tc_fence_after();
+      uint32_t a[CW];
+      if (rows_used) {
+#pragma unroll
+        for (int i = 0; i < CW / 16; ++i) tmem_ld16(tmem_d + lane_off + (uint32_t)(d * CO + half * CW + 16 * i), a + 16 * i);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d_empty[d]);
+      if (issuer && t > 0) {                                               // the previous tile's store (issued a whole pass ago) has read its tile
+        tma_store_wait_read0();
+        mbar_arrive(&zs_free[d_prev]);
+      }
+      if (rows_used) {
+#pragma unroll
+      for (int q = 0; q < CW / 8; ++q) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * q);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * q + 4);
+        const float v0 = __uint_as_float(a[8 * q + 0]) + b0.x, v1 = __uint_as_float(a[8 * q + 1]) + b0.y;
+        const float v2 = __uint_as_float(a[8 * q + 2]) + b0.z, v3 = __uint_as_float(a[8 * q + 3]) + b0.w;
+        const float v4 = __uint_as_float(a[8 * q + 4]) + b1.x, v5 = __uint_as_float(a[8 * q + 5]) + b1.y;
+        const float v6 = __uint_as_float(a[8 * q + 6]) + b1.z, v7 = __uint_as_float(a[8 * q + 7]) + b1.w;
+        uint4 u;
+        if (p.relu) { u.x = pack_bf16x2_relu(v0, v1); u.y = pack_bf16x2_relu(v2, v3); u.z = pack_bf16x2_relu(v4, v5); u.w = pack_bf16x2_relu(v6, v7); }
+        else { u.x = pack_bf16x2(v0, v1); u.y = pack_bf16x2(v2, v3); u.z = pack_bf16x2(v4, v5); u.w = pack_bf16x2(v6, v7); }
+        const int col = half * CW + 8 * q;
+        const int j = (col & 63) >> 3;
+        *reinterpret_cast<uint4*>(stage + (size_t)(col >> 6) * kGfTile + (size_t)r * 128 + ((j ^ (r & 7)) << 4)) = u;
+      }
+      fence_proxy_async_smem();
+      }
+      named_bar_sync(2, 32 * kGfGroupWarps);
+      if (issuer) {
+        for (int c = 0; c < KC2; ++c) tma_store_4d(&p.map_out, stage + (size_t)c * kGfTile, half_out * CO + c * 64, t0, 0, n);
+        tma_store_commit();
+      }
+      d_prev = d;
+      if (++d == ND) { d = 0; dpar ^= 1; }
+    }
+    if (issuer) tma_store_wait0();
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -596,7 +868,9 @@ struct GcnFusedPrepared {
   GcnFusedParams p;
   int cin, cout, smem_bytes;
   bool pair;                               // Cin = 64: two tiles per aggregation pass (gcn_fused_pair_kernel)
+  bool wide;                               // Cin = 256: quarter-streamed inputs, output channels split over two CTAs (gcn_wide_kernel)
 };
+constexpr int kGwCo = 128;                 // output channels per CTA of the wide kernel
 
 // Frames per tile: at most 7 (7 x 17 nodes = 119 of the 128 MMA rows), balanced over the ceil(T/7) tiles of a clip so
 // that the last tile re-does as few frames as possible (T=16: 3 tiles of 6, not 7+7+shifted 7; T=8: 2 tiles of 4).
@@ -607,6 +881,7 @@ int gcn_fused_frames(int T) {
 
 bool gcn_fused_supported(int cin, int cout, int V, int K) {
   if (K != 1 || V * 7 > 128 || V < 1) return false;
+  if (cin == 256 && cout == 256) return !getenv("TIK_NO_GCN_WIDE");          // gcn_wide_kernel
   return (cin == 64 && (cout == 64 || cout == 128)) || (cin == 128 && (cout == 128 || cout == 256));
 }
 
@@ -640,10 +915,31 @@ int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float
   if (rc == TIK_OK) {
     uint64_t dims[2] = {(uint64_t)cin, (uint64_t)cout};
     uint64_t strides[1] = {(uint64_t)cin * 2};
-    uint32_t box[2] = {64, (uint32_t)cout};
+    uint32_t box[2] = {64, (uint32_t)(cin == 256 ? kGwCo : cout)};
     rc = encode_bf16_map(&p.map_w, w, 2, dims, strides, box);
   }
   if (rc != TIK_OK) { delete g; return rc; }
+  g->wide = cin == 256;
+  if (g->wide) {
+    // W slice 64 KB + three Z / staging tiles 96 KB + bias; the rest is the ring of input slabs
+    p.halves = cout / kGwCo;
+    const int w_bytes = (cin / 64) * kGwCo * 128;
+    const int bias_bytes = (V * (kGwCo + 4) * 4 + 1023) / 1024 * 1024;
+    p.sbufs = 3;                           // Z / staging tiles (NZ in the kernel)
+    p.xslab = (p.ttg * V + 7) / 8 * 1024;
+    const int fixed = w_bytes + p.sbufs * (kGwCo / 64) * kGfTile + bias_bytes + 512;
+    p.xbufs = std::min((kGfSmemBudget - fixed) / p.xslab, kGwMaxBufs);
+    if (const char* e = getenv("TIK_GCN_WIDE_XBUFS")) p.xbufs = std::max(1, std::min(p.xbufs, atoi(e)));
+    p.off_w = 0;
+    p.off_x = w_bytes;
+    p.off_stage = p.off_x + p.xbufs * p.xslab;
+    p.off_bias = p.off_stage + p.sbufs * (kGwCo / 64) * kGfTile;
+    p.off_bar = p.off_bias + bias_bytes;
+    g->smem_bytes = p.off_bar + 512 + 1024;
+    g->pair = false;
+    *outp = g;
+    return TIK_OK;
+  }
   const int kc1 = cin / 64, kc2 = cout / 64;
   const int w_bytes = kc1 * cout * 128;
   const int bias_bytes = (V * (cout + 4) * 4 + 1023) / 1024 * 1024;
@@ -703,6 +999,19 @@ static int gf_launch_pair(const GcnFusedPrepared* g, unsigned grid, cudaStream_t
   return TIK_OK;
 }
 
+static int gf_launch_wide(const GcnFusedPrepared* g, unsigned grid, cudaStream_t s) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  TIK_CUDA(cudaGetDevice(&dev));
+  if (!attr_done[dev & 63]) {
+    TIK_CUDA(cudaFuncSetAttribute(gcn_wide_kernel<4, kGwCo>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGfSmemBudget + 2048));
+    TIK_CUDA(cudaFuncSetAttribute(gcn_wide_kernel<4, kGwCo>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_done[dev & 63] = true;
+  }
+  TIK_CUDA(launch_pdl(gcn_wide_kernel<4, kGwCo>, grid, kGfThreads, (size_t)g->smem_bytes, s, g->p));
+  return TIK_OK;
+}
+
 int gcn_fused_launch(GcnFusedPrepared* g, int64_t n_clips, cudaStream_t s) {
   GcnFusedParams& p = g->p;
   const int32_t cap = p.n_clips;
@@ -715,7 +1024,10 @@ int gcn_fused_launch(GcnFusedPrepared* g, int64_t n_clips, cudaStream_t s) {
   const int64_t tiles = n_clips * p.tiles_t;
   const unsigned grid = (unsigned)std::min<int64_t>(g->pair ? (tiles + 1) / 2 : tiles, sms);
   int rc;
-  if (g->pair && g->cout == 64) rc = gf_launch_pair<64>(g, grid, s);
+  if (g->wide) {                           // CTA parity = output-channel half: the grid is a multiple of the split
+    const int64_t want = tiles * p.halves, cap_ctas = sms / p.halves * p.halves;
+    rc = gf_launch_wide(g, (unsigned)std::min<int64_t>(want, cap_ctas), s);
+  } else if (g->pair && g->cout == 64) rc = gf_launch_pair<64>(g, grid, s);
   else if (g->pair && g->cout == 128) rc = gf_launch_pair<128>(g, grid, s);
   else if (g->cin == 64 && g->cout == 64) rc = gf_launch_variant<64, 64>(g, grid, s);
   else if (g->cin == 64 && g->cout == 128) rc = gf_launch_variant<64, 128>(g, grid, s);
