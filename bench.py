@@ -369,6 +369,26 @@ def _hbm_rooflines(dev, peaks, frames):
     return out
 
 
+def pin_to_gpu_numa_node(local):
+    """Bind this rank's threads to the CPUs nearest its GPU (NVML's ideal affinity), BEFORE any pinned host memory is
+    allocated: the e2e leg moves 62 MB per 4 ms step per GPU through host memory, and with 8 ranks on a two-socket host
+    half of them otherwise stage their copies on the far socket.  Best effort: returns the number of CPUs bound, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import copy
     import torch
@@ -380,6 +400,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    args.numa_cpus = pin_to_gpu_numa_node(local) if world > 1 else None     # one rank: leave every host thread to the CPU arm
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -671,7 +692,9 @@ def measure(args, dev, world, rank, local):
                            "parallelism": f"dp{world}",
                            "gather": ("none" if world == 1 else "ONE NCCL all_gather of the poses at the end of the step, on the compute stream"
                                       if args.config == 3 else "NCCL all_gather of the poses per step on a side stream from a 4-deep snapshot ring (overlaps the next steps)"),
-                           "e2e_pipeline": "pinned H2D of micro-batch k+1 and D2H of step i's results (double-buffered) overlap compute on a copy stream"},
+                           "e2e_pipeline": "pinned H2D of micro-batch k+1 and D2H of step i's results (double-buffered) overlap compute on a copy stream",
+                           "host_affinity": (f"rank 0 bound to the {args.numa_cpus} CPUs NVML names nearest its GPU" if getattr(args, "numa_cpus", None)
+                                             else "unbound")},
                 "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "note": "every step: pinned-host input -> H2D -> model(x) + fk_body -> D2H of poses and joints, all inside the timed "
                                 "region, copies overlapped on a copy stream; no L2 flush here (the step's input arrives over PCIe), "

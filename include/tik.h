@@ -116,8 +116,8 @@ int tik_aggregate(int dtype, const void* x_dev, const float* agg_dev, void* out_
 
 /* Fused graph convolution (tensor cores, bf16, K = 1 partition): aggregation + 1x1 channel GEMM + bias [+ReLU]
  * in one kernel; replaces tik_aggregate + tik_rowgemm for (Cin,Cout) in {(64,64),(64,128),(128,128),(128,256),(256,256)}.
- *   x (N,V,T,Cin) bf16; abd (128,128) bf16 with abd[w*f+t][v*f+t'] = agg[v][w] * (t==t'), f = ceil(T / ceil(T/7)) <= 7, zero
- *   elsewhere; w (Cout,Cin) bf16; bias (V,Cout) fp32; out (N,V,T,Cout) bf16. */
+ *   x (N,V,T,Cin) bf16; abd (128,128) bf16 with abd[w*f+t][v*f+t'] = agg[v][w] * (t==t'), f = ceil(T / ceil(T/7)) <= 7
+ *   (Cin = 256: f = ceil(T / ceil(T/5)) <= 5), zero elsewhere; w (Cout,Cin) bf16; bias (V,Cout) fp32; out (N,V,T,Cout) bf16. */
 int tik_gcn_fused(const void* x_dev, const void* abd_dev, const void* w_dev, const float* bias_dev, void* out_dev,
                   int64_t N, int T, int V, int Cin, int Cout, int relu, void* stream);
 

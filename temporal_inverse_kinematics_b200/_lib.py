@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtik.so")
+LIB_PATH = os.environ.get("TIK_LIB_PATH") or os.path.join(_HERE, "libtik.so")     # TIK_LIB_PATH: A/B builds of the same ABI (tools/)
 
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "tik.h")
 

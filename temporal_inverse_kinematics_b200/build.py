@@ -45,7 +45,7 @@ def _stale():
 
 def build(force=False, verbose=False):
     """Compiles every CUDA source for sm_100a into temporal_inverse_kinematics_b200/libtik.so."""
-    if not force and not _stale():
+    if not force and not os.environ.get("TIK_BUILD_VARIANT") and not _stale():
         return LIB
     objs = []
     flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -56,10 +56,14 @@ def build(force=False, verbose=False):
         flags += ["-DTIK_PROBE"]
     if os.environ.get("TIK_TEST_WAIT") == "1":      # experiment: spin on mbarrier.test_wait instead of try_wait
         flags += ["-DTIK_TEST_WAIT"]
+    variant = os.environ.get("TIK_BUILD_VARIANT")   # A/B library next to the product one: build/libtik_<name>.so with -D<NAME>
+    obj_dir = os.path.join(HERE, "build", variant) if variant else os.path.join(HERE, "build")
+    if variant:
+        flags += ["-D" + variant.upper()]
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
     for s in SOURCES:
-        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+        o = os.path.join(obj_dir, s.replace(".cu", ".o"))
         objs.append(o)
         procs.append((s, subprocess.Popen([_nvcc(), *flags, "-c", os.path.join(CSRC, s), "-o", o],
                                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -71,10 +75,12 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB, *objs, "-cudart", "static"])
-    with open(STAMP, "w") as f:
-        f.write(_flavour() + "\n")
-    return LIB
+    out = os.path.join(HERE, "build", f"libtik_{variant}.so") if variant else LIB
+    subprocess.check_call([_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", out, *objs, "-cudart", "static"])
+    if not variant:
+        with open(STAMP, "w") as f:
+            f.write(_flavour() + "\n")
+    return out
 
 
 if __name__ == "__main__":

@@ -32,7 +32,7 @@ constexpr int kGfThreads = 64 + 32 * 2 * kGfGroupWarps;
 constexpr int kGfTile = 16384;                     // one 128-row x 64-channel swizzled slab
 constexpr int kGfSmemBudget = 225 * 1024;
 constexpr int kGfMaxBufs = 8;                      // input tiles in flight: the kernel is HBM-latency bound otherwise
-constexpr int kGwMaxBufs = 12;                     // gcn_wide_kernel: 64-channel input slabs in flight
+constexpr int kGwMaxBufs = 16;                     // gcn_wide_kernel: 64-channel input slabs in flight
 
 struct GcnFusedParams {
   CUtensorMap map_x, map_out, map_w;
@@ -41,6 +41,7 @@ struct GcnFusedParams {
   int32_t sbufs;                          // staging tiles (2: the store of tile i-1 may still be reading while tile i is staged)
   int32_t halves;                         // gcn_wide_kernel: CTAs per tile (output-channel split)
   int32_t xslab;                          // gcn_wide_kernel: bytes between input slabs of the ring
+  const __nv_bfloat16* w;                 // gcn_wide_kernel: (Cout, Cin) weights, copied to tensor memory
   int32_t off_w, off_x, off_stage, off_bias, off_bar;
   const float* bias;                      // (V, COUT)
   const __nv_bfloat16* abd;               // (128, 128) row-major block-structured adjacency, copied to tensor memory
@@ -568,43 +569,44 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_pair_kernel(const __g
   }
 }
 
-// ------------------------------------------------------------------------------------------------ wide inputs (Cin = 256): channel GEMM first
+// ------------------------------------------------------------------------------------------------ wide inputs (Cin = 256): weights in tensor memory
 // A 256-channel tile (64 KB) plus its 256 x 256 weights (128 KB) and a staging tile do not fit one SM, so the last block ran
-// as two aggregation-only launches + a plain channel GEMM (three activation passes, 274 us at B = 4096).  Aggregation and
-// channel mix commute (both linear: A^ acts on nodes, Wg on channels), and with Cin = Cout doing the channel GEMM FIRST
-// costs the same tensor time while its operands come straight from TMA -- no register pass between load and MMA:
-//   MMA a:  Z[128 x CO]  = Xtile[128 x 256] . Wg'[half*CO.., :]^T   SS mode, X streamed as four 64-channel slabs (16 KB ring)
-//   mid:    Z fp32 (tensor memory) -> bf16 -> shared memory, laid out like an input tile (MN-major B operand)
-//   MMA b:  D[128 x CO]  = Abd . Z                                  TS mode, over the SAME tensor-memory columns (Z is in registers / smem by then)
-//   final:  D + bias[node] -> ReLU -> bf16 -> the same shared-memory tile (Z has been consumed) -> 4-D TMA store
-// The OUTPUT channels are split over NH = Cout / CO CTAs (CTA parity = column half; adjacent CTAs work on the same tile at
-// the same time, the second reader hits L2).  Three accumulators rotate through tensor memory and two Z / staging tiles
-// through shared memory, so MMA a of tile t+1 runs under the mid pass of tile t and the final pass of tile t-1.
-// (A first version aggregated first in 64-channel quarters -- four MMA -> register pass -> MMA hand-offs per tile: 348 us.)
-// Rounding: Z is rounded to bf16 before the aggregation (the other kernels round the aggregate before the channel mix).
-template <int NQ, int CO>
+// as two aggregation-only launches + a plain channel GEMM (three activation passes, 274 us at B = 4096).  This kernel does
+// it in one pass, TRANSPOSED: output channels on the 128 accumulator lanes, tile rows (node, frame) on the columns.
+//   * the weights are the TMEM-resident A operand (TS mode): 128 output channels x 256 input channels = 128 columns,
+//     loaded once per CTA; the output channels are split over NH = Cout / 128 CTAs (CTA parity = channel half; adjacent
+//     CTAs work on the same tile at the same time, the second reader hits L2);
+//   * MMA a: Z^T[128 ch x N] = Wg'[128 x 256] . Xtile^T -- aggregation and channel mix commute, and with Cin = Cout the
+//     channel GEMM first costs nothing extra; the X slabs are the B operand exactly as TMA delivers them (rows x 64
+//     channels, K-major), N = tile rows rounded up to 16 (80 for the 68 rows of a 4-frame tile, not 128);
+//   * mid: Z^T fp32 -> bf16 pairs in place in tensor memory (it is the A operand of the next MMA: no shared memory);
+//   * MMA b: D^T[128 ch x N] = Z^T . Abd^T, Abd (128 x 128, K-major) resident in shared memory;
+//   * final: D^T + bias[node][ch] -> ReLU -> bf16 -> transposed into the row-major staging tile -> 4-D TMA store.
+// Shared-memory traffic per tile drops from ~300 KB (SS-mode 128 x 128 x 16 MMAs read 8 KB each; Z went through shared
+// memory) to ~150 KB, the MMA work from 1344 to 840 cycles; what is left is the HBM time of one read + one write.
+// History: aggregation first in 64-channel quarters (four MMA -> register pass -> MMA hand-offs per tile): 348 us;
+// channel GEMM first in SS mode with Z staged through shared memory: 171 us (shared-memory bandwidth bound).
+// Tiles hold at most 5 frames here (N <= 96: two Z^T and two D^T accumulators of 96 columns beside the 128 weight columns).
+constexpr int kGwAcc = 96;                          // tensor-memory columns per accumulator
+template <int NQ>
 __global__ void __launch_bounds__(kGfThreads, 1) gcn_wide_kernel(const __grid_constant__ GcnFusedParams p) {
-  constexpr int KC2 = CO / 64;
-  constexpr int ND = 3;                               // accumulators in tensor memory: [Abd 64][D 3 x CO]
-  constexpr int TMEM_COLS = 512;
-  constexpr int NZ = 3;                               // Z / staging tiles in shared memory (rotate with the accumulators)
-  static_assert(NZ == ND, "one running index serves both rotations");
-  static_assert(64 + ND * CO <= 512, "tensor memory budget");
+  constexpr int CO = 128;                             // output channels per CTA = accumulator lanes
+  constexpr int TMEM_COLS = 512;                      // [W 128][Z^T 2 x 96][D^T 2 x 96]
+  static_assert(NQ * 32 == 128, "256 input channels as bf16 pairs fill 128 columns");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* s_w = smem + p.off_w;                      // NQ slabs of CO rows x 128 B
+  uint8_t* s_abd = smem + p.off_w;                    // 2 slabs of 128 rows x 64 K (the map_w box)
   uint8_t* s_x = smem + p.off_x;                      // xbufs slabs (64 channels of one tile each), p.xslab bytes apart
-  uint8_t* s_zs = smem + p.off_stage;                 // NZ tiles of KC2 slabs: Z, then the staged output of the same tile
-  float* s_bias = reinterpret_cast<float*>(smem + p.off_bias);
+  uint8_t* s_stage = smem + p.off_stage;              // 2 staging tiles of 2 slabs of 16 * n_groups rows (stores are unconditional)
+  float* s_bias = reinterpret_cast<float*>(smem + p.off_bias);   // [node][128]
   uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* x_empty = x_full + kGwMaxBufs;
-  uint64_t* w_full = x_empty + kGwMaxBufs;
-  uint64_t* da_full = w_full + 1;                     // [ND] channel GEMM done -> mid group
-  uint64_t* db_full = da_full + ND;                   // [ND] aggregation done -> final group
-  uint64_t* d_empty = db_full + ND;                   // [ND] final group has read D
-  uint64_t* z_full = d_empty + ND;                    // [NZ] mid group wrote Z -> aggregation MMA
-  uint64_t* zs_free = z_full + NZ;                    // [NZ] the output store has finished reading the tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zs_free + NZ);
+  uint64_t* abd_full = x_empty + kGwMaxBufs;
+  uint64_t* da_full = abd_full + 1;                   // [2] channel GEMM done -> mid group
+  uint64_t* z_full = da_full + 2;                     // [2] mid group packed Z^T -> aggregation MMA
+  uint64_t* d2_full = z_full + 2;                     // [2] aggregation done -> final group
+  uint64_t* d2_empty = d2_full + 2;                   // [2] final group has read D^T
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NH = p.halves;                            // CTAs per tile (gridDim.x is a multiple of it)
@@ -613,45 +615,45 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_wide_kernel(const __grid_co
   const int n_tiles = p.n_clips * p.tiles_t;
   const int my_tiles = n_tiles > first_tile ? (n_tiles - first_tile + tile_step - 1) / tile_step : 0;
   const int rows_valid = p.ttg * p.V;
-  const int ksteps = (rows_valid + 15) >> 4;          // K-steps of the aggregation that touch valid rows
+  const int n_groups = (rows_valid + 15) >> 4;        // 16-row groups = K-steps of the aggregation; N = 16 * n_groups <= 96
   const uint32_t x_bytes = (uint32_t)(rows_valid * 128);
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.map_x); tma_prefetch_desc(&p.map_out); tma_prefetch_desc(&p.map_w); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kGwMaxBufs; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-    mbar_init(w_full, 1);
-    for (int i = 0; i < ND; ++i) { mbar_init(&da_full[i], 1); mbar_init(&db_full[i], 1); mbar_init(&d_empty[i], kGfGroupWarps); }
-    for (int i = 0; i < NZ; ++i) { mbar_init(&z_full[i], kGfGroupWarps); mbar_init(&zs_free[i], 1); }
+    mbar_init(abd_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&da_full[i], 1); mbar_init(&z_full[i], kGfGroupWarps); mbar_init(&d2_full[i], 1); mbar_init(&d2_empty[i], kGfGroupWarps);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
   for (int i = threadIdx.x; i < p.V * CO; i += kGfThreads)
-    s_bias[(i / CO) * (CO + 4) + (i % CO)] = __ldg(p.bias + (size_t)(i / CO) * (CO * NH) + half_out * CO + (i % CO));
+    s_bias[i] = __ldg(p.bias + (size_t)(i / CO) * (CO * NH) + half_out * CO + (i % CO));
   {
-    // Input slabs are only as long as a tile has rows (rounded up to the 8-row swizzle atom), so that more of them are
-    // in flight: the kernel is bound by HBM latency x bytes in flight.  The 128-row MMA therefore reads past a slab's
-    // end into the next slab (or, for the last one, into the Z tiles): those rows become rows of Z that only meet zero
-    // columns of Abd, so they merely have to be FINITE -- bf16 activations are; the whole ring (slabs that are never
-    // filled, or not yet, hold whatever the previous kernel left) and the Z tiles are zeroed once here.
-    for (int i = threadIdx.x; i < p.xbufs * (p.xslab >> 4); i += kGfThreads) reinterpret_cast<uint4*>(s_x)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < NZ * KC2 * kGfTile / 16; i += kGfThreads) reinterpret_cast<uint4*>(s_zs)[i] = make_uint4(0, 0, 0, 0);
+    // Input slabs are only as long as a tile has rows (rounded up to the 8-row swizzle atom), so that many are in flight.
+    // The MMA reads N = 16 * n_groups rows, i.e. up to 15 rows past a slab's end into the next slab (for the last one: into
+    // the staging tiles); those become columns of Z^T that only meet zero columns of Abd, so they merely have to be FINITE:
+    // bf16 activations are, and the ring and the staging tiles are zeroed once here (a slab that is never filled, or not
+    // yet, holds whatever the previous kernel left).
+    const int n16 = p.xbufs * (p.xslab >> 4) + 4 * n_groups * 128;   // ring + 2 staging tiles of 2 slabs, contiguous
+    for (int i = threadIdx.x; i < n16; i += kGfThreads) reinterpret_cast<uint4*>(s_x)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_abd = tmem_base, tmem_d = tmem_base + 64;
+  const uint32_t tmem_w = tmem_base, tmem_z = tmem_base + 128, tmem_d2 = tmem_base + 128 + 2 * kGwAcc;
+  // ---- this CTA's 128 x 256 weight slice -> tensor memory: lane = output channel, column j = input channels 2j, 2j+1
   if (warp >= 2 && warp < 6) {
-    const int r = (warp & 3) * 32 + lane;
-    const uint4* arow = reinterpret_cast<const uint4*>(p.abd + (size_t)r * 128);
-    uint4 v[16];
+    const int c = (warp & 3) * 32 + lane;
+    const uint4* wrow = reinterpret_cast<const uint4*>(p.w + (size_t)(half_out * CO + c) * (NQ * 64));
 #pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = __ldg(arow + u);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const uint32_t w8[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w, v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
-      tmem_st8(tmem_abd + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(8 * u), w8);
+    for (int u = 0; u < NQ * 4; ++u) {                // 16 input channels = 8 columns per step
+      const uint4 v0 = __ldg(wrow + 2 * u), v1 = __ldg(wrow + 2 * u + 1);
+      const uint32_t w8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      tmem_st8(tmem_w + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(8 * u), w8);
     }
     tmem_st_wait();
   }
@@ -668,10 +670,11 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_wide_kernel(const __grid_co
   };
 
   if (warp == 0) {
-    // ===================== TMA producer: one 64-channel slab per step =====================
+    // ===================== TMA producer: Abd once, then one 64-channel slab per step =====================
     if (lane == 0) {
-      mbar_expect_tx(w_full, (uint32_t)(NQ * CO * 128));
-      for (int q = 0; q < NQ; ++q) tma_load_2d(s_w + (size_t)q * CO * 128, &p.map_w, w_full, q * 64, half_out * CO);
+      mbar_expect_tx(abd_full, 2u * kGfTile);
+      tma_load_2d(s_abd, &p.map_w, abd_full, 0, 0);
+      tma_load_2d(s_abd + kGfTile, &p.map_w, abd_full, 64, 0);
       int b = 0; uint32_t phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
         int n, t0;
@@ -685,146 +688,136 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_wide_kernel(const __grid_co
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: ONE thread, no warp-wide bookkeeping =====================
-    // A first version ran this role warp-uniformly with lane 0 elected per MMA and rebuilt every descriptor: ~540
-    // dependent scalar instructions per tile, which (not the tensor pipe, 42 % active, and not any barrier -- no wait in this
-    // role ever spun) set the tile time.  Descriptors are now one 64-bit add from three bases; indices are running counters.
-    if (lane == 0) {
-      constexpr uint32_t idesc_a = make_idesc_bf16(128, CO);
-      constexpr uint32_t idesc_b = make_idesc_bf16(128, CO) | (1u << 16);   // B operand (Z) MN-major
-      mbar_wait(w_full, 0);
+    // ===================== MMA issuer: the whole warp runs the loop, one elected lane issues (umma_*_w) =====================
+    // With N <= 96 an MMA is <= 48 tensor cycles, so this role is bound by how fast it can issue.  Run under `if (lane ==
+    // 0)` every tcgen05 instruction was wrapped in a uniformisation loop (~8 instructions; ~500 dependent scalar
+    // instructions per tile: 2800 cycles per tile with the tensor pipe 31 % active and no barrier ever spinning).
+    // Descriptors are one 64-bit add from two bases; ring indices are running counters.
+    {
+      const uint32_t idesc = make_idesc_bf16(128, 16 * n_groups);
+      mbar_wait(abd_full, 0);
       // the start-address field (bits 0..13, 16-byte units) never overflows: shared-memory addresses are < 256 KB
-      const uint64_t dw0 = make_smem_desc_kmajor_sw128(smem_u32(s_w));
       const uint64_t dx0 = make_smem_desc_kmajor_sw128(smem_u32(s_x));
-      const uint64_t dz0 = make_smem_desc_mnmajor_sw128(smem_u32(s_zs), (uint32_t)kGfTile);
+      const uint64_t dabd0 = make_smem_desc_kmajor_sw128(smem_u32(s_abd));
+      const uint32_t xstep = (uint32_t)(p.xslab >> 4);
       int b = 0; uint32_t xphase = 0;
-      int da = 0; uint32_t da_par = 1;                 // accumulator of the next channel GEMM, parity of its d_empty wait
-      auto mma_a = [&]() {                             // Z = X . W^T into accumulator da
-        mbar_wait(&d_empty[da], da_par);
-        const uint32_t dcol = tmem_d + (uint32_t)(da * CO);
+      auto mma_a = [&](int s) {                        // Z^T = W . X^T into accumulator s (its last reader, MMA b of two tiles ago, was issued earlier)
+        const uint32_t dcol = tmem_z + (uint32_t)(s * kGwAcc);
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
           mbar_wait(&x_full[b], xphase);
           tc_fence_after();
-          const uint64_t dx = dx0 + (uint64_t)(b * (p.xslab >> 4));
+          const uint64_t dx = dx0 + (uint64_t)((uint32_t)b * xstep);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(dcol, dx + (uint64_t)(2 * k), dw0 + (uint64_t)(q * ((CO * 128) >> 4) + 2 * k), idesc_a, (q | k) != 0 ? 1u : 0u);
-          umma_commit(&x_empty[b]);
+            umma_bf16_ts_w(dcol, tmem_w + (uint32_t)(q * 32 + k * 8), dx + (uint64_t)(2 * k), idesc, (q | k) != 0 ? 1u : 0u);
+          umma_commit_w(&x_empty[b]);
           if (++b == p.xbufs) { b = 0; xphase ^= 1; }
         }
-        umma_commit(&da_full[da]);
-        if (++da == ND) { da = 0; da_par ^= 1; }
+        umma_commit_w(&da_full[s]);
       };
-      int db = 0; uint32_t db_par = 0;
-      if (my_tiles > 0) mma_a();
+      if (my_tiles > 0) mma_a(0);
       for (int t = 0; t < my_tiles; ++t) {
-        if (t + 1 < my_tiles) mma_a();
-        mbar_wait(&z_full[db], db_par);
+        const int s = t & 1;
+        const uint32_t par = (uint32_t)((t >> 1) & 1);
+        if (t + 1 < my_tiles) mma_a(s ^ 1);
+        mbar_wait(&z_full[s], par);
+        mbar_wait(&d2_empty[s], par ^ 1);
         tc_fence_after();
-        const uint64_t dz = dz0 + (uint64_t)(db * ((KC2 * kGfTile) >> 4));
-        const uint32_t dcol = tmem_d + (uint32_t)(db * CO);
-        for (int k = 0; k < ksteps; ++k)
-          umma_bf16_ts(dcol, tmem_abd + (uint32_t)(8 * k), dz + (uint64_t)(k * (2048 >> 4)), idesc_b, k != 0 ? 1u : 0u);
-        umma_commit(&db_full[db]);
-        if (++db == ND) { db = 0; db_par ^= 1; }
+        for (int j = 0; j < n_groups; ++j)             // rows 16j..16j+15 of the tile: Z^T columns 16j.. (packed into 8), Abd K-columns 16j..
+          umma_bf16_ts_w(tmem_d2 + (uint32_t)(s * kGwAcc), tmem_z + (uint32_t)(s * kGwAcc + 16 * j),
+                         dabd0 + (uint64_t)((j >> 2) * (kGfTile >> 4) + (j & 3) * 2), idesc, j != 0 ? 1u : 0u);
+        umma_commit_w(&d2_full[s]);
       }
     }
   } else if (warp < 2 + kGfGroupWarps) {
-    // ===================== mid group: Z (fp32, tensor memory) -> bf16 tile in shared memory =====================
-    constexpr int CW = CO / 2;
+    // ===================== mid group: Z^T fp32 -> bf16 pairs, in place (16 columns -> the first 8 of the same 16) =====================
+    // Warp (lane group, half) takes the 16-column groups half, half + 2, half + 4 (N <= 96: at most three).
     const int lane_grp = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int r = lane_grp * 32 + lane;
     const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
-    const bool rows_used = lane_grp * 32 < ksteps * 16;                  // the aggregation never reads Z rows past its K-steps
-    int d = 0; uint32_t dpar = 0;
     for (int t = 0; t < my_tiles; ++t) {
-      uint8_t* zs = s_zs + (size_t)d * (KC2 * kGfTile);
-      mbar_wait(&da_full[d], dpar);
+      const int s = t & 1;
+      const uint32_t col = tmem_z + lane_off + (uint32_t)(s * kGwAcc + 16 * half);
+      mbar_wait(&da_full[s], (uint32_t)((t >> 1) & 1));
       tc_fence_after();
-      uint32_t a[CW];
-      if (rows_used) {
+      uint32_t a[3][16];
 #pragma unroll
-        for (int i = 0; i < CW / 16; ++i) tmem_ld16(tmem_d + lane_off + (uint32_t)(d * CO + half * CW + 16 * i), a + 16 * i);
-        tmem_ld_wait();
-      }
-      mbar_wait(&zs_free[d], dpar ^ 1);                                    // the store of tile t-3 has read this tile
-      if (rows_used) {
+      for (int i = 0; i < 3; ++i)
+        if (half + 2 * i < n_groups) tmem_ld16(col + 32 * i, a[i]);
+      tmem_ld_wait();
 #pragma unroll
-      for (int q = 0; q < CW / 8; ++q) {
-        uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(a[8 * q + 0]), __uint_as_float(a[8 * q + 1]));
-        u.y = pack_bf16x2(__uint_as_float(a[8 * q + 2]), __uint_as_float(a[8 * q + 3]));
-        u.z = pack_bf16x2(__uint_as_float(a[8 * q + 4]), __uint_as_float(a[8 * q + 5]));
-        u.w = pack_bf16x2(__uint_as_float(a[8 * q + 6]), __uint_as_float(a[8 * q + 7]));
-        const int col = half * CW + 8 * q;
-        const int j = (col & 63) >> 3;
-        *reinterpret_cast<uint4*>(zs + (size_t)(col >> 6) * kGfTile + (size_t)r * 128 + ((j ^ (r & 7)) << 4)) = u;
-      }
-      fence_proxy_async_smem();
-      }
+      for (int i = 0; i < 3; ++i)
+        if (half + 2 * i < n_groups) {
+          uint32_t w8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) w8[e] = pack_bf16x2(__uint_as_float(a[i][2 * e]), __uint_as_float(a[i][2 * e + 1]));
+          tmem_st8(col + 32 * i, w8);
+        }
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&z_full[d]);
-      if (++d == ND) { d = 0; dpar ^= 1; }
+      if (lane == 0) mbar_arrive(&z_full[s]);
     }
   } else {
-    // ===================== final group: D + bias -> ReLU -> bf16 -> the tile's shared-memory slot -> TMA store =====================
-    constexpr int CW = CO / 2;
+    // ===================== final group: D^T + bias -> ReLU -> bf16 -> transposed staging -> TMA store =====================
     const int lane_grp = warp & 3;
     const int half = (warp - 2 - kGfGroupWarps) >> 2;
-    const int r = lane_grp * 32 + lane;
-    const int node = r / p.ttg;
-    const float* bias = s_bias + (node < p.V ? node : 0) * (CO + 4) + half * CW;
+    const int c = lane_grp * 32 + lane;                // this thread's output channel (within the CTA's 128)
     const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
     const bool issuer = threadIdx.x == 32 * (2 + kGfGroupWarps);
-    const bool rows_used = lane_grp * 32 < rows_valid;                   // warps whose 32 rows are all padding only keep the barriers
-    int d = 0, d_prev = 0; uint32_t dpar = 0;
+    // Row n of a tile is always the same node, and this thread always the same channel: its bias values live in registers.
+    float bias_r[3][16];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int row = 16 * (half + 2 * i) + j;
+        bias_r[i][j] = row < rows_valid ? s_bias[(row / p.ttg) * CO + c] : 0.f;
+      }
+    // staging address of (row n, channel c): slab c/64, 128-byte rows, 16-byte chunks XOR-swizzled with the row (n & 7 = j & 7).
+    // Slabs have 16 * n_groups rows, so every row of a group is stored without a bounds test (the TMA store reads the valid
+    // ones); the eight swizzle variants are base registers, (group, row) is an immediate offset of the store.
+    const bool relu = p.relu != 0;
+    const uint32_t sslab = (uint32_t)n_groups * 2048u;
+    const uint32_t c_off = smem_u32(s_stage) + (uint32_t)(c >> 6) * sslab + (uint32_t)(c & 7) * 2u + (uint32_t)(16 * half) * 128u;
+    const uint32_t c_chunk = (uint32_t)((c & 63) >> 3);
     for (int t = 0; t < my_tiles; ++t) {
       int n, t0;
       tile_of(t, n, t0);
-      uint8_t* stage = s_zs + (size_t)d * (KC2 * kGfTile);
-      mbar_wait(&db_full[d], dpar);                                        // also: the aggregation MMA has consumed Z(t)
-      tc_fence_after();
-      uint32_t a[CW];
-      if (rows_used) {
+      const int s = t & 1;
+      uint8_t* stage = s_stage + (size_t)s * (2 * sslab);
+      uint32_t base8[8];
 #pragma unroll
-        for (int i = 0; i < CW / 16; ++i) tmem_ld16(tmem_d + lane_off + (uint32_t)(d * CO + half * CW + 16 * i), a + 16 * i);
-        tmem_ld_wait();
-      }
+      for (int m = 0; m < 8; ++m) base8[m] = c_off + (uint32_t)s * (2u * sslab) + ((c_chunk ^ (uint32_t)m) << 4);
+      if (issuer) tma_store_wait_read1();              // the store of tile t-2 has read this staging tile
+      mbar_wait(&d2_full[s], (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+      const uint32_t col = tmem_d2 + lane_off + (uint32_t)(s * kGwAcc + 16 * half);
+      named_bar_sync(1, 32 * kGfGroupWarps);           // the issuer has passed its wait: the staging tile is free
+#pragma unroll
+      for (int i = 0; i < 3; ++i)                      // one 16-row group at a time: 48 bias registers leave room for 16 accumulators
+        if (half + 2 * i < n_groups) {
+          uint32_t a[16];
+          tmem_ld16(col + 32 * i, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float v = __uint_as_float(a[j]) + bias_r[i][j];
+            v = relu ? fmaxf(v, 0.f) : v;
+            const uint16_t h16 = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(base8[j & 7] + (uint32_t)((32 * i + j) * 128)), "h"(h16) : "memory");
+          }
+        }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&d_empty[d]);
-      if (issuer && t > 0) {                                               // the previous tile's store (issued a whole pass ago) has read its tile
-        tma_store_wait_read0();
-        mbar_arrive(&zs_free[d_prev]);
-      }
-      if (rows_used) {
-#pragma unroll
-      for (int q = 0; q < CW / 8; ++q) {
-        const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * q);
-        const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * q + 4);
-        const float v0 = __uint_as_float(a[8 * q + 0]) + b0.x, v1 = __uint_as_float(a[8 * q + 1]) + b0.y;
-        const float v2 = __uint_as_float(a[8 * q + 2]) + b0.z, v3 = __uint_as_float(a[8 * q + 3]) + b0.w;
-        const float v4 = __uint_as_float(a[8 * q + 4]) + b1.x, v5 = __uint_as_float(a[8 * q + 5]) + b1.y;
-        const float v6 = __uint_as_float(a[8 * q + 6]) + b1.z, v7 = __uint_as_float(a[8 * q + 7]) + b1.w;
-        uint4 u;
-        if (p.relu) { u.x = pack_bf16x2_relu(v0, v1); u.y = pack_bf16x2_relu(v2, v3); u.z = pack_bf16x2_relu(v4, v5); u.w = pack_bf16x2_relu(v6, v7); }
-        else { u.x = pack_bf16x2(v0, v1); u.y = pack_bf16x2(v2, v3); u.z = pack_bf16x2(v4, v5); u.w = pack_bf16x2(v6, v7); }
-        const int col = half * CW + 8 * q;
-        const int j = (col & 63) >> 3;
-        *reinterpret_cast<uint4*>(stage + (size_t)(col >> 6) * kGfTile + (size_t)r * 128 + ((j ^ (r & 7)) << 4)) = u;
-      }
+      if (lane == 0) mbar_arrive(&d2_empty[s]);        // the accumulator has been read
       fence_proxy_async_smem();
-      }
       named_bar_sync(2, 32 * kGfGroupWarps);
       if (issuer) {
-        for (int c = 0; c < KC2; ++c) tma_store_4d(&p.map_out, stage + (size_t)c * kGfTile, half_out * CO + c * 64, t0, 0, n);
+        for (int h = 0; h < 2; ++h) tma_store_4d(&p.map_out, stage + (size_t)h * sslab, half_out * CO + h * 64, t0, 0, n);
         tma_store_commit();
       }
-      d_prev = d;
-      if (++d == ND) { d = 0; dpar ^= 1; }
     }
     if (issuer) tma_store_wait0();
   }
@@ -878,6 +871,12 @@ int gcn_fused_frames(int T) {
   const int tiles = (T + 6) / 7;
   return (T + tiles - 1) / tiles;
 }
+// the 256-channel kernel keeps tile rows on the accumulator columns: at most 5 frames (85 rows -> N = 96)
+int gcn_fused_frames(int T, int cin) {
+  if (cin != 256) return gcn_fused_frames(T);
+  const int tiles = (T + 4) / 5;
+  return (T + tiles - 1) / tiles;
+}
 
 bool gcn_fused_supported(int cin, int cout, int V, int K) {
   if (K != 1 || V * 7 > 128 || V < 1) return false;
@@ -896,7 +895,7 @@ int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float
   memset(&p, 0, sizeof(p));
   g->cin = cin; g->cout = cout;
   p.n_clips = (int32_t)n_clips; p.T = T; p.V = V;
-  p.ttg = gcn_fused_frames(T);
+  p.ttg = gcn_fused_frames(T, cin);
   p.tiles_t = (T + p.ttg - 1) / p.ttg;
   p.bias = bias; p.relu = relu; p.abd = reinterpret_cast<const __nv_bfloat16*>(abd);
   int rc = TIK_OK;
@@ -912,28 +911,34 @@ int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float
     uint32_t box[4] = {64, (uint32_t)p.ttg, (uint32_t)V, 1};
     rc = encode_bf16_map(&p.map_out, out, 4, dims, strides, box);
   }
-  if (rc == TIK_OK) {
+  if (rc == TIK_OK && cin == 256) {                        // wide kernel: weights go to tensor memory, the 2-D map fetches Abd
+    uint64_t dims[2] = {128, 128};
+    uint64_t strides[1] = {128 * 2};
+    uint32_t box[2] = {64, 128};
+    rc = encode_bf16_map(&p.map_w, abd, 2, dims, strides, box);
+    p.w = reinterpret_cast<const __nv_bfloat16*>(w);
+  } else if (rc == TIK_OK) {
     uint64_t dims[2] = {(uint64_t)cin, (uint64_t)cout};
     uint64_t strides[1] = {(uint64_t)cin * 2};
-    uint32_t box[2] = {64, (uint32_t)(cin == 256 ? kGwCo : cout)};
+    uint32_t box[2] = {64, (uint32_t)cout};
     rc = encode_bf16_map(&p.map_w, w, 2, dims, strides, box);
   }
   if (rc != TIK_OK) { delete g; return rc; }
   g->wide = cin == 256;
   if (g->wide) {
-    // W slice 64 KB + three Z / staging tiles 96 KB + bias; the rest is the ring of input slabs
+    // Abd 32 KB + two staging tiles of two slabs + bias [node][128]; the rest is the ring of input slabs
     p.halves = cout / kGwCo;
-    const int w_bytes = (cin / 64) * kGwCo * 128;
-    const int bias_bytes = (V * (kGwCo + 4) * 4 + 1023) / 1024 * 1024;
-    p.sbufs = 3;                           // Z / staging tiles (NZ in the kernel)
+    const int bias_bytes = (V * kGwCo * 4 + 1023) / 1024 * 1024;
+    p.sbufs = 2;
     p.xslab = (p.ttg * V + 7) / 8 * 1024;
-    const int fixed = w_bytes + p.sbufs * (kGwCo / 64) * kGfTile + bias_bytes + 512;
+    const int sslab = (p.ttg * V + 15) / 16 * 2048;        // staging slab: rows rounded up to the 16-row groups
+    const int fixed = 2 * kGfTile + 4 * sslab + bias_bytes + 512;
     p.xbufs = std::min((kGfSmemBudget - fixed) / p.xslab, kGwMaxBufs);
     if (const char* e = getenv("TIK_GCN_WIDE_XBUFS")) p.xbufs = std::max(1, std::min(p.xbufs, atoi(e)));
-    p.off_w = 0;
-    p.off_x = w_bytes;
+    p.off_w = 0;                           // Abd
+    p.off_x = 2 * kGfTile;
     p.off_stage = p.off_x + p.xbufs * p.xslab;
-    p.off_bias = p.off_stage + p.sbufs * (kGwCo / 64) * kGfTile;
+    p.off_bias = p.off_stage + 4 * sslab;
     p.off_bar = p.off_bias + bias_bytes;
     g->smem_bytes = p.off_bar + 512 + 1024;
     g->pair = false;
@@ -1004,11 +1009,11 @@ static int gf_launch_wide(const GcnFusedPrepared* g, unsigned grid, cudaStream_t
   int dev = 0;
   TIK_CUDA(cudaGetDevice(&dev));
   if (!attr_done[dev & 63]) {
-    TIK_CUDA(cudaFuncSetAttribute(gcn_wide_kernel<4, kGwCo>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGfSmemBudget + 2048));
-    TIK_CUDA(cudaFuncSetAttribute(gcn_wide_kernel<4, kGwCo>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    TIK_CUDA(cudaFuncSetAttribute(gcn_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGfSmemBudget + 2048));
+    TIK_CUDA(cudaFuncSetAttribute(gcn_wide_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_done[dev & 63] = true;
   }
-  TIK_CUDA(launch_pdl(gcn_wide_kernel<4, kGwCo>, grid, kGfThreads, (size_t)g->smem_bytes, s, g->p));
+  TIK_CUDA(launch_pdl(gcn_wide_kernel<4>, grid, kGfThreads, (size_t)g->smem_bytes, s, g->p));
   return TIK_OK;
 }
 

@@ -307,7 +307,7 @@ int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int64_t
       P->chunk_steps.push_back(s);
     } else if (dtype == TIK_BF16 && gcn_fused_supported(b.c_in, b.c_out, V, K) && !getenv("TIK_NO_FUSED_GCN")) {
       // aggregation + channel GEMM in one kernel: build the block-structured bf16 operand Abd in the workspace
-      const int f = gcn_fused_frames(t);
+      const int f = gcn_fused_frames(t, b.c_in);
       std::vector<float> a_host((size_t)V * V);
       cudaError_t ce = cudaMemcpy(a_host.data(), b.agg_dev, a_host.size() * sizeof(float), cudaMemcpyDeviceToHost);
       std::vector<__nv_bfloat16> abd_host(128 * 128, __float2bfloat16_rn(0.f));

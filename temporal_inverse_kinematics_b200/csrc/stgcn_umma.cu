@@ -73,6 +73,7 @@ struct UmmaParams {
   void* out; int32_t out_layout;
   int32_t ts;                      // weights stationary in tensor memory (rowgemm_ts_kernel)
   int32_t two_cta;                 // CTA pairs sharing one weight stream (rowgemm_umma2_kernel)
+  int32_t mc;                      // clusters of two CTAs multicasting the weight stream (rowgemm_umma_mc_kernel)
   const __nv_bfloat16* w_gmem;     // ts: (c_out, ktot) row-major weights
   int32_t ktot;
   unsigned long long* dbg_times;   // probe hook: clock64 timeline of CTA 0 (tools/umma_probe.py)
@@ -95,8 +96,15 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
 #define TIK_PROBE_ONLY(x) false
 #endif
 
-template <int BN, int ACT>
-__global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __grid_constant__ UmmaParams p) {
+// CL = CTAs per cluster.  CL = 2 (rowgemm_umma_mc_kernel, BN = 256 with streamed weights): the two CTAs of a cluster work
+// on two row tiles of the SAME column tile in lock step and share one weight stream -- each loads half of every W chunk
+// and TMA-multicasts it into both CTAs' ring slots, so the L2 -> SM weight traffic halves (the 256-channel temporal convs and
+// the first head layer re-stream 0.5-2.2 MB of weights per tile: 3.0 GB in 268 us for the b6 temporal conv = 11 TB/s).
+// Opt-in experiment (TIK_MC=1): it turned out NOT to be the limiter, see umma_prepare.  A ring slot is free when BOTH CTAs'
+// MMAs have read it: tcgen05.commit multicasts its
+// arrival to both empty barriers (count CL).  An odd last row tile is computed (and stored, identically) by both CTAs.
+template <int BN, int ACT, int CL>
+__device__ __forceinline__ void rowgemm_umma_body(const UmmaParams& p) {
   constexpr int kBBytes = BN * kChunkK * 2;
   if (threadIdx.x == 0) TIK_T(0);
   extern __shared__ uint8_t smem_raw[];
@@ -119,6 +127,18 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
   const int chunk_bytes = kABytes + (p.w_resident ? 0 : kBBytes);
   const int stage_bytes = p.group * chunk_bytes;
   const int64_t num_tiles = p.tiles_m * p.n_tiles_n;
+  // work items: tiles (CL = 1), or groups of CL row tiles of one column tile, one per CTA of the cluster
+  const int cl_rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int g0 = CL > 1 ? (int)blockIdx.x / CL : (int)blockIdx.x, gstep = CL > 1 ? (int)gridDim.x / CL : (int)gridDim.x;
+  const int n_items = CL > 1 ? (int)(((p.tiles_m + CL - 1) / CL) * p.n_tiles_n) : (int)num_tiles;
+  auto tile_of = [&](int g) -> int {
+    if (CL == 1) return g;
+    const int tn = g % p.n_tiles_n;
+    int64_t tm = (int64_t)(g / p.n_tiles_n) * CL + cl_rank;
+    if (tm >= p.tiles_m) tm = p.tiles_m - 1;              // odd tail: the same tile twice (identical stores)
+    return (int)(tm * p.n_tiles_n + tn);
+  };
+  constexpr uint16_t kClMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.n_slabs; ++s) tma_prefetch_desc(&p.map_a[s]);
@@ -126,7 +146,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
     if (p.tma_store) tma_prefetch_desc(&p.map_out);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&stage_full[i], kEpiWarps); mbar_init(&stage_empty[i], 1); }
@@ -138,6 +158,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (CL > 1) cluster_sync_all();                           // the peer's barriers are initialised before anyone signals them
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();                                  // the next kernel may begin its own prologue
   pdl_wait();                                               // everything below reads what the previous kernel wrote
@@ -156,7 +177,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
     const bool skip_a = (p.dbg_flags & 8) != 0;
     const int group = p.group, total_chunks = p.total_chunks;
     int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < (int)num_tiles; tile += gridDim.x) {
+    for (int g = g0; g < n_items; g += gstep) {
+      const int tile = tile_of(g);
       const int tm = tile / p.n_tiles_n;
       const int n0 = (tile - tm * p.n_tiles_n) * BN;
       const int tile_nv = tm / p.tiles_t;
@@ -181,7 +203,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
           uint8_t* sa = ring + (size_t)stage * stage_bytes + (size_t)j * chunk_bytes;
           if (leader) {
             if (!skip_a) tma_load_3d(sa, &p.map_a[s], &full_bar[stage], c * kChunkK, ts, nv0);
-            if (!p.w_resident) tma_load_2d(sa + kABytes, &p.map_w, &full_bar[stage], kw * kChunkK, n0);
+            if (!p.w_resident) {
+              if (CL > 1) tma_load_2d_mc(sa + kABytes + cl_rank * (kBBytes / CL), &p.map_w, &full_bar[stage], kw * kChunkK, n0 + cl_rank * (BN / CL), kClMask);
+              else tma_load_2d(sa + kABytes, &p.map_w, &full_bar[stage], kw * kChunkK, n0);
+            }
           }
           if (p3) TIK_T(27);
           __syncwarp();
@@ -207,7 +232,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     const int total_chunks = p.total_chunks, group = p.group;
-    for (int tile = blockIdx.x; tile < (int)num_tiles; tile += gridDim.x) {
+    for (int g = g0; g < n_items; g += gstep) {
+      const int tile = tile_of(g);
       const bool m3 = TIK_PROBE_ONLY(leader && tile == (int)blockIdx.x + 3 * (int)gridDim.x);
       if (m3) TIK_T(16);
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);        // epilogue has drained this accumulator
@@ -241,7 +267,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
         }
         if (leader) {
           if (m3 && kc < 2 * group) TIK_T(19 + 3 * (kc / group));
-          umma_commit(&empty_bar[stage]);                  // frees this ring slot once the MMAs have read it
+          if (CL > 1) umma_commit_mc(&empty_bar[stage], kClMask); else umma_commit(&empty_bar[stage]);   // frees this ring slot (in every CTA of the cluster) once the MMAs have read it
           if (m3 && kc < 2 * group) TIK_T(20 + 3 * (kc / group));
         }
         __syncwarp();
@@ -262,7 +288,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
       const int ntn = p.n_tiles_n, tiles_t = p.tiles_t;
       int sbuf = 0; uint32_t sphase = 0;
       int prev = -1;
-      for (int tile = blockIdx.x; tile < (int)num_tiles; tile += gridDim.x) {
+      for (int g = g0; g < n_items; g += gstep) {
+      const int tile = tile_of(g);
         const int tm = tile / ntn;
         const int n0 = (tile - tm * ntn) * BN;
         const int tile_nv = tm / tiles_t, tile_t = tm - tile_nv * tiles_t;
@@ -293,10 +320,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
     const int nv_l = r / p.tt, t_l = r - nv_l * p.tt;
     const bool use_res = p.res_kind == TIK_RES_IDENTITY && !(p.dbg_flags & 2);
     const int ntn = p.n_tiles_n, tiles_t = p.tiles_t;
-    const int n_tiles = (int)num_tiles;
     int acc = 0; uint32_t acc_phase = 0;
     int sbuf = 0; uint32_t sphase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int g = g0; g < n_items; g += gstep) {
+      const int tile = tile_of(g);
       const int tm = tile / ntn;
       const int n0 = (tile - tm * ntn) * BN;
       const int tile_nv = tm / tiles_t, tile_t = tm - tile_nv * tiles_t;
@@ -401,6 +428,16 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __g
     tmem_dealloc<2 * BN>(tmem_base);
   }
   if (threadIdx.x == 64) TIK_T(10);
+  if (CL > 1) cluster_sync_all();                           // no CTA leaves while its peer may still multicast into its ring / signal its barriers
+}
+
+template <int BN, int ACT>
+__global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_kernel(const __grid_constant__ UmmaParams p) {
+  rowgemm_umma_body<BN, ACT, 1>(p);
+}
+template <int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1) rowgemm_umma_mc_kernel(const __grid_constant__ UmmaParams p) {
+  rowgemm_umma_body<256, ACT, 2>(p);
 }
 
 // ------------------------------------------------------------------------------------------------ CTA-pair variant (cta_group::2)
@@ -989,6 +1026,30 @@ static int launch_variant(const UmmaParams& p, int smem_bytes, unsigned grid, cu
   return TIK_OK;
 }
 
+// Clusters of two: the grid is sized by how many clusters the device can hold at once (a second wave would double the time
+// of a persistent kernel), queried once per device.
+template <int ACT>
+static int launch_mc(const UmmaParams& p, int smem_bytes, cudaStream_t s) {
+  static int clusters[64] = {};
+  int dev = 0;
+  TIK_CUDA(cudaGetDevice(&dev));
+  if (!clusters[dev & 63]) {
+    TIK_CUDA(cudaFuncSetAttribute(rowgemm_umma_mc_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048));
+    TIK_CUDA(cudaFuncSetAttribute(rowgemm_umma_mc_kernel<ACT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (num_sms() / 2), 1, 1);
+    cfg.blockDim = dim3(kUmmaThreads, 1, 1);
+    cfg.dynamicSmemBytes = kSmemBudget + 2048;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, rowgemm_umma_mc_kernel<ACT>, &cfg) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = num_sms() / 2; }
+    clusters[dev & 63] = std::min(n, num_sms() / 2);
+  }
+  const int64_t items = ((p.tiles_m + 1) / 2) * p.n_tiles_n;
+  const unsigned grid = 2u * (unsigned)std::min<int64_t>(items, clusters[dev & 63]);
+  TIK_CUDA(launch_pdl(rowgemm_umma_mc_kernel<ACT>, grid, kUmmaThreads, (size_t)smem_bytes, s, p));
+  return TIK_OK;
+}
+
 int umma_prepare(const TikRowGemm* d, int64_t nv_capacity, UmmaPrepared** out) {
   TIK_CHECK_ARG(d->c_out % 64 == 0, "bf16 path: c_out=%d must be a multiple of 64", d->c_out);
   TIK_CHECK_ARG(nv_capacity >= d->nv && nv_capacity > 0, "nv capacity");
@@ -1117,6 +1178,21 @@ int umma_prepare(const TikRowGemm* d, int64_t nv_capacity, UmmaPrepared** out) {
     int rc = encode_map(&p.map_w, d->w_dev, 2, dims, strides, box, estr);
     if (rc != TIK_OK) { delete u; return rc; }
   }
+  // Streamed 256-column weights: clusters of two CTAs share the stream (TMA multicast), see rowgemm_umma_body.
+  // EXPERIMENT, opt-in (TIK_MC=1): parity-green, and slower on one box in an A/B (tools/ab_trace.sh): b6 temporal conv
+  // 293 vs 270 us, b7 154 -> 161, head 85 -> 90.  Halving the L2 -> SM weight traffic does not help because these
+  // launches are bound by SHARED-MEMORY bandwidth, not L2: every operand byte is written once by TMA and read once by
+  // the SS-mode MMA -- per 64-wide K chunk 48 KB in + 48 KB out against 512 tensor cycles = 188 B/clk wanted, 128 B/clk
+  // available, i.e. at most 68 % tensor-pipe activity before the epilogue's own traffic (measured: 48-61 %).
+  p.mc = (!p.ts && !p.two_cta && u->bn == 256 && !w_res && getenv("TIK_MC")) ? 1 : 0;
+  if (p.mc) {
+    uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d->c_out};
+    uint64_t strides[1] = {(uint64_t)ktot * 2};
+    uint32_t box[2] = {(uint32_t)kChunkK, (uint32_t)(u->bn / 2)};
+    uint32_t estr[2] = {1, 1};
+    int rc = encode_map(&p.map_w, d->w_dev, 2, dims, strides, box, estr);
+    if (rc != TIK_OK) { delete u; return rc; }
+  }
   p.group = group;
   p.stage_bufs = sbufs;
   const int stage_out_bytes = sbufs * one_stage_tile;
@@ -1185,6 +1261,11 @@ int umma_launch(UmmaPrepared* u, const TikRowGemm* d, cudaStream_t s) {
     else rowgemm_umma2_kernel<TIK_ACT_NONE><<<grid2, kUmmaThreads, u->smem_bytes, s>>>(p);
     TIK_LAUNCH_CHECK();
     return TIK_OK;
+  }
+  if (p.mc) {
+    if (d->act == TIK_ACT_RELU) return launch_mc<TIK_ACT_RELU>(p, u->smem_bytes, s);
+    if (d->act == TIK_ACT_LEAKY) return launch_mc<TIK_ACT_LEAKY>(p, u->smem_bytes, s);
+    return launch_mc<TIK_ACT_NONE>(p, u->smem_bytes, s);
   }
   if (p.ts) {
     static int ts_attr[64] = {};

@@ -16,6 +16,7 @@ void umma_free(UmmaPrepared* u);
 struct GcnFusedPrepared;
 bool gcn_fused_supported(int cin, int cout, int V, int K);
 int gcn_fused_frames(int T);          // frames per tile = the block size of the Abd operand
+int gcn_fused_frames(int T, int cin); // same; the 256-channel kernel holds at most 5 frames per tile
 int gcn_fused_prepare(const void* x, const void* abd, const void* w, const float* bias, void* out, int64_t n_clips, int T, int V,
                       int cin, int cout, int relu, GcnFusedPrepared** outp, int x_row = 0, int out_row = 0);
 int gcn_fused_launch(GcnFusedPrepared* g, int64_t n_clips, cudaStream_t s);

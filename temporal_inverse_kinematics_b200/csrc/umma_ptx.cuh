@@ -109,6 +109,49 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-collective forms: the WHOLE warp executes them with warp-uniform operands and one elected lane issues.  Inside
+// an `if (lane == 0)` branch the compiler cannot prove the operands uniform and wraps every tcgen05 instruction in a
+// uniformisation loop (R2UR + ELECT + BRA.U.ANY, ~8 instructions per MMA); here the election is inside the asm and the
+// descriptor arithmetic stays on the uniform datapath.  Used by gcn_wide_kernel, whose N <= 96 MMAs (<= 48 tensor cycles)
+// are issue-bound otherwise (176 -> 131 us).  A/B on one box (tools/ab_trace.sh): the kernels with N >= 128 MMAs do NOT
+// gain from it -- stem block +1 %, 64-channel temporal conv and gcn<64,128> +3 % slower -- and keep the leader branch.
+#ifdef TIK_ISSUE_LEADER   // A/B build: lane 0 issues under a branch (what every kernel did before)
+__device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if ((threadIdx.x & 31) == 0) umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+  __syncwarp();
+}
+__device__ __forceinline__ void umma_bf16_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if ((threadIdx.x & 31) == 0) umma_bf16_ts(tmem_d, tmem_a, desc_b, idesc, accumulate);
+  __syncwarp();
+}
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar);
+#else
+__device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)) : "memory");
+}
+#endif
 // registers -> tensor memory: 8 consecutive 32-bit columns of this thread's lane
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -120,6 +163,12 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifdef TIK_ISSUE_LEADER
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
+  if ((threadIdx.x & 31) == 0) umma_commit(bar);
+  __syncwarp();
+}
+#endif
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -230,6 +279,19 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA multicast: the box lands at the same shared-memory offset in every CTA of `mask`, and the bytes are counted on the
+// barrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// arrive on the barrier at this offset in every CTA of `mask` once the MMAs issued so far by this thread are done
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 // TMA loads of a CTA pair: the data lands in THIS CTA's shared memory, the bytes are counted on a barrier that may
 // live in the peer (shared::cluster address)

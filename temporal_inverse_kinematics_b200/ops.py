@@ -63,11 +63,13 @@ def stem_gcn(x, in_scale, in_shift, A_hat, w, bias, out_dtype, relu=True, res_w=
     return out if res_w is None else (out, res)
 
 
-def build_abd(A_hat, T):
+def build_abd(A_hat, T, cin=None):
     """(128,128) bf16 block-structured aggregation operand of the fused graph conv: rows (w, t), columns (v, t'),
-    entry A_hat[v, w] * (t == t'), f = ceil(T / ceil(T/7)) frames per tile (tik.h), zero padding."""
+    entry A_hat[v, w] * (t == t'), f = ceil(T / ceil(T/7)) frames per tile (tik.h; at most 5 frames for the 256-channel
+    kernel: f = ceil(T / ceil(T/5))), zero padding."""
     V = A_hat.shape[-1]
-    tiles = (int(T) + 6) // 7
+    fmax = 5 if cin == 256 else 7
+    tiles = (int(T) + fmax - 1) // fmax
     f = (int(T) + tiles - 1) // tiles
     a = A_hat.reshape(V, V).float()
     abd = torch.zeros(128, 128, dtype=torch.float32, device=A_hat.device)

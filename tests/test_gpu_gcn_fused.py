@@ -1,6 +1,6 @@
 """tik_gcn_fused (aggregation + channel GEMM + bias + ReLU in one tensor-core kernel) against a torch emulation that
 rounds where the kernel rounds (bf16 adjacency, bf16 aggregate, fp32 accumulate), for every (Cin, Cout) variant --
-including the 256 -> 256 kernel that streams 64-channel quarters and splits the output channels over two CTAs."""
+including the transposed 256 -> 256 kernel (weights in tensor memory, output channels split over two CTAs)."""
 import numpy as np
 import pytest
 import torch
@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
     (150, 64, 64, 128),
     (3, 8, 256, 256),        # one wave, 4-frame tiles (the last block at T = 64)
     (1, 1, 256, 256),        # a single frame
-    (2, 13, 256, 256),       # 7 + shifted 7 frames: overlapping last tile
+    (2, 13, 256, 256),       # 5 + 5 + shifted 5 frames: overlapping last tile
+    (3, 32, 256, 256),       # 5-frame tiles: 85 rows, N = 96 (the widest accumulator)
     (5, 16, 256, 256),       # the last block at T = 128
     (310, 8, 256, 256),      # 620 tiles x 2 halves over 148 CTAs: every ring / accumulator parity, ragged tail
 ])
@@ -25,7 +26,7 @@ def test_gcn_fused_matches_emulation(n, t, cin, cout):
     A = (torch.rand(1, V, V, generator=g) * (torch.rand(1, V, V, generator=g) > 0.6)).float()
     w = (torch.randn(cout, cin, generator=g) / np.sqrt(cin)).bfloat16()
     b = torch.randn(V, cout, generator=g)
-    y = ops.gcn_fused(x.cuda(), ops.build_abd(A, t).cuda(), w.cuda(), b.cuda())
+    y = ops.gcn_fused(x.cuda(), ops.build_abd(A, t, cin).cuda(), w.cuda(), b.cuda())
     torch.cuda.synchronize()
     Ab = A[0].bfloat16().float()
     if cin == 256:           # channel GEMM first, its result rounded to bf16, then the aggregation

@@ -225,11 +225,13 @@ def test_bf16_forward_windows_equals_materialised_windows(win, offset, stride):
     assert float((got.cpu() - ref).abs().max()) < TOL_BF16_ABS
 
 
-@pytest.mark.parametrize("switch", ["TIK_NO_STEM_BLOCK", "TIK_NO_TS", "TIK_NO_FUSED_GCN", "TIK_NO_TC_AGG", "TIK_NO_TCN_HALO", "TIK_2CTA"])
+@pytest.mark.parametrize("switch", ["TIK_NO_STEM_BLOCK", "TIK_NO_TS", "TIK_NO_FUSED_GCN", "TIK_NO_TC_AGG", "TIK_NO_TCN_HALO", "TIK_2CTA", "TIK_MC",
+                                    "TIK_NO_GCN_WIDE"])
 def test_bf16_kernel_variants_agree(monkeypatch, switch):
     """Every specialised tensor-core kernel has a more general one behind it (first block: stem + temporal conv;
     halo / weight-stationary temporal conv: per-tap TS kernel, then the SS-mode kernel; fused graph conv: aggregate +
-    channel GEMM; TIK_2CTA switches the experimental cta_group::2 kernel ON for the 256-channel layers).  Both routes must
+    channel GEMM; TIK_2CTA / TIK_MC switch the experimental cta_group::2 and TMA-multicast kernels ON for the 256-channel
+    layers; TIK_NO_GCN_WIDE takes the last block's graph conv back to aggregation launches + channel GEMM).  Both routes must
     meet the stated bf16 tolerance against the oracle and stay close to each other."""
     x = synth.make_clips(6, 40, seed=21)
     m, sd = _model(dtype="bf16")
