@@ -79,7 +79,7 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
-TC_KERNELS = ("rowgemm_umma", "rowgemm_ts", "tcn_halo", "gcn_fused", "stem_block", "block_fused")
+TC_KERNELS = ("rowgemm_umma", "rowgemm_ts", "tcn_halo", "gcn_fused", "gcn_wide", "stem_block", "block_fused")
 
 
 def _ncu_traffic_per_launch():
@@ -662,7 +662,7 @@ def measure(args, dev, world, rank, local):
         achieved = gemm_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
         if dtype == "bf16":
             peak, peak_name = peaks["bf16_tflops"], f"{peak_src} bf16_tflops (burst: cuBLAS 8192^3, best of 10)"
-            kern = "tcgen05 family: rowgemm_umma_kernel / rowgemm_ts_kernel / tcn_halo_kernel / gcn_fused_kernel / stem_block_kernel"
+            kern = "tcgen05 family: rowgemm_umma_kernel / rowgemm_ts_kernel / tcn_halo_kernel / gcn_fused_kernel / gcn_wide_kernel / stem_block_kernel"
         else:
             peak, peak_name = 74.0, "nominal fp32 SIMT: 148 SM x 128 FMA x 2 x 1.965 GHz"
             kern = "rowgemm_f32_kernel"
