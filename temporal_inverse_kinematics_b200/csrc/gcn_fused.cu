@@ -46,6 +46,7 @@ struct GcnFusedParams {
   const float* bias;                      // (V, COUT)
   const __nv_bfloat16* abd;               // (128, 128) row-major block-structured adjacency, copied to tensor memory
   int32_t relu;
+  int32_t rev, l2;                        // LaunchOpts: clips walked last to first; evict-first hint on the X loads
 };
 
 template <int CIN, int COUT>
@@ -134,13 +135,15 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
       mbar_expect_tx(w_full, (uint32_t)(KC1 * COUT * 128));
       for (int kc = 0; kc < KC1; ++kc) tma_load_2d(s_w + (size_t)kc * COUT * 128, &p.map_w, w_full, kc * 64, 0);
       int b = 0; uint32_t phase = 0;
+      const uint64_t pol = p.l2 ? l2_policy_evict_first() : 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int n = tile / p.tiles_t, tt = tile - n * p.tiles_t;
+        const int nf = tile / p.tiles_t, tt = tile - nf * p.tiles_t;
+        const int n = p.rev ? p.n_clips - 1 - nf : nf;
         const int t0 = min(tt * p.ttg, p.T - p.ttg);          // the last tile of a clip is shifted back, never out of range
         mbar_wait(&x_empty[b], phase ^ 1);
         mbar_expect_tx(&x_full[b], x_bytes);
         for (int kc = 0; kc < KC1; ++kc)
-          tma_load_4d(s_x + ((size_t)b * KC1 + kc) * kGfTile, &p.map_x, &x_full[b], kc * 64, t0, 0, n);
+          tma_load_4d(s_x + ((size_t)b * KC1 + kc) * kGfTile, &p.map_x, &x_full[b], kc * 64, t0, 0, n, pol);
         if (++b == p.xbufs) { b = 0; phase ^= 1; }
       }
     }
@@ -254,7 +257,8 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_kernel(const __grid_c
     const bool issuer = threadIdx.x == 32 * (2 + kGfGroupWarps);
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-      const int n = tile / p.tiles_t, tt = tile - n * p.tiles_t;
+      const int nf = tile / p.tiles_t, tt = tile - nf * p.tiles_t;
+      const int n = p.rev ? p.n_clips - 1 - nf : nf;
       const int t0 = min(tt * p.ttg, p.T - p.ttg);
       const int s2 = ND2 == 2 ? (it & 1) : 0;
       uint8_t* stage = s_stage + (size_t)((p.sbufs == 2) ? (it & 1) : 0) * (KC2 * kGfTile);
@@ -397,6 +401,7 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_pair_kernel(const __g
     n = tile / p.tiles_t;
     const int tt = tile - n * p.tiles_t;
     t0 = min(tt * p.ttg, p.T - p.ttg);
+    if (p.rev) n = p.n_clips - 1 - n;
   };
 
   if (warp == 0) {
@@ -405,6 +410,7 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_pair_kernel(const __g
       mbar_expect_tx(w_full, (uint32_t)(COUT * 128));
       tma_load_2d(s_w, &p.map_w, w_full, 0, 0);
       int b = 0; uint32_t phase = 0;
+      const uint64_t pol = p.l2 ? l2_policy_evict_first() : 0;
       for (int it = 0; it < my_pairs; ++it) {
         mbar_wait(&x_empty[b], phase ^ 1);
         mbar_expect_tx(&x_full[b], 2 * x_bytes);
@@ -412,7 +418,7 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_fused_pair_kernel(const __g
         for (int h = 0; h < 2; ++h) {
           int n, t0; bool valid;
           tile_of(it, h, n, t0, valid);
-          tma_load_4d(s_x + ((size_t)b * 2 + h) * kGfTile, &p.map_x, &x_full[b], 0, t0, 0, n);
+          tma_load_4d(s_x + ((size_t)b * 2 + h) * kGfTile, &p.map_x, &x_full[b], 0, t0, 0, n, pol);
         }
         if (++b == p.xbufs) { b = 0; phase ^= 1; }
       }
@@ -667,6 +673,7 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_wide_kernel(const __grid_co
     const int tile = first_tile + it * tile_step;
     n = tile / p.tiles_t;
     t0 = min((tile - n * p.tiles_t) * p.ttg, p.T - p.ttg);
+    if (p.rev) n = p.n_clips - 1 - n;
   };
 
   if (warp == 0) {
@@ -676,13 +683,14 @@ __global__ void __launch_bounds__(kGfThreads, 1) gcn_wide_kernel(const __grid_co
       tma_load_2d(s_abd, &p.map_w, abd_full, 0, 0);
       tma_load_2d(s_abd + kGfTile, &p.map_w, abd_full, 64, 0);
       int b = 0; uint32_t phase = 0;
+      const uint64_t pol = p.l2 ? l2_policy_evict_first() : 0;
       for (int it = 0; it < my_tiles; ++it) {
         int n, t0;
         tile_of(it, n, t0);
         for (int q = 0; q < NQ; ++q) {
           mbar_wait(&x_empty[b], phase ^ 1);
           mbar_expect_tx(&x_full[b], x_bytes);
-          tma_load_4d(s_x + (size_t)b * p.xslab, &p.map_x, &x_full[b], q * 64, t0, 0, n);
+          tma_load_4d(s_x + (size_t)b * p.xslab, &p.map_x, &x_full[b], q * 64, t0, 0, n, pol);
           if (++b == p.xbufs) { b = 0; phase ^= 1; }
         }
       }
@@ -1024,6 +1032,7 @@ int gcn_fused_launch(GcnFusedPrepared* g, int64_t n_clips, cudaStream_t s) {
   TIK_CHECK_ARG(n_clips <= cap, "fused gcn: n_clips exceeds the prepared capacity");
   const int32_t saved = p.n_clips;
   p.n_clips = (int32_t)n_clips;            // tiles only over the valid clips (tensor maps keep the full capacity)
+  p.rev = launch_opts().rev; p.l2 = launch_opts().l2;
   int sms = 148;
   { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int64_t tiles = n_clips * p.tiles_t;

@@ -25,6 +25,25 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+LaunchOpts& launch_opts() {
+  static thread_local LaunchOpts o = {0, 0};
+  return o;
+}
+// Serpentine tile order + evict-first activation loads (tik_common.cuh LaunchOpts): TIK_SERPENTINE / TIK_L2_HINT = 0 | 1.
+// Measured on one box, three alternating rounds (tools/ab_env.sh, profiles/r2_ab_serpentine.log), sum of the 17 network
+// launches of a configs[2] step: serpentine 3653-3658 us vs 3672-3700 us (on by default); the evict-first hint costs
+// 3-4 % (3755-3816 us: it also evicts tiles that a second CTA is about to read) and stays off.
+static int serpentine_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TIK_SERPENTINE"); v = e ? atoi(e) : 1; }
+  return v;
+}
+static int l2_hint_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TIK_L2_HINT"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -191,23 +210,32 @@ static int run_impl(TikPlan* P, const float* x, int64_t N, float* poses, void* f
     if (st) trace->push_back({st, n});
     return TIK_OK;
   };
+  const int serp = serpentine_enabled(), l2 = l2_hint_enabled();
   for (int64_t b0 = 0; b0 < N; b0 += P->n_max) {
     const int64_t nb = std::min<int64_t>(P->n_max, N - b0);
     for (int64_t n0 = 0; n0 < nb; n0 += P->n_chunk) {
       const int64_t n = std::min<int64_t>(P->n_chunk, nb - n0);
       const float* xc = win ? x : x + (b0 + n0) * (int64_t)T * V * net.c_in;   // window mode: x is the whole sequence
+      int k = 0;
       for (auto& st : P->chunk_steps) {
         int rc = mark(&st, n);
         if (rc != TIK_OK) return rc;
+        launch_opts() = {serp ? (k & 1) : 0, l2};          // consecutive kernels walk the clips in opposite directions
         rc = run_step(P, st, xc, n, n0, nullptr, s, win, b0 + n0);
+        launch_opts() = {0, 0};
         if (rc != TIK_OK) return rc;
+        ++k;
       }
     }
+    int k = (int)P->chunk_steps.size();
     for (auto& st : P->batch_steps) {
       int rc = mark(&st, nb);
       if (rc != TIK_OK) return rc;
+      launch_opts() = {serp && nb <= P->n_chunk ? (k & 1) : 0, l2};   // several chunks: the features were not written in one sweep
       rc = run_step(P, st, nullptr, nb, 0, poses ? poses + b0 * (int64_t)P->T_out * net.head_out : nullptr, s);
+      launch_opts() = {0, 0};
       if (rc != TIK_OK) return rc;
+      ++k;
     }
     if (feat_out) {
       TIK_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(feat_out) + b0 * P->feat_elems_per_clip * (int64_t)P->es, P->feat,

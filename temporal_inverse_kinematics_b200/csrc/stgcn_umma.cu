@@ -76,6 +76,7 @@ struct UmmaParams {
   int32_t mc;                      // clusters of two CTAs multicasting the weight stream (rowgemm_umma_mc_kernel)
   const __nv_bfloat16* w_gmem;     // ts: (c_out, ktot) row-major weights
   int32_t ktot;
+  int32_t rev, l2;                 // LaunchOpts: tiles walked last to first; evict-first hint on the activation loads
   unsigned long long* dbg_times;   // probe hook: clock64 timeline of CTA 0 (tools/umma_probe.py)
   int32_t dbg_flags;               // probe hook: 1 skip epilogue body, 2 skip residual, 4 skip MMAs, 8 skip A loads
   int32_t dbg_shift_rows, dbg_base_offset_mode;   // experiment hook: A operand read at a row offset (tik_debug_set_umma_shift)
@@ -132,7 +133,7 @@ __device__ __forceinline__ void rowgemm_umma_body(const UmmaParams& p) {
   const int g0 = CL > 1 ? (int)blockIdx.x / CL : (int)blockIdx.x, gstep = CL > 1 ? (int)gridDim.x / CL : (int)gridDim.x;
   const int n_items = CL > 1 ? (int)(((p.tiles_m + CL - 1) / CL) * p.n_tiles_n) : (int)num_tiles;
   auto tile_of = [&](int g) -> int {
-    if (CL == 1) return g;
+    if (CL == 1) return p.rev ? (int)num_tiles - 1 - g : g;
     const int tn = g % p.n_tiles_n;
     int64_t tm = (int64_t)(g / p.n_tiles_n) * CL + cl_rank;
     if (tm >= p.tiles_m) tm = p.tiles_m - 1;              // odd tail: the same tile twice (identical stores)
@@ -176,6 +177,7 @@ __device__ __forceinline__ void rowgemm_umma_body(const UmmaParams& p) {
     const uint32_t tx_bytes = (uint32_t)(p.a_box_bytes + (p.w_resident ? 0 : kBBytes));
     const bool skip_a = (p.dbg_flags & 8) != 0;
     const int group = p.group, total_chunks = p.total_chunks;
+    const uint64_t pol = p.l2 ? l2_policy_evict_first() : 0;
     int stage = 0; uint32_t phase = 0;
     for (int g = g0; g < n_items; g += gstep) {
       const int tile = tile_of(g);
@@ -202,7 +204,7 @@ __device__ __forceinline__ void rowgemm_umma_body(const UmmaParams& p) {
           if (p3) TIK_T(26);
           uint8_t* sa = ring + (size_t)stage * stage_bytes + (size_t)j * chunk_bytes;
           if (leader) {
-            if (!skip_a) tma_load_3d(sa, &p.map_a[s], &full_bar[stage], c * kChunkK, ts, nv0);
+            if (!skip_a) tma_load_3d(sa, &p.map_a[s], &full_bar[stage], c * kChunkK, ts, nv0, pol);
             if (!p.w_resident) {
               if (CL > 1) tma_load_2d_mc(sa + kABytes + cl_rank * (kBBytes / CL), &p.map_w, &full_bar[stage], kw * kChunkK, n0 + cl_rank * (BN / CL), kClMask);
               else tma_load_2d(sa + kABytes, &p.map_w, &full_bar[stage], kw * kChunkK, n0);
@@ -779,7 +781,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_ts_kernel(const __gri
     // ===================== TMA producer: activation chunks only =====================
     const bool leader = lane == 0;
     int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint64_t pol = p.l2 ? l2_policy_evict_first() : 0;
+    for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x) {
+      const int tile = p.rev ? n_tiles - 1 - ti : ti;
       const int tile_nv = tile / p.tiles_t;
       const int t0 = (tile - tile_nv * p.tiles_t) * p.tt;
       const int nv0 = tile_nv * p.vv;
@@ -796,7 +800,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_ts_kernel(const __gri
             }
           }
           if (leader && !TIK_PROBE_ONLY((p.dbg_flags & 8) != 0))
-            tma_load_3d(ring + (size_t)stage * stage_bytes + (size_t)j * kABytes, &p.map_a[s], &full_bar[stage], c * kChunkK, ts, nv0);
+            tma_load_3d(ring + (size_t)stage * stage_bytes + (size_t)j * kABytes, &p.map_a[s], &full_bar[stage], c * kChunkK, ts, nv0, pol);
           __syncwarp();
           if (++j == group || kw + 1 == total_chunks) {
             j = 0;
@@ -862,7 +866,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) rowgemm_ts_kernel(const __gri
     if (lane == 0) {
       int sbuf = 0; uint32_t sphase = 0;
       int prev = -1;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x) {
+        const int tile = p.rev ? n_tiles - 1 - ti : ti;
         const int tile_nv = tile / p.tiles_t, tile_t = tile - tile_nv * p.tiles_t;
         mbar_wait(&stage_full[sbuf], sphase);
         for (int c = 0; c < (TIK_PROBE_ONLY((p.dbg_flags & 16) != 0) ? 0 : regions); ++c)
@@ -1231,6 +1236,7 @@ int umma_launch(UmmaPrepared* u, const TikRowGemm* d, cudaStream_t s) {
   p.res_kind = d->res_kind; p.res = d->res_dev; p.res_w = d->res_w_dev;
   p.res_cin = d->res_cin; p.res_t_mul = d->res_t_mul; p.res_t_in = d->res_t_in;
   p.out = d->out_dev; p.out_layout = d->out_layout;
+  p.rev = launch_opts().rev; p.l2 = launch_opts().l2;
   if (d->nv == 0 || d->t_out == 0) return TIK_OK;
   p.tiles_m = ceil_div(d->nv, p.vv) * ceil_div(d->t_out, p.tt);
   p.tiles_t = (int)ceil_div(d->t_out, p.tt);

@@ -66,6 +66,13 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 
+// Per-launch options the plan sets before each tensor-core launch (thread-local; read when the launch fills its
+// parameters).  rev: walk the tiles from the last to the first -- consecutive kernels alternate, so each starts on the
+// part of its input the previous kernel wrote last, which is still in L2.  l2: read-once activation loads carry an
+// evict-first hint, so that they do not push the freshly written output out of L2.
+struct LaunchOpts { int rev; int l2; };
+LaunchOpts& launch_opts();
+
 // internal entry points shared between translation units
 int rowgemm_f32(const TikRowGemm* d, cudaStream_t s);
 int rowgemm_bf16(const TikRowGemm* d, cudaStream_t s);
