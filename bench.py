@@ -664,8 +664,12 @@ def measure(args, dev, world, rank, local):
             peak, peak_name = peaks["bf16_tflops"], f"{peak_src} bf16_tflops (burst: cuBLAS 8192^3, best of 10)"
             kern = "tcgen05 family: rowgemm_umma_kernel / rowgemm_ts_kernel / tcn_halo_kernel / gcn_fused_kernel / gcn_wide_kernel / stem_block_kernel"
         else:
-            peak, peak_name = 74.0, "nominal fp32 SIMT: 148 SM x 128 FMA x 2 x 1.965 GHz"
-            kern = "rowgemm_f32_kernel"
+            if os.environ.get("TIK_NO_TF32"):
+                peak, peak_name = 74.0, "nominal fp32 SIMT: 148 SM x 128 FMA x 2 x 1.965 GHz"
+                kern = "rowgemm_f32_kernel"
+            else:
+                peak, peak_name = 1125.0 / 3.0, "nominal dense TF32 1125 TFLOP/s (B200_PROFILING.md) / 3 MMAs per fp32 product (3xTF32 split)"
+                kern = "rowgemm_tf32_kernel (tcgen05.mma kind::tf32, 3xTF32, per-chunk accumulation)"
         traffic, traffic_src = _ncu_traffic_per_launch()
         launches_per_step = len(mbs) * (plan.launches(micro) + 1)   # + FK per micro-batch
         roofline = {"bound": "tensor", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

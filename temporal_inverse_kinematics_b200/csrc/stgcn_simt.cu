@@ -87,17 +87,6 @@ aggregate_kernel(const T* __restrict__ x, const float* __restrict__ agg, T* __re
 // 128x64 tile, BK = 16, 256 threads, 8x4 register micro-tile.  M rows are (row group nv, frame t).
 constexpr int GM = 128, GN = 64, GK = 16, GT = 256;
 
-struct F32Slab { const float* a; int c, t_in, t_mul, t_off, koff; };
-struct F32Args {
-  F32Slab slabs[TIK_MAX_SLABS];
-  int n_slabs;
-  const float* w; int ktot;
-  const float* bias; int bias_per_node;
-  int64_t rows; int v, t_out, c_out, c_out_valid;
-  int act; float slope;
-  int res_kind; const void* res; const float* res_w; int res_cin, res_t_mul, res_t_in;
-  float* out; int out_layout;
-};
 
 __global__ void __launch_bounds__(GT, 3) rowgemm_f32_kernel(const __grid_constant__ F32Args p) {
   __shared__ __align__(16) float As[GK][GM + 4];
@@ -252,6 +241,7 @@ int rowgemm_f32(const TikRowGemm* d, cudaStream_t s) {
   a.res_cin = d->res_cin; a.res_t_mul = d->res_t_mul; a.res_t_in = d->res_t_in;
   a.out = reinterpret_cast<float*>(d->out_dev); a.out_layout = d->out_layout;
   if (a.rows == 0) return TIK_OK;
+  if (rowgemm_tf32_supported(a)) return rowgemm_tf32_launch(a, s);     // 3xTF32 on the tensor pipe (rowgemm_tf32.cu)
   dim3 grid((unsigned)ceil_div(a.rows, GM), (unsigned)ceil_div(d->c_out, GN));
   rowgemm_f32_kernel<<<grid, GT, 0, s>>>(a);
   TIK_LAUNCH_CHECK();

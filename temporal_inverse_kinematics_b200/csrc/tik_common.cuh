@@ -73,6 +73,21 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 struct LaunchOpts { int rev; int l2; };
 LaunchOpts& launch_opts();
 
+// fp32 implicit-GEMM arguments (stgcn_simt.cu rowgemm_f32_kernel, rowgemm_tf32.cu): TikRowGemm with the K offsets resolved
+struct F32Slab { const float* a; int c, t_in, t_mul, t_off, koff; };
+struct F32Args {
+  F32Slab slabs[TIK_MAX_SLABS];
+  int n_slabs;
+  const float* w; int ktot;
+  const float* bias; int bias_per_node;
+  int64_t rows; int v, t_out, c_out, c_out_valid;
+  int act; float slope;
+  int res_kind; const void* res; const float* res_w; int res_cin, res_t_mul, res_t_in;
+  float* out; int out_layout;
+};
+bool rowgemm_tf32_supported(const F32Args& a);
+int rowgemm_tf32_launch(const F32Args& a, cudaStream_t s);
+
 // internal entry points shared between translation units
 int rowgemm_f32(const TikRowGemm* d, cudaStream_t s);
 int rowgemm_bf16(const TikRowGemm* d, cudaStream_t s);

@@ -274,7 +274,7 @@ def test_latency_plan_matches_reference_path(n, t):
     got = m(x.cuda())["poses"].cpu()
     assert got.shape == want.shape
     assert float((got - want).abs().max()) < TOL_F32
-    assert float((got - multi).abs().max()) < 2e-5
+    assert float((got - multi).abs().max()) < 4e-5      # fp32 FMA (latency plan) vs 3xTF32 tensor-core GEMMs: each ~1e-5 from the reference
     # batches above the head's 32-row limit fall back to the throughput plan
     big = synth.make_clips(40, t, seed=1)
     assert not isinstance(m.plan_for(40, t), engine.LatencyPlan) or 40 * m.backbone.out_frames(t) <= 32
