@@ -13,8 +13,9 @@
 // alternating between two accumulators) and the chunk sums are added in registers (round to nearest) while the next
 // chunk's MMAs run: single-GEMM error <= 1.1e-6 at every K above (the SIMT fp32 kernel: 3.6e-7 ... 2.8e-6), network
 // parity 1.07e-5 / 1.14e-5 / 1.0e-5 on poses / rotation matrices / joints (SIMT: 7.6e-6) -- 9x inside the 1e-4 bar.
-// Speed (B200, 1.97 GHz): 96-108 TFLOP/s on the K >= 1024 layers (SIMT: 38), 45 at K = 256, 14 at K = 64 (per-tile
-// prologue / epilogue not overlapped); configs[1] GEMM time 4.41 -> 3.1 ms.  TIK_NO_TF32=1 restores the SIMT kernel.
+// Speed (B200, 1.97 GHz): 109-114 TFLOP/s on the K >= 1024 layers (SIMT: 38), 60 at K = 256, 15 at K = 64 (per-tile
+// prologue / epilogue not overlapped); configs[1] GEMM time 4.41 -> 2.38 ms, step 4.62 -> 2.60 ms (3.54 -> 6.3 M
+// frames/s).  TIK_NO_TF32=1 restores the SIMT kernel.
 //
 // One CTA = one 128-row x BN-column tile; 512 threads.  Activations and weights stay fp32 in HBM: per 32-wide K chunk
 // every thread loads its float4 pieces with plain coalesced loads (row = (row group, frame) with the tap shift / stride
@@ -22,8 +23,9 @@
 // 128B-swizzled shared-memory tiles (chunk j of row r at 16-byte slot j ^ (r & 7): the canonical layout the MMA
 // descriptors expect, here written by hand instead of by TMA because the split has to happen on the way).  One
 // thread issues the 12 MMAs of the chunk (4 K-steps of 8 x 3 products) and commits them to the stage's mbarrier; two
-// stages, so the loads / split / stores of chunk i+1 overlap the MMAs of chunk i, and the global loads of chunk i+1 are
-// issued before the wait for stage i+1 to drain.  Epilogue: tcgen05.ld -> bias / residual / activation -> fp32 rows.
+// stages, so the split / stores of chunk i+1 overlap the MMAs of chunk i, and the global loads run two chunks ahead in
+// registers.  Epilogue: the register sums go through a padded shared-memory tile (aliasing the dead stages) so that a
+// warp stores whole rows (bias / residual loads of four rows in flight at a time) -> fp32 rows, any output layout.
 #include <stdlib.h>
 
 #include <type_traits>
@@ -59,20 +61,32 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ float tf32_rna(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
+// warp-collective form (umma_ptx.cuh: the whole warp executes it with uniform operands, one elected lane issues)
+__device__ __forceinline__ void umma_tf32_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
+// big = v rounded to TF32 (nearest, ties away: add half an ulp of the 13 dropped bits to the magnitude and mask -- what
+// cvt.rna.tf32.f32 does, minus its Inf / NaN test: 2 instructions instead of 4); small = v - big is exact in fp32 and goes to
+// the tensor core as it is (the hardware drops its low 13 bits: rounding it here as well changed the network's parity
+// from 3.19e-5 to 3.15e-5 at 4-chunk accumulation -- not worth 4 more instructions per element on an issue-bound fill).
+__device__ __forceinline__ float tf32_big(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void split_store(uint8_t* big, uint8_t* small, uint32_t off, float4 v) {
   float4 b, s;
-  b.x = tf32_rna(v.x); b.y = tf32_rna(v.y); b.z = tf32_rna(v.z); b.w = tf32_rna(v.w);
-  // the remainder is rounded to TF32 here (nearest) -- left to the tensor core it would be truncated, a bias toward zero
-  s.x = tf32_rna(v.x - b.x); s.y = tf32_rna(v.y - b.y); s.z = tf32_rna(v.z - b.z); s.w = tf32_rna(v.w - b.w);
+  b.x = tf32_big(v.x); b.y = tf32_big(v.y); b.z = tf32_big(v.z); b.w = tf32_big(v.w);
+  s.x = v.x - b.x; s.y = v.y - b.y; s.z = v.z - b.z; s.w = v.w - b.w;
   *reinterpret_cast<float4*>(big + off) = b;
   *reinterpret_cast<float4*>(small + off) = s;
 }
 
+// Tried and dropped: a 17th warp that only issues the MMAs (fill warps hand stages over through mbarriers, no bar.sync per
+// chunk) -- 544 threads cap the kernel at 96 registers, the two-deep load buffer spills (800 B) and the K = 4352 layer
+// drops from 114 to 84 TFLOP/s.
 // BN = 128: 512 threads, one CTA per SM.  BN = 64 (the 64-channel layers: 2-6 chunks per tile, where the per-tile prologue
 // and epilogue weigh most): 256 threads and half the shared memory, two CTAs per SM overlap each other's fixed costs.
 template <int BN, int kTfThreads>
@@ -130,16 +144,32 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
   // exposed in every iteration (2850 cycles per chunk at K = 4352 against 12 x 64 cycles of MMAs).
   float4 ra[2][NQA], rw[2][NQW];
   int ls = 0, lk0 = 0, loaded = 0;                   // cursor of the next chunk to load
+  constexpr bool kCachePtr = NQA <= 2;
+  const float* a_src[kCachePtr ? NQA : 1];           // this thread's rows in the cursor's slab (nullptr: padding frame / row past the end)
   auto issue_loads = [&](auto PB) {
     constexpr int pb = decltype(PB)::value;
     if (loaded >= n_chunks) return;
-    const F32Slab sl = p.slabs[ls];
+    const F32Slab& sl = p.slabs[ls];
+    if constexpr (kCachePtr) {
+      if (lk0 == 0) {                                // new slab: resolve the tap shift / stride / padding once per row
 #pragma unroll
-    for (int q = 0; q < NQA; ++q) {
-      const int ts = a_t[q] * sl.t_mul + sl.t_off;
-      const bool ok = a_ok[q] && ts >= 0 && ts < sl.t_in;
-      ra[pb][q] = ok ? __ldg(reinterpret_cast<const float4*>(sl.a + ((int64_t)a_nv[q] * sl.t_in + ts) * (int64_t)sl.c + lk0 + a_k))
-                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < NQA; ++q) {
+          const int ts = a_t[q] * sl.t_mul + sl.t_off;
+          const bool ok = a_ok[q] && ts >= 0 && ts < sl.t_in;
+          a_src[q] = ok ? sl.a + ((int64_t)a_nv[q] * sl.t_in + ts) * (int64_t)sl.c + a_k : nullptr;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NQA; ++q)
+        ra[pb][q] = a_src[q] ? __ldg(reinterpret_cast<const float4*>(a_src[q] + lk0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {                                         // 256-thread variant (4 rows per thread, 128-register cap): cached pointers spill
+#pragma unroll
+      for (int q = 0; q < NQA; ++q) {
+        const int ts = a_t[q] * sl.t_mul + sl.t_off;
+        const bool ok = a_ok[q] && ts >= 0 && ts < sl.t_in;
+        ra[pb][q] = ok ? __ldg(reinterpret_cast<const float4*>(sl.a + ((int64_t)a_nv[q] * sl.t_in + ts) * (int64_t)sl.c + lk0 + a_k))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
 #pragma unroll
     for (int q = 0; q < NQW; ++q)
@@ -187,7 +217,7 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
     issue_loads(PB);                                         // chunk ch + 2 into the registers just consumed
     fence_proxy_async_smem();                                // generic-proxy stores -> visible to the MMA's async-proxy reads
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {                                         // warp-uniform: the election is inside the asm (no uniformisation loop per MMA)
       tc_fence_after();
       const uint32_t ab = smem_base + (uint32_t)(st * STAGE), as = ab + kTfATile, wb = as + kTfATile, ws = wb + WT;
       const uint32_t d = tmem_acc + (uint32_t)(((ch / kTfBlock) & 1) * BN);
@@ -195,11 +225,11 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
 #pragma unroll
       for (int k = 0; k < kTfKc / 8; ++k) {
         const uint32_t ko = (uint32_t)k * 32u;               // 8 tf32 = 32 bytes along K inside the swizzled row
-        umma_tf32(d, make_smem_desc_kmajor_sw128(as + ko), make_smem_desc_kmajor_sw128(wb + ko), idesc, (fresh && k == 0) ? 0u : 1u);
-        umma_tf32(d, make_smem_desc_kmajor_sw128(ab + ko), make_smem_desc_kmajor_sw128(ws + ko), idesc, 1u);
-        umma_tf32(d, make_smem_desc_kmajor_sw128(ab + ko), make_smem_desc_kmajor_sw128(wb + ko), idesc, 1u);
+        umma_tf32_w(d, make_smem_desc_kmajor_sw128(as + ko), make_smem_desc_kmajor_sw128(wb + ko), idesc, (fresh && k == 0) ? 0u : 1u);
+        umma_tf32_w(d, make_smem_desc_kmajor_sw128(ab + ko), make_smem_desc_kmajor_sw128(ws + ko), idesc, 1u);
+        umma_tf32_w(d, make_smem_desc_kmajor_sw128(ab + ko), make_smem_desc_kmajor_sw128(wb + ko), idesc, 1u);
       }
-      umma_commit(&mma_done[st]);
+      umma_commit_w(&mma_done[st]);
     }
   };
   issue_loads(std::integral_constant<int, 0>{});
