@@ -41,6 +41,12 @@ for what in "$@"; do
           --clock-control none -k regex:'rowgemm|tcn_halo|gcn_fused|gcn_wide|stem_|block_fused|fk_|aggregate' -c 120 --csv --log-file gpurun_out/launches.csv \
           python bench.py --steps 1 --warmup 3 --no-cpu --no-hbm --no-c3 --no-graph > gpurun_out/ncu_net.log 2>&1
       echo "ncu_net exit $?" | tee -a gpurun_out/summary.txt ;;
+    ncu_c1)
+      timeout 300 python bench.py --config 1 --steps 1 --warmup 3 --no-cpu --no-graph > gpurun_out/c1_plain.log 2>&1 &&
+      timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active \
+          --clock-control none -k regex:'rowgemm_tf32|rowgemm_f32|aggregate|stem_' -s 75 -c 25 --csv --log-file gpurun_out/launches_c1.csv \
+          python bench.py --config 1 --steps 1 --warmup 3 --no-cpu --no-graph > gpurun_out/ncu_c1.log 2>&1
+      echo "ncu_c1 exit $?" | tee -a gpurun_out/summary.txt ;;
     ncu_full)
       timeout 300 python bench.py --steps 1 --warmup 3 --no-cpu --no-hbm --no-c3 --no-graph > gpurun_out/full_plain.log 2>&1 &&
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'rowgemm|tcn_halo|gcn_fused|gcn_wide|stem_|block_fused' -s 51 -c 17 -f -o gpurun_out/prof_net \
