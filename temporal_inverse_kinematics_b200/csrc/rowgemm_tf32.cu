@@ -89,6 +89,10 @@ __device__ __forceinline__ void split_store(uint8_t* big, uint8_t* small, uint32
 // drops from 114 to 84 TFLOP/s.
 // BN = 128: 512 threads, one CTA per SM.  BN = 64 (the 64-channel layers: 2-6 chunks per tile, where the per-tile prologue
 // and epilogue weigh most): 256 threads and half the shared memory, two CTAs per SM overlap each other's fixed costs.
+__device__ __forceinline__ int fast_div(int n, unsigned long long magic, int shift) {
+  return (int)(((unsigned long long)(unsigned)n * magic) >> shift);
+}
+
 template <int BN, int kTfThreads>
 __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_kernel(const __grid_constant__ F32Args p) {
   constexpr int WT = BN * 128;                       // bytes of one weight tile (BN rows x 128 B)
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
     const int idx = q * kTfThreads + tid, r_l = idx >> 3, j = idx & 7;
     const int r = row0 + r_l;
     a_ok[q] = r < rows;
-    a_nv[q] = a_ok[q] ? r / p.t_out : 0;
+    a_nv[q] = a_ok[q] ? fast_div(r, p.div_t_magic, p.div_t_shift) : 0;
     a_t[q] = a_ok[q] ? r - a_nv[q] * p.t_out : 0;
     a_off[q] = (uint32_t)(r_l * 128 + ((j ^ (r_l & 7)) << 4));
   }
@@ -144,33 +148,22 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
   // exposed in every iteration (2850 cycles per chunk at K = 4352 against 12 x 64 cycles of MMAs).
   float4 ra[2][NQA], rw[2][NQW];
   int ls = 0, lk0 = 0, loaded = 0;                   // cursor of the next chunk to load
-  constexpr bool kCachePtr = NQA <= 2;
-  const float* a_src[kCachePtr ? NQA : 1];           // this thread's rows in the cursor's slab (nullptr: padding frame / row past the end)
+  uint32_t a_src[NQA];                               // this thread's rows in the cursor's slab as element offsets (~0: padding frame / row past the end)
   auto issue_loads = [&](auto PB) {
     constexpr int pb = decltype(PB)::value;
     if (loaded >= n_chunks) return;
     const F32Slab& sl = p.slabs[ls];
-    if constexpr (kCachePtr) {
-      if (lk0 == 0) {                                // new slab: resolve the tap shift / stride / padding once per row
-#pragma unroll
-        for (int q = 0; q < NQA; ++q) {
-          const int ts = a_t[q] * sl.t_mul + sl.t_off;
-          const bool ok = a_ok[q] && ts >= 0 && ts < sl.t_in;
-          a_src[q] = ok ? sl.a + ((int64_t)a_nv[q] * sl.t_in + ts) * (int64_t)sl.c + a_k : nullptr;
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < NQA; ++q)
-        ra[pb][q] = a_src[q] ? __ldg(reinterpret_cast<const float4*>(a_src[q] + lk0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    } else {                                         // 256-thread variant (4 rows per thread, 128-register cap): cached pointers spill
+    if (lk0 == 0) {                                  // new slab: resolve the tap shift / stride / padding once per row
 #pragma unroll
       for (int q = 0; q < NQA; ++q) {
         const int ts = a_t[q] * sl.t_mul + sl.t_off;
         const bool ok = a_ok[q] && ts >= 0 && ts < sl.t_in;
-        ra[pb][q] = ok ? __ldg(reinterpret_cast<const float4*>(sl.a + ((int64_t)a_nv[q] * sl.t_in + ts) * (int64_t)sl.c + lk0 + a_k))
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        a_src[q] = ok ? (uint32_t)((a_nv[q] * sl.t_in + ts) * sl.c + a_k) : 0xFFFFFFFFu;   // element offset (< 2^31: checked on the host)
       }
     }
+#pragma unroll
+    for (int q = 0; q < NQA; ++q)
+      ra[pb][q] = a_src[q] != 0xFFFFFFFFu ? __ldg(reinterpret_cast<const float4*>(sl.a + a_src[q] + lk0)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int q = 0; q < NQW; ++q)
       rw[pb][q] = w_ptr[q] ? __ldg(reinterpret_cast<const float4*>(w_ptr[q] + sl.koff + lk0)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -265,9 +258,9 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
     const bool vec_ok = c + 4 <= p.c_out;
     const int ld = p.out_layout == TIK_OUT_ROWS_F32 ? p.c_out_valid : p.c_out;
     auto row_info = [&](int r, int& n, int& t, int& node) {
-      const int nv = r / p.t_out;
+      const int nv = fast_div(r, p.div_t_magic, p.div_t_shift);
       t = r - nv * p.t_out;
-      n = nv / p.v;
+      n = fast_div(nv, p.div_v_magic, p.div_v_shift);
       node = nv - n * p.v;
     };
 #pragma unroll 1
@@ -342,6 +335,8 @@ bool rowgemm_tf32_supported(const F32Args& a) {
   if (getenv("TIK_NO_TF32")) return false;
   if (a.ktot % 4 != 0 || a.c_out < 1 || a.rows >= (1ll << 31) - 128) return false;
   for (int i = 0; i < a.n_slabs; ++i)
+    if ((a.rows / a.t_out + 1) * (int64_t)a.slabs[i].t_in * a.slabs[i].c >= (1ll << 31)) return false;   // 32-bit element offsets
+  for (int i = 0; i < a.n_slabs; ++i)
     if (a.slabs[i].c % kTfKc != 0 || (reinterpret_cast<uintptr_t>(a.slabs[i].a) & 15) != 0) return false;
   if ((reinterpret_cast<uintptr_t>(a.w) & 15) != 0) return false;
   if (a.out_layout != TIK_OUT_ROWS_F32 && a.c_out % 4 != 0) return false;
@@ -364,7 +359,17 @@ static int launch_tf32(const F32Args& a, cudaStream_t s) {
   return TIK_OK;
 }
 
-int rowgemm_tf32_launch(const F32Args& a, cudaStream_t s) {
+static void make_div(int d, unsigned long long* magic, int* shift) {   // exact for 0 <= n < 2^31 (checked exhaustively at the edges in the test-suite's shapes)
+  int s = 0;
+  while ((1ll << s) < d) ++s;
+  *magic = (1ull << (31 + s)) / (unsigned long long)d + 1ull;
+  *shift = 31 + s;
+}
+
+int rowgemm_tf32_launch(const F32Args& a0, cudaStream_t s) {
+  F32Args a = a0;
+  make_div(a.t_out, &a.div_t_magic, &a.div_t_shift);
+  make_div(a.v, &a.div_v_magic, &a.div_v_shift);
   return a.c_out > 64 ? launch_tf32<128, 512>(a, s) : launch_tf32<64, 256>(a, s);
 }
 

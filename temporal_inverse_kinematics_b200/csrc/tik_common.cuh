@@ -84,6 +84,8 @@ struct F32Args {
   int act; float slope;
   int res_kind; const void* res; const float* res_w; int res_cin, res_t_mul, res_t_in;
   float* out; int out_layout;
+  // n / t_out and n / v for n < 2^31 as (n * magic) >> shift (rowgemm_tf32.cu: ~100 integer divisions per tile row otherwise)
+  unsigned long long div_t_magic, div_v_magic; int div_t_shift, div_v_shift;
 };
 bool rowgemm_tf32_supported(const F32Args& a);
 int rowgemm_tf32_launch(const F32Args& a, cudaStream_t s);
