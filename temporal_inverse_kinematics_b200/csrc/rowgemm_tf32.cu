@@ -249,50 +249,68 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
   }
   __syncthreads();
   {
-    // rows rr = warp + i * NW, four at a time: first the four rows' residual / bias loads go out (their latencies overlap;
-    // one row after the other cost 8 serialized L2 round trips per warp), then the math and the stores
-    constexpr int NW = kTfThreads / 32, NR = 128 / NW, RB = 4;
-    const int c_l = lane * 4;
+    // A warp stores whole rows: BN = 128: one row per pass (32 lanes x 4 columns), BN = 64: two rows per pass (lane >> 4 picks
+    // the row).  Passes go RB at a time: first the RB rows' residual / bias loads go out (their latencies overlap), then the
+    // math and the stores.  The epilogue was 57 % of a K = 64 tile (in-kernel clock probe: 11.4 k of 20 k cycles, ~70
+    // instructions per row with half the lanes idle at BN = 64): rows and pointers now advance incrementally, the
+    // (clip, node, frame) split is computed only when the bias / layout / residual needs it, the activation is branch-free.
+    constexpr int LPR = BN / 4;                        // lanes per row
+    constexpr int RPP = 32 / LPR;                      // rows per pass
+    constexpr int NW = kTfThreads / 32, NP = 128 / (NW * RPP), RB = 4;
+    static_assert(NP % RB == 0, "passes per warp must be a multiple of the batch");
+    const int sub = lane / LPR;                        // row of the pass this lane works on
+    const int c_l = (lane % LPR) * 4;
     const int c = col0 + c_l;
-    const bool lane_on = c_l < BN && c < p.c_out;
+    const bool lane_on = c < p.c_out;
     const bool vec_ok = c + 4 <= p.c_out;
     const int ld = p.out_layout == TIK_OUT_ROWS_F32 ? p.c_out_valid : p.c_out;
+    const bool vec_st = c + 4 <= ld && (ld & 3) == 0;
+    const bool need_info = p.bias_per_node || p.out_layout == TIK_OUT_TIME_MAJOR || p.res_kind == TIK_RES_STEM;
+    const float act_s = p.act == TIK_ACT_RELU ? 0.f : (p.act == TIK_ACT_LEAKY ? p.slope : 1.f);   // act(v) = max(v, v * s), s in [0, 1]
     auto row_info = [&](int r, int& n, int& t, int& node) {
       const int nv = fast_div(r, p.div_t_magic, p.div_t_shift);
       t = r - nv * p.t_out;
       n = fast_div(nv, p.div_v_magic, p.div_v_shift);
       node = nv - n * p.v;
     };
+    float4 bias_shared = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane_on && !p.bias_per_node) {
+      if (vec_ok) bias_shared = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+      else { bias_shared.x = __ldg(p.bias + c); if (c + 1 < p.c_out) bias_shared.y = __ldg(p.bias + c + 1); if (c + 2 < p.c_out) bias_shared.z = __ldg(p.bias + c + 2); }
+    }
+    const int rr0 = warp * RPP + sub;                  // first tile row of this lane; a pass advances it by NW * RPP
 #pragma unroll 1
-    for (int i0 = 0; i0 < NR; i0 += RB) {
+    for (int i0 = 0; i0 < NP; i0 += RB) {
       float4 res4[RB], bias4[RB];
 #pragma unroll
       for (int i = 0; i < RB; ++i) {
-        const int r = min(row0 + warp + (i0 + i) * NW, rows - 1);
-        int n, t, node;
-        row_info(r, n, t, node);
+        const int r = min(row0 + rr0 + (i0 + i) * NW * RPP, rows - 1);
         res4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        bias4[i] = res4[i];
+        bias4[i] = bias_shared;
         if (lane_on) {
-          const float* bias = p.bias + (p.bias_per_node ? node * p.c_out : 0) + c;
-          if (vec_ok) bias4[i] = __ldg(reinterpret_cast<const float4*>(bias));
-          else { bias4[i].x = __ldg(bias); if (c + 1 < p.c_out) bias4[i].y = __ldg(bias + 1); if (c + 2 < p.c_out) bias4[i].z = __ldg(bias + 2); }
+          if (p.bias_per_node) {
+            int n, t, node;
+            row_info(r, n, t, node);
+            const float* bias = p.bias + node * p.c_out + c;
+            if (vec_ok) bias4[i] = __ldg(reinterpret_cast<const float4*>(bias));
+            else { bias4[i].x = __ldg(bias); if (c + 1 < p.c_out) bias4[i].y = __ldg(bias + 1); if (c + 2 < p.c_out) bias4[i].z = __ldg(bias + 2); }
+          }
           if (p.res_kind == TIK_RES_IDENTITY) {
-            const float* rr = reinterpret_cast<const float*>(p.res) + (int64_t)r * p.c_out + c;
-            if (vec_ok) res4[i] = __ldg(reinterpret_cast<const float4*>(rr));
-            else { res4[i].x = __ldg(rr); if (c + 1 < p.c_out) res4[i].y = __ldg(rr + 1); if (c + 2 < p.c_out) res4[i].z = __ldg(rr + 2); }
+            const float* rp = reinterpret_cast<const float*>(p.res) + (int64_t)r * p.c_out + c;
+            if (vec_ok) res4[i] = __ldg(reinterpret_cast<const float4*>(rp));
+            else { res4[i].x = __ldg(rp); if (c + 1 < p.c_out) res4[i].y = __ldg(rp + 1); if (c + 2 < p.c_out) res4[i].z = __ldg(rp + 2); }
           }
         }
       }
 #pragma unroll
       for (int i = 0; i < RB; ++i) {
-        const int rr = warp + (i0 + i) * NW;
+        const int rr = rr0 + (i0 + i) * NW * RPP;
         const int r = row0 + rr;
         if (r >= rows || !lane_on) continue;
-        int n, t, node;
-        row_info(r, n, t, node);
         const float4 v4 = *reinterpret_cast<const float4*>(smem + (size_t)rr * OUT_PITCH + (size_t)c_l * 4);
         float o[4] = {v4.x + bias4[i].x + res4[i].x, v4.y + bias4[i].y + res4[i].y, v4.z + bias4[i].z + res4[i].z, v4.w + bias4[i].w + res4[i].w};
+        int n = 0, t = 0, node = 0;
+        if (need_info) row_info(r, n, t, node);
         if (p.res_kind == TIK_RES_STEM) {
           const float* xin = reinterpret_cast<const float*>(p.res) + ((((int64_t)n * p.res_t_in + (int64_t)t * p.res_t_mul) * p.v + node) * p.res_cin);
 #pragma unroll
@@ -304,15 +322,11 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
           }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (p.act == TIK_ACT_RELU) o[j] = fmaxf(o[j], 0.f);
-          else if (p.act == TIK_ACT_LEAKY) o[j] = o[j] > 0.f ? o[j] : o[j] * p.slope;
-        }
+        for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], o[j] * act_s);
         float* dst;
-        if (p.out_layout == TIK_OUT_NODE_MAJOR) dst = p.out + (int64_t)r * p.c_out;
-        else if (p.out_layout == TIK_OUT_TIME_MAJOR) dst = p.out + (((int64_t)n * p.t_out + t) * p.v + node) * (int64_t)p.c_out;
-        else dst = p.out + (int64_t)r * p.c_out_valid;
-        if (c + 4 <= ld && (ld & 3) == 0) {
+        if (p.out_layout == TIK_OUT_TIME_MAJOR) dst = p.out + (((int64_t)n * p.t_out + t) * p.v + node) * (int64_t)p.c_out;
+        else dst = p.out + (int64_t)r * ld;
+        if (vec_st) {
           *reinterpret_cast<float4*>(dst + c) = make_float4(o[0], o[1], o[2], o[3]);
         } else {
 #pragma unroll
