@@ -686,7 +686,14 @@ extern "C" int tik_fk_body(const float* pose_dev, int pose_is_rotmat, const floa
         int rc = cfg == 1   ? launch_fk_bulk<TreeFull60, 32, 3>(pose_dev, transl_dev, joints_dev, F, p.rest, s, &done_frames)
                  : cfg == 2 ? launch_fk_bulk<TreeFull60, 64, 3>(pose_dev, transl_dev, joints_dev, F, p.rest, s, &done_frames)
                  : cfg == 3 ? launch_fk_bulk<TreeFull60, 32, 2>(pose_dev, transl_dev, joints_dev, F, p.rest, s, &done_frames)
-                            : launch_fk_bulk<TreeFull60, 64, 2>(pose_dev, transl_dev, joints_dev, F, p.rest, s, &done_frames);
+                 : cfg == 4 ? launch_fk_bulk<TreeFull60, 64, 2>(pose_dev, transl_dev, joints_dev, F, p.rest, s, &done_frames)
+                 : cfg == 5 ? launch_fk_bulk<TreeFull60, 128, 1>(pose_dev, transl_dev, joints_dev, F, p.rest, s, &done_frames)
+                 : cfg == 6 ? launch_fk_bulk<TreeFull60, 32, 1>(pose_dev, transl_dev, joints_dev, F, p.rest, s, &done_frames)
+                            // default: ONE buffer per CTA, four CTAs per SM.  720 B per frame in place means ~315 frames per SM whatever
+                            // the shape; single-buffered CTAs put all of them under compute threads (8 warps instead of 4) and
+                            // overlap each other's load / compute / store phases: 0.68 of the HBM peak against 0.48-0.55 with
+                            // two buffers per CTA (cfg 4), 0.67 with 128 frames x 1 (cfg 5), 0.48 with 32 x 1 (cfg 6).
+                            : launch_fk_bulk<TreeFull60, 64, 1>(pose_dev, transl_dev, joints_dev, F, p.rest, s, &done_frames);
         if (rc != TIK_OK) return rc;
         if (done_frames == F) return TIK_OK;
         pose_dev += done_frames * (kF60 * 3);
