@@ -14,7 +14,7 @@
 // chunk's MMAs run: single-GEMM error <= 1.1e-6 at every K above (the SIMT fp32 kernel: 3.6e-7 ... 2.8e-6), network
 // parity 1.07e-5 / 1.14e-5 / 1.0e-5 on poses / rotation matrices / joints (SIMT: 7.6e-6) -- 9x inside the 1e-4 bar.
 // Speed (B200, 1.97 GHz): 109-114 TFLOP/s on the K >= 1024 layers (SIMT: 38), 60 at K = 256, 15 at K = 64 (per-tile
-// prologue / epilogue not overlapped); configs[1] GEMM time 4.41 -> 2.38 ms, step 4.62 -> 2.60 ms (3.54 -> 6.3 M
+// prologue / epilogue not overlapped); configs[1] GEMM time 4.41 -> 1.83 ms, step 4.62 -> 2.05 ms (3.54 -> 8.0 M
 // frames/s).  TIK_NO_TF32=1 restores the SIMT kernel.
 //
 // One CTA = one 128-row x BN-column tile; 512 threads.  Activations and weights stay fp32 in HBM: per 32-wide K chunk
