@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
 bool rowgemm_tf32_supported(const F32Args& a) {
   // On by default for the fp32 path; TIK_NO_TF32=1 forces the SIMT kernel (read per call: A/B inside one process).
   if (getenv("TIK_NO_TF32")) return false;
-  if (a.ktot % 4 != 0 || a.c_out < 1 || a.rows >= (1ll << 31) - 128) return false;
+  if (a.ktot % 4 != 0 || a.c_out < 1 || a.v < 1 || a.t_out < 1 || a.n_slabs < 1 || a.rows >= (1ll << 31) - 128) return false;
   for (int i = 0; i < a.n_slabs; ++i)
     if ((a.rows / a.t_out + 1) * (int64_t)a.slabs[i].t_in * a.slabs[i].c >= (1ll << 31)) return false;   // 32-bit element offsets
   for (int i = 0; i < a.n_slabs; ++i)
