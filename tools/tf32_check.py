@@ -10,7 +10,9 @@ from temporal_inverse_kinematics_b200 import ops  # noqa: E402
 
 
 def run(rows, k, n, mode):
-    os.environ["TIK_TF32X3"] = mode
+    os.environ.pop("TIK_NO_TF32", None)
+    if mode == "simt":
+        os.environ["TIK_NO_TF32"] = "1"
     g = torch.Generator(device="cuda").manual_seed(1)
     a = torch.randn(rows, 1, k, device="cuda", generator=g)
     w = torch.randn(n, k, device="cuda", generator=g) / k ** 0.5
@@ -31,7 +33,15 @@ def run(rows, k, n, mode):
 
 
 if __name__ == "__main__":
+    if "--once" in sys.argv:      # one launch per shape on the tensor-core kernel: the input of an ncu capture
+        os.environ.pop("TIK_NO_TF32", None)
+        for rows, k, n in ((65536, 64, 64), (65536, 256, 128), (65536, 1024, 256), (16384, 4352, 512)):
+            a = torch.randn(rows, 1, k, device="cuda")
+            w = torch.randn(n, k, device="cuda") / k ** 0.5
+            ops.rowgemm([(a, 1, 0)], w, torch.zeros(1, n, device="cuda"), rows, 1, 1)
+        torch.cuda.synchronize()
+        sys.exit(0)
     for rows, k, n in ((65536, 64, 64), (65536, 256, 128), (65536, 1024, 256), (16384, 4352, 512)):
-        for mode in ("0", "1"):
+        for mode in ("simt", "tf32x3"):
             err, us, tf = run(rows, k, n, mode)
-            print(f"rows={rows} K={k} N={n} TF32X3={mode}: max rel err {err:.2e}  {us:.1f} us  {tf:.1f} TFLOP/s")
+            print(f"rows={rows} K={k} N={n} {mode:7s}: max rel err {err:.2e}  {us:.1f} us  {tf:.1f} TFLOP/s")
