@@ -33,15 +33,13 @@ LaunchOpts& launch_opts() {
 // Measured on one box, three alternating rounds (tools/ab_env.sh, profiles/r2_ab_serpentine.log), sum of the 17 network
 // launches of a configs[2] step: serpentine 3653-3658 us vs 3672-3700 us (on by default); the evict-first hint costs
 // 3-4 % (3755-3816 us: it also evicts tiles that a second CTA is about to read) and stays off.
-static int serpentine_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("TIK_SERPENTINE"); v = e ? atoi(e) : 1; }
-  return v;
+static int serpentine_enabled() {           // read per run (two getenv calls): tests and A/B tools flip it inside one process
+  const char* e = getenv("TIK_SERPENTINE");
+  return e ? atoi(e) : 1;
 }
 static int l2_hint_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("TIK_L2_HINT"); v = e ? atoi(e) : 0; }
-  return v;
+  const char* e = getenv("TIK_L2_HINT");
+  return e ? atoi(e) : 0;
 }
 
 void set_error(const char* fmt, ...) {

@@ -245,6 +245,20 @@ def test_bf16_kernel_variants_agree(monkeypatch, switch):
     assert float((fast - slow).abs().max()) < 0.06
 
 
+@pytest.mark.parametrize("dtype,n,t", [("bf16", 300, 64), ("bf16", 37, 128), ("bf16", 5, 9), ("fp32", 40, 64)])
+def test_serpentine_order_is_bit_identical(monkeypatch, dtype, n, t):
+    """Consecutive kernels walk the clips in opposite directions (LaunchOpts::rev, csrc/plan.cu): a pure re-ordering of
+    independent tiles, so the poses must not change by a single bit -- also with the evict-first hint on the loads."""
+    x = synth.make_clips(n, t, seed=77).cuda()
+    m, _ = _model(dtype=dtype)
+    monkeypatch.setenv("TIK_SERPENTINE", "0")
+    base = m(x)["poses"].clone()
+    monkeypatch.setenv("TIK_SERPENTINE", "1")
+    assert torch.equal(m(x)["poses"], base)
+    monkeypatch.setenv("TIK_L2_HINT", "1")
+    assert torch.equal(m(x)["poses"], base)
+
+
 @pytest.mark.parametrize("n,t", [(1, 1), (1, 2), (2, 11), (1, 12), (2, 13), (3, 25), (7, 33), (2, 61), (1, 65), (2, 95),
                                  (1, 100), (2, 126), (1, 127), (1, 129), (1, 190), (1, 191), (1, 200), (1, 256), (33, 16)])
 def test_bf16_edge_shapes(n, t):
