@@ -17,7 +17,7 @@
 // prologue / epilogue not overlapped); configs[1] GEMM time 4.41 -> 1.83 ms, step 4.62 -> 2.05 ms (3.54 -> 8.0 M
 // frames/s).  TIK_NO_TF32=1 restores the SIMT kernel.
 //
-// One CTA = one 128-row x BN-column tile; 512 threads.  Activations and weights stay fp32 in HBM: per 32-wide K chunk
+// Persistent CTAs (one per resident slot) walk 128-row x BN-column tiles; 512 threads.  Activations and weights stay fp32 in HBM: per 32-wide K chunk
 // every thread loads its float4 pieces with plain coalesced loads (row = (row group, frame) with the tap shift / stride
 // / zero padding of the slab resolved per row), splits them, and writes big and small parts into two K-major
 // 128B-swizzled shared-memory tiles (chunk j of row r at 16-byte slot j ^ (r & 7): the canonical layout the MMA
@@ -26,8 +26,11 @@
 // stages, so the split / stores of chunk i+1 overlap the MMAs of chunk i, and the global loads run two chunks ahead in
 // registers.  Epilogue: the register sums go through a padded shared-memory tile (aliasing the dead stages) so that a
 // warp stores whole rows (bias / residual loads of four rows in flight at a time) -> fp32 rows, any output layout.
+// The next tile's row bookkeeping and its first two chunks' loads are issued before the current tile's epilogue
+// (K = 64 ... 256 layers: -8 %; the K >= 384 layers pay ~4 % for the longer loop bookkeeping: net +1 % on configs[1]).
 #include <stdlib.h>
 
+#include <algorithm>
 #include <type_traits>
 
 #include "tik_common.cuh"
@@ -108,9 +111,9 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
   uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row0 = (int)blockIdx.x * 128;
-  const int col0 = blockIdx.y * BN;
   const int rows = (int)p.rows;
+  const int tiles_n = (p.c_out + BN - 1) / BN, total_tiles = ((rows + 127) / 128) * tiles_n;
+  int row0 = 0, col0 = 0;                            // tile the load cursor works on (one tile ahead of the epilogue)
 
   if (tid == 0) { mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1); fence_barrier_init(); }
   if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
@@ -122,24 +125,17 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
   // this thread's pieces: A piece q is 16-byte slot tid & 7 of tile row (q * 512 + tid) >> 3
   int a_nv[NQA], a_t[NQA]; bool a_ok[NQA]; uint32_t a_off[NQA];
   const int a_k = (tid & 7) * 4;
+  const float* w_ptr[NQW]; uint32_t w_off[NQW];
 #pragma unroll
   for (int q = 0; q < NQA; ++q) {
     const int idx = q * kTfThreads + tid, r_l = idx >> 3, j = idx & 7;
-    const int r = row0 + r_l;
-    a_ok[q] = r < rows;
-    a_nv[q] = a_ok[q] ? fast_div(r, p.div_t_magic, p.div_t_shift) : 0;
-    a_t[q] = a_ok[q] ? r - a_nv[q] * p.t_out : 0;
     a_off[q] = (uint32_t)(r_l * 128 + ((j ^ (r_l & 7)) << 4));
   }
-  const float* w_ptr[NQW]; uint32_t w_off[NQW];
 #pragma unroll
   for (int q = 0; q < NQW; ++q) {
     const int idx = q * kTfThreads + tid, n_l = idx >> 3, j = idx & 7;
-    const int col = col0 + n_l;
-    w_ptr[q] = col < p.c_out ? p.w + (int64_t)col * p.ktot + j * 4 : nullptr;
     w_off[q] = (uint32_t)(n_l * 128 + ((j ^ (n_l & 7)) << 4));
   }
-
   int n_chunks = 0;
   for (int s = 0; s < p.n_slabs; ++s) n_chunks += p.slabs[s].c / kTfKc;
   const int n_blocks = (n_chunks + kTfBlock - 1) / kTfBlock;
@@ -172,15 +168,37 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
     if (lk0 >= sl.c) { ++ls; lk0 = 0; }
   };
 
+  // Persistent over tiles: the row / column bookkeeping of the NEXT tile and its first two chunks' loads are issued right
+  // after the K loop of the current tile, so their latency hides behind the current tile's epilogue.
+  auto setup_tile = [&](int tile) {
+    const int tm = tile / tiles_n;                   // column tiles of one row tile run side by side: A is read from DRAM once
+    row0 = tm * 128;
+    col0 = (tile - tm * tiles_n) * BN;
+#pragma unroll
+    for (int q = 0; q < NQA; ++q) {
+      const int r = row0 + ((q * kTfThreads + tid) >> 3);
+      a_ok[q] = r < rows;
+      a_nv[q] = a_ok[q] ? fast_div(r, p.div_t_magic, p.div_t_shift) : 0;
+      a_t[q] = a_ok[q] ? r - a_nv[q] * p.t_out : 0;
+    }
+#pragma unroll
+    for (int q = 0; q < NQW; ++q) {
+      const int col = col0 + ((q * kTfThreads + tid) >> 3);
+      w_ptr[q] = col < p.c_out ? p.w + (int64_t)col * p.ktot + a_k : nullptr;
+    }
+    ls = 0; lk0 = 0; loaded = 0;
+    issue_loads(std::integral_constant<int, 0>{});
+    issue_loads(std::integral_constant<int, 1>{});
+  };
+
   // K is accumulated in tensor memory in BLOCKS of kTfBlock chunks (alternating between two accumulators) and the block
   // sums are added up in registers (header comment: the tensor core's accumulation truncates).
   const int lg = warp & 3, cq = warp >> 2;
   float acc[NACC];
-#pragma unroll
-  for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+  int gch0 = 0, gblk0 = 0;                           // chunks / blocks this CTA has issued before the current tile (barrier phases, accumulator parity)
   auto drain = [&](int blk) {
     uint32_t a[NACC];
-    const uint32_t taddr = tmem_acc + ((uint32_t)(lg * 32) << 16) + (uint32_t)((blk & 1) * BN + cq * NACC);
+    const uint32_t taddr = tmem_acc + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((gblk0 + blk) & 1) * BN + cq * NACC);
     if constexpr (NACC == 32) tmem_ld32(taddr, a); else tmem_ld16(taddr, a);
     tmem_ld_wait();
 #pragma unroll
@@ -193,13 +211,14 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
   int drained = 0;
   auto body = [&](int ch, auto PB) {
     constexpr int pb = decltype(PB)::value;
-    const int st = ch & 1;
+    const int gch = gch0 + ch;                               // stage and barrier phase follow the CTA's running chunk count
+    const int st = gch & 1;
     uint8_t* sa_big = smem + (size_t)st * STAGE;
     uint8_t* sa_small = sa_big + kTfATile;
     uint8_t* sw_big = sa_small + kTfATile;
     uint8_t* sw_small = sw_big + WT;
     if (ch >= 2) {                                           // the MMAs of chunk ch-2 have finished: its stage is free ...
-      mbar_wait_warp(&mma_done[st], (uint32_t)(((ch >> 1) - 1) & 1));
+      mbar_wait_warp(&mma_done[st], (uint32_t)(((gch >> 1) - 1) & 1));
       tc_fence_after();
       if ((ch - 2) % kTfBlock == kTfBlock - 1) { drain(drained); ++drained; }   // ... and if it closed a block, so is that block's sum
     }
@@ -213,7 +232,7 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
     if (warp == 0) {                                         // warp-uniform: the election is inside the asm (no uniformisation loop per MMA)
       tc_fence_after();
       const uint32_t ab = smem_base + (uint32_t)(st * STAGE), as = ab + kTfATile, wb = as + kTfATile, ws = wb + WT;
-      const uint32_t d = tmem_acc + (uint32_t)(((ch / kTfBlock) & 1) * BN);
+      const uint32_t d = tmem_acc + (uint32_t)(((gblk0 + ch / kTfBlock) & 1) * BN);
       const bool fresh = ch % kTfBlock == 0;                 // first chunk of a block overwrites the accumulator
 #pragma unroll
       for (int k = 0; k < kTfKc / 8; ++k) {
@@ -225,18 +244,24 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
       umma_commit_w(&mma_done[st]);
     }
   };
-  issue_loads(std::integral_constant<int, 0>{});
-  issue_loads(std::integral_constant<int, 1>{});
+  if ((int)blockIdx.x < total_tiles) setup_tile((int)blockIdx.x);
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  const int e_row0 = row0, e_col0 = col0;                    // the epilogue's tile (setup_tile moves row0 / col0 on to the next one)
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+  drained = 0;
   for (int ch = 0; ch < n_chunks; ch += 2) {
     body(ch, std::integral_constant<int, 0>{});
     if (ch + 1 < n_chunks) body(ch + 1, std::integral_constant<int, 1>{});
   }
+  if (tile + (int)gridDim.x < total_tiles) setup_tile(tile + (int)gridDim.x);   // both load buffers are free: next tile's first chunks
   {
-    const int last = n_chunks - 1;                           // the commit of the last chunk covers every MMA of the tile
+    const int last = gch0 + n_chunks - 1;                    // the commit of the last chunk covers every MMA of the tile
     mbar_wait_warp(&mma_done[last & 1], (uint32_t)((last >> 1) & 1));
     tc_fence_after();
     for (; drained < n_blocks; ++drained) drain(drained);
   }
+  gch0 += n_chunks; gblk0 += n_blocks;
   __syncthreads();                                           // operand stages are dead: they become the staging tile
 
   // ---- epilogue: raw sums -> shared memory (thread = tile row), then one warp per row: bias / residual / activation and
@@ -260,7 +285,7 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
     static_assert(NP % RB == 0, "passes per warp must be a multiple of the batch");
     const int sub = lane / LPR;                        // row of the pass this lane works on
     const int c_l = (lane % LPR) * 4;
-    const int c = col0 + c_l;
+    const int c = e_col0 + c_l;
     const bool lane_on = c < p.c_out;
     const bool vec_ok = c + 4 <= p.c_out;
     const int ld = p.out_layout == TIK_OUT_ROWS_F32 ? p.c_out_valid : p.c_out;
@@ -284,7 +309,7 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
       float4 res4[RB], bias4[RB];
 #pragma unroll
       for (int i = 0; i < RB; ++i) {
-        const int r = min(row0 + rr0 + (i0 + i) * NW * RPP, rows - 1);
+        const int r = min(e_row0 + rr0 + (i0 + i) * NW * RPP, rows - 1);
         res4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         bias4[i] = bias_shared;
         if (lane_on) {
@@ -305,7 +330,7 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
 #pragma unroll
       for (int i = 0; i < RB; ++i) {
         const int rr = rr0 + (i0 + i) * NW * RPP;
-        const int r = row0 + rr;
+        const int r = e_row0 + rr;
         if (r >= rows || !lane_on) continue;
         const float4 v4 = *reinterpret_cast<const float4*>(smem + (size_t)rr * OUT_PITCH + (size_t)c_l * 4);
         float o[4] = {v4.x + bias4[i].x + res4[i].x, v4.y + bias4[i].y + res4[i].y, v4.z + bias4[i].z + res4[i].z, v4.w + bias4[i].w + res4[i].w};
@@ -336,6 +361,8 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
       }
     }
   }
+  __syncthreads();                                           // the staging tile has been read: the next tile may refill the stages
+  }  // tile loop
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -367,7 +394,10 @@ static int launch_tf32(const F32Args& a, cudaStream_t s) {
     TIK_CUDA(cudaFuncSetAttribute(rowgemm_tf32_kernel<BN, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done[dev & 63] = true;
   }
-  dim3 grid((unsigned)ceil_div(a.rows, 128), (unsigned)ceil_div(a.c_out, BN));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = ceil_div(a.rows, 128) * ceil_div(a.c_out, BN);
+  const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)sms * (BN == 64 ? 2 : 1));   // persistent: one CTA per resident slot
   rowgemm_tf32_kernel<BN, TH><<<grid, TH, smem, s>>>(a);
   TIK_LAUNCH_CHECK();
   return TIK_OK;
