@@ -108,3 +108,55 @@ def test_tf32_long_k_accumulation_does_not_drift():
     out = ops.rowgemm([(a, 1, 0)], w, b, 1, 1, rows)
     want = a[0].double() @ w.double().t()
     assert float(((out[0].double() - want).abs() / want.abs()).max()) < 2e-6
+
+
+def test_tf32_rowgemm_random_shapes():
+    """Seeded sweep over ragged shapes: row counts that are not multiples of 128, output widths that are not multiples of
+    64 / 4, one to four slabs with strides 1..3 and tap offsets, K from 32 to 544 -- each against fp64 with a guard region."""
+    import random
+    from temporal_inverse_kinematics_b200 import ops
+    rnd = random.Random(1234)
+    for case in range(24):
+        n = rnd.choice([1, 2, 3, 9])
+        v = rnd.choice([1, 5, 17])
+        nv = n * v
+        t_out = rnd.choice([1, 3, 8, 31, 64])
+        t_mul = rnd.choice([1, 1, 2, 3])
+        n_slabs = rnd.choice([1, 1, 2, 3, 4])
+        c_out = rnd.choice([4, 40, 64, 72, 100, 128, 132, 256, 260])
+        slabs = []
+        g = torch.Generator().manual_seed(case)
+        for _ in range(n_slabs):
+            c = 32 * rnd.choice([1, 1, 2, 3, 4, 5])
+            t_in = t_out * t_mul + rnd.choice([0, 1, 2])
+            slabs.append((torch.randn(nv, t_in, c, generator=g), t_mul, rnd.choice([-2, -1, 0, 0, 1, 2])))
+        ktot = sum(a.shape[2] for a, _, _ in slabs)
+        w = torch.randn(c_out, ktot, generator=g) / ktot ** 0.5
+        per_node = rnd.random() < 0.5
+        bias = torch.randn(v if per_node else 1, c_out, generator=g)
+        res = torch.randn(nv, t_out, c_out, generator=g) if rnd.random() < 0.5 else None
+        act = rnd.choice(["none", "relu", "leaky"])
+        acc = torch.zeros(nv, t_out, c_out, dtype=torch.float64)
+        koff = 0
+        for a, m, o in slabs:
+            ts = torch.arange(t_out) * m + o
+            ok = (ts >= 0) & (ts < a.shape[1])
+            rows = torch.zeros(nv, t_out, a.shape[2], dtype=torch.float64)
+            rows[:, ok] = a.double()[:, ts[ok]]
+            acc += rows @ w.double()[:, koff:koff + a.shape[2]].t()
+            koff += a.shape[2]
+        acc += bias.double()[torch.arange(nv) % v][:, None, :] if per_node else bias.double()[0]
+        if res is not None:
+            acc += res.double()
+        if act == "relu":
+            acc = acc.clamp_min(0)
+        elif act == "leaky":
+            acc = torch.where(acc > 0, acc, acc * 0.01)
+        guard = torch.full((nv + 2, t_out, c_out), 4242.0, device="cuda")
+        out = guard[1:-1]
+        ops.rowgemm([(a.cuda(), m, o) for a, m, o in slabs], w.cuda(), bias.cuda(), nv, v, t_out, act=act, slope=0.01,
+                    residual=None if res is None else res.cuda(), out=out)
+        torch.cuda.synchronize()
+        assert bool((guard[0] == 4242.0).all()) and bool((guard[-1] == 4242.0).all()), case
+        err = float((out.cpu().double() - acc).abs().max() / acc.abs().max())
+        assert err < 3e-6, (case, err, nv, t_out, c_out, ktot)
