@@ -69,6 +69,8 @@ struct Step {
   bool out_is_poses = false;  // GEMM: writes the caller's poses pointer
   bool agg_only = false;      // FUSED_GCN used as a pure aggregation pass (identity weights): counts as 'aggregate'
   int k_identity = 0;         // GEMM: K columns that only carry an identity residual (not algorithmic FLOPs)
+  const float* w_big = nullptr;   // fp32 GEMM: the weights split into their TF32 parts once per plan (rowgemm_tf32.cu)
+  const float* w_small = nullptr;
 };
 
 }  // namespace tik
@@ -98,7 +100,7 @@ struct TikPlan {
 namespace tik {
 
 struct WsLayout {
-  int64_t off_x0, off_x1, off_agg, off_h, off_r0, off_feat, off_z, off_abd, off_w16, off_eye, off_zbias, total_bytes;
+  int64_t off_x0, off_x1, off_agg, off_h, off_r0, off_feat, off_z, off_abd, off_w16, off_eye, off_zbias, off_wsplit, total_bytes;
 };
 
 static int check_net(const TikNet* net, int dtype) {
@@ -162,6 +164,17 @@ static void ws_layout(const TikNet* net, int dtype, int64_t n, int64_t n_max, in
   L->off_w16 = off; off = align_up(off + stem_block_workspace_bytes(), 1024);
   L->off_eye = off; off = align_up(off + 128 * 128 * 2, 1024);               // identity weights: aggregation-only passes
   L->off_zbias = off; off = align_up(off + 32 * 128 * 4, 1024);             // zero bias table (V <= 32 rows)
+  L->off_wsplit = off;                                                       // fp32 plans: every GEMM's weights as TF32 big / small parts
+  if (dtype == TIK_F32) {
+    int64_t w_elems = 0;
+    for (int i = 0; i < net->n_blocks; ++i) {          // only the 64-column GEMMs read pre-split weights (rowgemm_tf32.cu)
+      const TikBlock& b = net->blocks[i];
+      if (b.c_out <= 64) w_elems += align_up((int64_t)b.c_out * net->K * b.c_in, 256) + align_up((int64_t)b.c_out * (b.kt * b.c_out + b.c_in), 256);
+    }
+    if (net->head_hidden > 0 && net->head_hidden <= 64) w_elems += align_up((int64_t)net->head_hidden * V * net->blocks[net->n_blocks - 1].c_out, 256);
+    if (net->head_hidden > 0 && net->head_out <= 64) w_elems += align_up((int64_t)net->head_out * net->head_hidden, 256);
+    off = align_up(off + 2 * w_elems * 4, 1024);
+  }
   L->total_bytes = off;
 }
 
@@ -191,7 +204,7 @@ static int run_step(TikPlan* P, Step& st, const float* xc, int64_t n, int64_t cl
   }
   if (st.out_is_feat) g.out_dev = P->feat + clip_off * P->feat_elems_per_clip * (int64_t)P->es;
   if (st.out_is_poses) g.out_dev = poses;
-  return P->dtype == TIK_BF16 ? umma_launch(st.prep, &g, s) : rowgemm_f32(&g, s);
+  return P->dtype == TIK_BF16 ? umma_launch(st.prep, &g, s) : rowgemm_f32_presplit(&g, st.w_big, st.w_small, s);
 }
 
 static int run_impl(TikPlan* P, const float* x, int64_t N, float* poses, void* feat_out, cudaStream_t s,
@@ -460,6 +473,24 @@ int tik_stgcn_plan_create(const TikNet* net, int dtype, int64_t n_chunk, int64_t
         int rc2 = umma_prepare(&g, g.nv, &s.prep);
         if (rc2 != TIK_OK) { delete P; return rc2; }
       }
+  }
+  if (dtype == TIK_F32 && !getenv("TIK_NO_TF32_PRESPLIT")) {
+    // weights are constants of the plan (a weight update re-creates it): split them into TF32 parts once
+    float* wsp = reinterpret_cast<float*>(ws + L.off_wsplit);
+    for (auto* v : {&P->chunk_steps, &P->batch_steps})
+      for (auto& s : *v) {
+        if (s.kind != Step::GEMM || s.g.c_out > 64) continue;   // only the 64-column kernel reads pre-split weights (rowgemm_tf32.cu)
+        int64_t ktot = 0;
+        for (int k = 0; k < s.g.n_slabs; ++k) ktot += s.g.slabs[k].c;
+        const int64_t n = align_up((int64_t)s.g.c_out * ktot, 256);
+        if ((reinterpret_cast<uint8_t*>(wsp + 2 * n) - ws) > L.total_bytes) break;      // ws_layout's bound covers every GEMM; never overrun
+        int rc3 = tf32_split_weights(reinterpret_cast<const float*>(s.g.w_dev), wsp, wsp + n, (int64_t)s.g.c_out * ktot, 0);
+        if (rc3 != TIK_OK) { delete P; return rc3; }
+        s.w_big = wsp; s.w_small = wsp + n;
+        wsp += 2 * n;
+      }
+    cudaError_t ce = cudaStreamSynchronize(0);
+    if (ce != cudaSuccess) { set_error("plan: weight split failed: %s", cudaGetErrorString(ce)); delete P; return TIK_ERR_CUDA; }
   }
   *plan_out = P;
   return TIK_OK;

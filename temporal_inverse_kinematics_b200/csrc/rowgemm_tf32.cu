@@ -92,23 +92,37 @@ __device__ __forceinline__ void split_store(uint8_t* big, uint8_t* small, uint32
 // drops from 114 to 84 TFLOP/s.
 // BN = 128: 512 threads, one CTA per SM.  BN = 64 (the 64-channel layers: 2-6 chunks per tile, where the per-tile prologue
 // and epilogue weigh most): 256 threads and half the shared memory, two CTAs per SM overlap each other's fixed costs.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ int fast_div(int n, unsigned long long magic, int shift) {
   return (int)(((unsigned long long)(unsigned)n * magic) >> shift);
 }
 
-template <int BN, int kTfThreads>
+template <int BN, int kTfThreads, bool kPre>
 __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_kernel(const __grid_constant__ F32Args p) {
   constexpr int WT = BN * 128;                       // bytes of one weight tile (BN rows x 128 B)
   constexpr int STAGE = 2 * kTfATile + 2 * WT;       // [A_big | A_small | W_big | W_small]
+  // kPre (BN = 64 only; weights pre-split by the plan): W_big / W_small of a chunk go global -> shared memory with cp.async,
+  // no registers and no split arithmetic: -10 % on the 64-column layers, where two CTAs per SM cover the copy latency.  At
+  // BN = 128 (one CTA per SM) the same scheme measured SLOWER than splitting in the kernel -- copy started when the stage is
+  // free: +15..40 %; with a third weight buffer and the copy one chunk ahead: still +7..10 % -- so those layers keep the
+  // register path (profiles/r2_notes.md).
+  static_assert(!kPre || BN == 64, "pre-split weights are used by the 64-column kernel only");
+  constexpr int NWB = 2;                             // weight buffers = the stages' own W slots
+  constexpr int WDIST = 0;                           // chunks the weight copy runs ahead
+  constexpr int OPER_BYTES = 2 * STAGE + (NWB - 2) * 2 * WT;
   constexpr int NQA = 128 * 8 / kTfThreads;          // float4 pieces of A per thread and chunk
   constexpr int NQW = BN * 8 / kTfThreads;           // float4 pieces of W per thread and chunk
   constexpr int NACC = 128 * BN / kTfThreads;        // fp32 accumulators per thread (one tile row x a quarter of the columns)
   constexpr int OUT_PITCH = BN * 4 + 16;             // staging row pitch (bytes): float4 writes of 8 consecutive rows hit 32 different banks
-  static_assert(128 * OUT_PITCH <= 2 * STAGE, "the output staging tile aliases the operand stages");
+  static_assert(128 * OUT_PITCH <= OPER_BYTES, "the output staging tile aliases the operand buffers");
   static_assert(NACC == 16 || NACC == 32, "drain uses one tcgen05.ld of 16 or 32 columns");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);   // [2]
+  uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem + OPER_BYTES);   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows = (int)p.rows;
@@ -142,7 +156,30 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
 
   // Global loads run TWO chunks ahead of the split (register double buffer): one chunk of distance left the L2 latency
   // exposed in every iteration (2850 cycles per chunk at K = 4352 against 12 x 64 cycles of MMAs).
-  float4 ra[2][NQA], rw[2][NQW];
+  float4 ra[2][NQA], rw[2][kPre ? 1 : NQW];
+  const int64_t w_small_delta = kPre ? p.w_small - p.w_big : 0;
+  // kPre: weight buffer of (tile-relative) chunk c: the two stages' W slots, then the extra buffer
+  auto w_buf = [&](int c) -> uint8_t* {
+    const int b = c % NWB;
+    return b < 2 ? smem + (size_t)b * STAGE + 2 * kTfATile : smem + 2 * STAGE + (size_t)(b - 2) * 2 * WT;
+  };
+  auto copy_w = [&](int c) {                         // cp.async of chunk c's W_big / W_small (one group per call, empty past the end)
+    if (c < n_chunks) {
+      uint8_t* wb = w_buf(c);
+      const int wk = c * kTfKc;                      // the slabs are concatenated along K in order
+#pragma unroll
+      for (int q = 0; q < NQW; ++q) {
+        if (w_ptr[q] != nullptr) {
+          cp_async16(wb + w_off[q], w_ptr[q] + wk);
+          cp_async16(wb + WT + w_off[q], w_ptr[q] + w_small_delta + wk);
+        } else {
+          *reinterpret_cast<float4*>(wb + w_off[q]) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(wb + WT + w_off[q]) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+    cp_async_commit();
+  };
   int ls = 0, lk0 = 0, loaded = 0;                   // cursor of the next chunk to load
   uint32_t a_src[NQA];                               // this thread's rows in the cursor's slab as element offsets (~0: padding frame / row past the end)
   auto issue_loads = [&](auto PB) {
@@ -160,9 +197,11 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
 #pragma unroll
     for (int q = 0; q < NQA; ++q)
       ra[pb][q] = a_src[q] != 0xFFFFFFFFu ? __ldg(reinterpret_cast<const float4*>(sl.a + a_src[q] + lk0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!kPre) {
 #pragma unroll
-    for (int q = 0; q < NQW; ++q)
-      rw[pb][q] = w_ptr[q] ? __ldg(reinterpret_cast<const float4*>(w_ptr[q] + sl.koff + lk0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < NQW; ++q)
+        rw[pb][q] = w_ptr[q] ? __ldg(reinterpret_cast<const float4*>(w_ptr[q] + sl.koff + lk0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     ++loaded;
     lk0 += kTfKc;
     if (lk0 >= sl.c) { ++ls; lk0 = 0; }
@@ -184,7 +223,7 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
 #pragma unroll
     for (int q = 0; q < NQW; ++q) {
       const int col = col0 + ((q * kTfThreads + tid) >> 3);
-      w_ptr[q] = col < p.c_out ? p.w + (int64_t)col * p.ktot + a_k : nullptr;
+      w_ptr[q] = col < p.c_out ? (kPre ? p.w_big : p.w) + (int64_t)col * p.ktot + a_k : nullptr;
     }
     ls = 0; lk0 = 0; loaded = 0;
     issue_loads(std::integral_constant<int, 0>{});
@@ -222,16 +261,22 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
       tc_fence_after();
       if ((ch - 2) % kTfBlock == kTfBlock - 1) { drain(drained); ++drained; }   // ... and if it closed a block, so is that block's sum
     }
+    if (kPre) copy_w(ch + WDIST);                            // its buffer was last read by the MMAs of chunk ch + WDIST - NWB <= ch - 2: finished
 #pragma unroll
     for (int q = 0; q < NQA; ++q) split_store(sa_big, sa_small, a_off[q], ra[pb][q]);
+    if (kPre) {
+      cp_async_wait<WDIST>();                                // chunk ch's weights have landed (the newest WDIST groups may still fly)
+    } else {
 #pragma unroll
-    for (int q = 0; q < NQW; ++q) split_store(sw_big, sw_small, w_off[q], rw[pb][q]);
+      for (int q = 0; q < NQW; ++q) split_store(sw_big, sw_small, w_off[q], rw[pb][q]);
+    }
     issue_loads(PB);                                         // chunk ch + 2 into the registers just consumed
     fence_proxy_async_smem();                                // generic-proxy stores -> visible to the MMA's async-proxy reads
     __syncthreads();
     if (warp == 0) {                                         // warp-uniform: the election is inside the asm (no uniformisation loop per MMA)
       tc_fence_after();
-      const uint32_t ab = smem_base + (uint32_t)(st * STAGE), as = ab + kTfATile, wb = as + kTfATile, ws = wb + WT;
+      const uint32_t ab = smem_base + (uint32_t)(st * STAGE), as = ab + kTfATile;
+      const uint32_t wb = kPre ? smem_u32(w_buf(ch)) : as + kTfATile, ws = wb + WT;
       const uint32_t d = tmem_acc + (uint32_t)(((gblk0 + ch / kTfBlock) & 1) * BN);
       const bool fresh = ch % kTfBlock == 0;                 // first chunk of a block overwrites the accumulator
 #pragma unroll
@@ -250,6 +295,10 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
 #pragma unroll
   for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
   drained = 0;
+  if (kPre) {
+#pragma unroll
+    for (int c = 0; c < WDIST; ++c) copy_w(c);               // the copies that run ahead of the first chunk
+  }
   for (int ch = 0; ch < n_chunks; ch += 2) {
     body(ch, std::integral_constant<int, 0>{});
     if (ch + 1 < n_chunks) body(ch + 1, std::integral_constant<int, 1>{});
@@ -371,6 +420,21 @@ __global__ void __launch_bounds__(kTfThreads, BN == 64 ? 2 : 1) rowgemm_tf32_ker
   }
 }
 
+__global__ void tf32_split_kernel(const float* __restrict__ w, float* __restrict__ big, float* __restrict__ small, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = w[i], b = tf32_big(v);
+    big[i] = b;
+    small[i] = v - b;
+  }
+}
+
+int tf32_split_weights(const float* w, float* big, float* small, int64_t n, cudaStream_t s) {
+  if (n <= 0) return TIK_OK;
+  tf32_split_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, s>>>(w, big, small, n);
+  TIK_LAUNCH_CHECK();
+  return TIK_OK;
+}
+
 bool rowgemm_tf32_supported(const F32Args& a) {
   // On by default for the fp32 path; TIK_NO_TF32=1 forces the SIMT kernel (read per call: A/B inside one process).
   if (getenv("TIK_NO_TF32")) return false;
@@ -380,25 +444,26 @@ bool rowgemm_tf32_supported(const F32Args& a) {
   for (int i = 0; i < a.n_slabs; ++i)
     if (a.slabs[i].c % kTfKc != 0 || (reinterpret_cast<uintptr_t>(a.slabs[i].a) & 15) != 0) return false;
   if ((reinterpret_cast<uintptr_t>(a.w) & 15) != 0) return false;
+  if (a.w_big && ((reinterpret_cast<uintptr_t>(a.w_big) | reinterpret_cast<uintptr_t>(a.w_small)) & 15) != 0) return false;
   if (a.out_layout != TIK_OUT_ROWS_F32 && a.c_out % 4 != 0) return false;
   return true;
 }
 
-template <int BN, int TH>
+template <int BN, int TH, bool kPre>
 static int launch_tf32(const F32Args& a, cudaStream_t s) {
   constexpr int smem = 2 * (2 * kTfATile + 2 * BN * 128) + 64 + 1024;
   static bool attr_done[64] = {};
   int dev = 0;
   TIK_CUDA(cudaGetDevice(&dev));
   if (!attr_done[dev & 63]) {
-    TIK_CUDA(cudaFuncSetAttribute(rowgemm_tf32_kernel<BN, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TIK_CUDA(cudaFuncSetAttribute(rowgemm_tf32_kernel<BN, TH, kPre>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done[dev & 63] = true;
   }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = ceil_div(a.rows, 128) * ceil_div(a.c_out, BN);
   const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)sms * (BN == 64 ? 2 : 1));   // persistent: one CTA per resident slot
-  rowgemm_tf32_kernel<BN, TH><<<grid, TH, smem, s>>>(a);
+  rowgemm_tf32_kernel<BN, TH, kPre><<<grid, TH, smem, s>>>(a);
   TIK_LAUNCH_CHECK();
   return TIK_OK;
 }
@@ -414,7 +479,8 @@ int rowgemm_tf32_launch(const F32Args& a0, cudaStream_t s) {
   F32Args a = a0;
   make_div(a.t_out, &a.div_t_magic, &a.div_t_shift);
   make_div(a.v, &a.div_v_magic, &a.div_v_shift);
-  return a.c_out > 64 ? launch_tf32<128, 512>(a, s) : launch_tf32<64, 256>(a, s);
+  if (a.c_out > 64) return launch_tf32<128, 512, false>(a, s);
+  return a.w_big != nullptr ? launch_tf32<64, 256, true>(a, s) : launch_tf32<64, 256, false>(a, s);
 }
 
 }  // namespace tik

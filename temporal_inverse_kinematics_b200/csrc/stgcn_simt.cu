@@ -219,8 +219,11 @@ __global__ void __launch_bounds__(GT, 3) rowgemm_f32_kernel(const __grid_constan
   }
 }
 
-int rowgemm_f32(const TikRowGemm* d, cudaStream_t s) {
+int rowgemm_f32(const TikRowGemm* d, cudaStream_t s) { return rowgemm_f32_presplit(d, nullptr, nullptr, s); }
+
+int rowgemm_f32_presplit(const TikRowGemm* d, const float* w_big, const float* w_small, cudaStream_t s) {
   F32Args a;
+  a.w_big = w_big; a.w_small = w_small;
   int koff = 0;
   for (int i = 0; i < d->n_slabs; ++i) {
     const TikSlab& sl = d->slabs[i];

@@ -86,12 +86,17 @@ struct F32Args {
   float* out; int out_layout;
   // n / t_out and n / v for n < 2^31 as (n * magic) >> shift (rowgemm_tf32.cu: ~100 integer divisions per tile row otherwise)
   unsigned long long div_t_magic, div_v_magic; int div_t_shift, div_v_shift;
+  // optional: the weights already split into their TF32 parts (tf32_split_weights; the plan does it once per weight
+  // version in its workspace), both (c_out, ktot) like w.  nullptr: the kernel splits W on the way, like the activations.
+  const float* w_big; const float* w_small;
 };
 bool rowgemm_tf32_supported(const F32Args& a);
 int rowgemm_tf32_launch(const F32Args& a, cudaStream_t s);
 
 // internal entry points shared between translation units
 int rowgemm_f32(const TikRowGemm* d, cudaStream_t s);
+int rowgemm_f32_presplit(const TikRowGemm* d, const float* w_big, const float* w_small, cudaStream_t s);
+int tf32_split_weights(const float* w, float* big, float* small, int64_t n, cudaStream_t s);
 int rowgemm_bf16(const TikRowGemm* d, cudaStream_t s);
 int launch_batch_rodrigues(const float* aa, float* R9, int64_t M, cudaStream_t s);
 int stem_gcn_impl(int dtype, const float* x, const float* in_scale, const float* in_shift, const float* agg,
